@@ -1,0 +1,215 @@
+/*
+ * plenoxel_abi.h — C ABI of libplenoxel_b200.so (sm_100a CUDA kernels for the voxel-grid volume renderer).
+ *
+ * The reference (DanJbk/Plenoxels) has no FFI: its boundary is a set of Python free functions on torch
+ * tensors.  Each entry point below names the reference function(s) it stands under
+ * (`file:line` in the reference tree); `plenoxels_b200/*.py` binds them with ctypes and keeps the
+ * reference's Python signatures on top (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller unless the name ends in `_host`.
+ *   - Nothing allocates, synchronises or keeps global state; every call is asynchronous on `stream`
+ *     (a `cudaStream_t` passed as `void*`; NULL = the legacy default stream).
+ *   - Return value: 0 on success, a negative PLX_E_* code for an argument error, or a positive
+ *     `cudaError_t` if a launch failed.  `plx_last_error()` returns a thread-local message.  Nothing throws.
+ *   - All floating-point data is fp32; cells are 4 floats (R, G, B, opacity) — src/grid_functions.py:214.
+ *   - Index arithmetic is IEEE fp32 with every operation rounded separately (no FMA contraction, true
+ *     division, round-half-even), so voxel indices match the reference's CPU path bit for bit
+ *     (SURVEY.md §7 H2, Appendix A1-A5).
+ */
+#ifndef PLENOXEL_ABI_H_
+#define PLENOXEL_ABI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLX_ABI_VERSION 1
+
+/* error codes */
+#define PLX_OK 0
+#define PLX_E_NULL (-1)        /* a required pointer is NULL */
+#define PLX_E_SHAPE (-2)       /* a size / stride is invalid */
+#define PLX_E_UNSUPPORTED (-3) /* valid request the library does not implement */
+#define PLX_E_ALIGN (-4)       /* pointer not aligned for the vector path */
+
+/* lookup mode */
+#define PLX_NEAREST 0   /* get_nearest_voxels, src/grid_functions.py:103-114 */
+#define PLX_TRILINEAR 1 /* get_grid_points_indices + trilinear_interpolation, src/grid_functions.py:220-246, :7-44 */
+
+/* flags of PlxMarch.flags */
+#define PLX_CLAMP01 1u        /* look the grid up through clip(0,1) (scripts/train.py:146); backward applies the pass-mask */
+#define PLX_NO_CLIP 2u        /* visit every sample k = 1..S (disable the conservative ray/box pre-filter) */
+#define PLX_NO_EARLY_STOP 4u  /* keep marching after the transmittance reached exactly 0 */
+
+/* Ray-marching geometry shared by the fused kernels. */
+typedef struct PlxMarch {
+    int32_t nx, ny, nz;       /* grid cells per axis (X, Y, Z) */
+    int32_t num_samples;      /* S samples per ray, k = 1..S (src/ray_sampling.py:161) */
+    int64_t sx, sy, sz, sc;   /* element strides of the (X,Y,Z,4) grid tensor (pooled grids are channel-planar) */
+    float gmin[3];            /* world coordinate of cell (0,0,0) = grid_indices.min(0)[0] (src/ray_sampling.py:13) */
+    float points_distance;    /* fp32(pd), the divisor of src/ray_sampling.py:13 */
+    float delta_step;         /* fp32(delta), t_k = fl(delta * k) */
+    int32_t mode;             /* PLX_NEAREST | PLX_TRILINEAR */
+    uint32_t flags;           /* PLX_CLAMP01 | PLX_NO_CLIP | PLX_NO_EARLY_STOP */
+} PlxMarch;
+
+/* Rays: component a of the origin of ray r is origins[(r / rays_per_origin) * origin_stride + a * origin_comp_stride],
+ * i.e. one origin per camera exactly as `camera_positions` is repeated in src/ray_sampling.py:164.  A packed (C,3) tensor
+ * has strides (3,1); the view `transform_matrices[:, :3, 3]` of src/ray_sampling.py:159 has (16,4) and is read in place.
+ * Pass rays_per_origin = 1 for per-ray origins. */
+typedef struct PlxRays {
+    const float* origins;
+    const float* dirs;        /* (n_rays, 3) contiguous */
+    int64_t n_rays;
+    int64_t rays_per_origin;
+    int64_t origin_stride;
+    int64_t origin_comp_stride;
+} PlxRays;
+
+int plx_version(void);
+const char* plx_last_error(void);
+
+/* Number of 32-sample chunks the fused kernels use per ray; `tcarry` buffers are (n_rays, plx_num_chunks(S)) fp32. */
+int32_t plx_num_chunks(int32_t num_samples);
+
+/*
+ * K1 — fused forward: sample placement + normalisation + lookup + mask + compositing, one warp per ray.
+ * Stands under the sequence scripts/train.py:130-151 / src/visualization.py:125-146:
+ *   sample_camera_rays_batched (src/ray_sampling.py:161-167), normalize_samples_for_indecies (:13),
+ *   get_nearest_voxels on grid.clip(0,1) (src/grid_functions.py:103-114) * mask, compute_alpha_weighted_pixels (:172-192).
+ * Outputs (any of depth/count/sample_index/tcarry may be NULL):
+ *   rgba (n_rays,4); depth (n_rays) = sum_k w_k t_k; count (n_rays) int32 = in-bounds samples of the ray;
+ *   sample_index (n_rays,S) int32 linear cell index nx-major ((ix*ny+iy)*nz+iz) or -1 when out of bounds
+ *   (debug/parity dump; forces PLX_NO_CLIP | PLX_NO_EARLY_STOP); tcarry (n_rays, plx_num_chunks(S)) transmittance at
+ *   the start of each 32-sample chunk of the clipped range, consumed by plx_render_bwd.
+ * Optional MSE epilogue (scripts/train.py:156): if `targets` != NULL, also writes
+ *   grad_rgba = (rgba - targets) * grad_scale   and atomically adds  sum((rgba-targets)^2) * loss_scale  to loss[0].
+ */
+typedef struct PlxRenderFwd {
+    PlxMarch march;
+    PlxRays rays;
+    const float* grid;
+    float* rgba;
+    float* depth;
+    int32_t* count;
+    int32_t* sample_index;
+    float* tcarry;
+    const float* targets;   /* (n_rays,4) or NULL */
+    float* grad_rgba;       /* (n_rays,4), required when targets != NULL */
+    float* loss;            /* 1 float accumulator (caller zeroes it), or NULL */
+    float grad_scale;       /* 2 / (4 * N_global) for mean-MSE */
+    float loss_scale;       /* 1 / (4 * N_global) */
+} PlxRenderFwd;
+int plx_render_fwd(const PlxRenderFwd* args, void* stream);
+
+/*
+ * K2 — fused backward: recomputes the march, runs the division-free reverse recurrence
+ *   d alpha_k = T_k (v_k - S_k),  S_k = alpha_{k+1} v_{k+1} + (1 - alpha_{k+1}) S_{k+1},  d c_k = alpha_k T_k g_rgb
+ * and scatter-ADDS into grad_grid (contiguous (X,Y,Z,4)) with warp-aggregated 16-byte vector reductions,
+ * gated per channel by the clip pass-mask 0 <= raw <= 1 when PLX_CLAMP01 is set.
+ * This is the autograd of scripts/train.py:146-151 triggered at :181 (cumprod/index/clamp backward, index_put accumulate).
+ * `beta` adds the sparsity-loss term of scripts/train.py:170-177 with weight beta_over_m = beta / M_global (0 = off).
+ * `tcarry` may be NULL (the kernel then recomputes the chunk transmittances in a first pass).
+ */
+typedef struct PlxRenderBwd {
+    PlxMarch march;
+    PlxRays rays;
+    const float* grid;
+    const float* grad_rgba;   /* (n_rays,4) */
+    const float* tcarry;      /* from plx_render_fwd, or NULL */
+    float* grad_grid;         /* (nx,ny,nz,4) contiguous, accumulated into */
+    float beta_over_m;
+} PlxRenderBwd;
+int plx_render_bwd(const PlxRenderBwd* args, void* stream);
+
+/*
+ * K3 — optimiser: one torch.optim.Adam step over n fp32 values (torch/optim/adam.py `_single_tensor_adam`, as used
+ * at scripts/train.py:89,:180-182) fused with `grid_grad += |grad|` (:184) and, with zero_grad != 0, clearing `g` for
+ * the next step (:180).  Scalars are formed in double like the Python code (bias corrections 1 - beta^step).
+ * `gabs` may be NULL.  `step` counts from 1.
+ */
+int plx_adam_step(float* p, float* g, float* m, float* v, float* gabs, int64_t n, double lr, double beta1, double beta2,
+                  double eps, int64_t step, int32_t zero_grad, void* stream);
+
+/*
+ * Ray generation — generate_rays_batched, src/ray_sampling.py:195-264.
+ * imgs (C,H,W,4); poses (C,4,4) row-major camera-to-world; uv (C,R,2) in [0,1] (the `torch.rand` draw of :227) or NULL
+ * for the even-spread lattice of :220-223 with R = n_side^2 rays (u-major, linspace(0,1,n_side)).
+ * Writes dirs (C*R,3) and, when imgs/targets are non-NULL, targets (C*R,4) = imgs[cam, v_pix, u_pix] (:238-248).
+ */
+int plx_generate_rays(const float* imgs, int32_t n_cams, int32_t img_h, int32_t img_w, const float* poses, float fov,
+                      const float* uv, int32_t rays_per_cam, int32_t n_side, float* dirs, float* targets, void* stream);
+
+/* Eager per-function kernels (reference semantics, materialised tensors) ------------------------------------------- */
+
+/* samples (n_rays*S,3) = o + d * (delta*k) — sample_camera_rays_batched, src/ray_sampling.py:161-167 */
+int plx_sample_points(const PlxRays* rays, int32_t num_samples, float delta_step, float* samples, void* stream);
+
+/* out (M,3) = (samples - gmin) / pd — normalize_samples_for_indecies, src/ray_sampling.py:12-13 */
+int plx_normalize_points(const float* samples, int64_t m, const float gmin[3], float points_distance, float* out,
+                         void* stream);
+
+/* get_nearest_voxels, src/grid_functions.py:103-114: vals (M,4) at periodically wrapped indices (unmasked),
+ * inbounds (M) uint8; idx_out (M,3) int64 wrapped indices or NULL.  Grid given with explicit strides. */
+int plx_gather_nearest(const float* ns, int64_t m, const float* grid, const int32_t dims[3], const int64_t strides[4],
+                       float* vals, uint8_t* inbounds, int64_t* idx_out, void* stream);
+/* its autograd: grad_grid[(wrapped idx)] += grad_vals, grad_grid contiguous (X,Y,Z,4) */
+int plx_gather_nearest_bwd(const float* ns, int64_t m, const float* grad_vals, const int32_t dims[3], float* grad_grid,
+                           void* stream);
+
+/* trilinear lookup: corners of get_grid_points_indices (src/grid_functions.py:220-246) wrapped periodically (:66-79),
+ * interpolated as trilinear_interpolation (:7-44).  `masked` != 0 multiplies by the float in-bounds test. */
+int plx_trilinear_fwd(const float* ns, int64_t m, const float* grid, const int32_t dims[3], const int64_t strides[4],
+                      int32_t masked, float* vals, uint8_t* inbounds, void* stream);
+int plx_trilinear_bwd(const float* ns, int64_t m, const float* grad_vals, const int32_t dims[3], int32_t masked,
+                      float* grad_grid, void* stream);
+
+/* compute_alpha_weighted_pixels, src/ray_sampling.py:172-192: samples (n_rays,S,4) -> out (n_rays,4) */
+int plx_composite_fwd(const float* samples, int64_t n_rays, int32_t num_samples, float* out, void* stream);
+/* its autograd: grad_samples (n_rays,S,4) from grad_out (n_rays,4) */
+int plx_composite_bwd(const float* samples, int64_t n_rays, int32_t num_samples, const float* grad_out,
+                      float* grad_samples, void* stream);
+
+/*
+ * One whole training step of scripts/train.py:130-184 (tv = 0) in a single host call:
+ *   plx_generate_rays -> plx_render_fwd (+MSE epilogue) -> plx_render_bwd -> [caller's collective] -> plx_adam_step.
+ * `phase` selects which part runs so a multi-GPU caller can put the gradient all-reduce between the two halves:
+ *   PLX_STEP_RENDER = rays + forward + loss + backward;  PLX_STEP_OPTIM = Adam;  PLX_STEP_ALL = both.
+ * Scratch (dirs, targets, rgba, grad_rgba, tcarry) is caller-provided.  loss[0] is zeroed by the call.
+ */
+#define PLX_STEP_RENDER 1
+#define PLX_STEP_OPTIM 2
+#define PLX_STEP_ALL 3
+typedef struct PlxTrainStep {
+    PlxMarch march;
+    /* scene, resident on the device */
+    const float* imgs; int32_t n_cams, img_h, img_w;
+    const float* poses; float fov;
+    /* this step's rays */
+    const float* uv; int32_t rays_per_cam;
+    int64_t n_rays_global;    /* N over all ranks: mean-MSE scale 1/(4*N_global) so a plain SUM of grads is exact */
+    /* state */
+    float* grid; float* grad; float* exp_avg; float* exp_avg_sq; float* grad_abs_sum;
+    double lr, beta1, beta2, eps; int64_t step;
+    float beta_over_m;
+    /* scratch */
+    float* dirs; float* targets; float* rgba; float* grad_rgba; float* tcarry;
+    /* result */
+    float* loss;
+} PlxTrainStep;
+int plx_train_step(const PlxTrainStep* args, int32_t phase, void* stream);
+
+/*
+ * The same step driven from HOST buffers (the end-to-end path): copies this step's `uv_host` (pinned, C*R*2 floats)
+ * to args->uv on `stream`, runs the phases, and copies loss[0] back to `loss_host` (pinned).  Asynchronous; the caller
+ * synchronises the stream before reading `loss_host`.
+ */
+int plx_train_step_host(const PlxTrainStep* args, const float* uv_host, float* loss_host, int32_t phase, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLENOXEL_ABI_H_ */

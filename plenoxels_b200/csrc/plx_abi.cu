@@ -1,0 +1,256 @@
+// plx_abi.cu — the extern "C" boundary of libplenoxel_b200.so (include/plenoxel_abi.h): argument validation, error
+// strings, and the single-call training-step driver.  No torch types, no allocation, no synchronisation.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+
+#include "plx_device.cuh"
+#include "plx_launch.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_result(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return PLX_OK;
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return (int)e;
+}
+
+int check_march(const PlxMarch& m, const float* grid) {
+    if (!grid) return fail(PLX_E_NULL, "grid is NULL");
+    if (m.nx <= 0 || m.ny <= 0 || m.nz <= 0) return fail(PLX_E_SHAPE, "grid dims must be positive (%d,%d,%d)", m.nx, m.ny, m.nz);
+    if ((int64_t)m.nx * m.ny * m.nz > 0x7fffffffLL / 4) return fail(PLX_E_SHAPE, "grid too large for 32-bit cell indices");
+    if (m.num_samples < 0) return fail(PLX_E_SHAPE, "num_samples < 0");
+    if (m.mode != PLX_NEAREST && m.mode != PLX_TRILINEAR) return fail(PLX_E_UNSUPPORTED, "unknown lookup mode %d", m.mode);
+    if (!(m.points_distance == m.points_distance) || m.points_distance == 0.f)
+        return fail(PLX_E_SHAPE, "points_distance must be a non-zero number");
+    return PLX_OK;
+}
+
+int check_rays(const PlxRays& r) {
+    if (r.n_rays < 0) return fail(PLX_E_SHAPE, "n_rays < 0");
+    if (r.n_rays > 0 && (!r.origins || !r.dirs)) return fail(PLX_E_NULL, "ray origins/dirs are NULL");
+    if (r.rays_per_origin <= 0) return fail(PLX_E_SHAPE, "rays_per_origin must be >= 1");
+    if (r.origin_comp_stride == 0 && r.n_rays > 0) return fail(PLX_E_SHAPE, "origin_comp_stride must be non-zero");
+    return PLX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int plx_version(void) { return PLX_ABI_VERSION; }
+
+const char* plx_last_error(void) { return g_err; }
+
+int32_t plx_num_chunks(int32_t num_samples) { return plx::num_chunks(num_samples < 0 ? 0 : num_samples); }
+
+int plx_render_fwd(const PlxRenderFwd* a, void* stream) {
+    if (!a) return fail(PLX_E_NULL, "args is NULL");
+    int rc;
+    if ((rc = check_march(a->march, a->grid)) != PLX_OK) return rc;
+    if ((rc = check_rays(a->rays)) != PLX_OK) return rc;
+    if (a->rays.n_rays > 0 && !a->rgba) return fail(PLX_E_NULL, "rgba is NULL");
+    if ((uintptr_t)a->rgba % 16) return fail(PLX_E_ALIGN, "rgba must be 16-byte aligned");
+    if (a->targets) {
+        if (!a->grad_rgba) return fail(PLX_E_NULL, "grad_rgba is required with targets");
+        if ((uintptr_t)a->targets % 16 || (uintptr_t)a->grad_rgba % 16) return fail(PLX_E_ALIGN, "targets/grad_rgba must be 16-byte aligned");
+    }
+    return cuda_result(plx::launch_render_fwd(*a, (cudaStream_t)stream), "plx_render_fwd");
+}
+
+int plx_render_bwd(const PlxRenderBwd* a, void* stream) {
+    if (!a) return fail(PLX_E_NULL, "args is NULL");
+    int rc;
+    if ((rc = check_march(a->march, a->grid)) != PLX_OK) return rc;
+    if ((rc = check_rays(a->rays)) != PLX_OK) return rc;
+    if (a->rays.n_rays > 0 && (!a->grad_rgba || !a->grad_grid)) return fail(PLX_E_NULL, "grad_rgba/grad_grid is NULL");
+    if ((uintptr_t)a->grad_rgba % 16 || (uintptr_t)a->grad_grid % 16) return fail(PLX_E_ALIGN, "grad_rgba/grad_grid must be 16-byte aligned");
+    if (!a->tcarry && (size_t)plx::num_chunks(a->march.num_samples) * 8 * sizeof(float) > 200 * 1024)
+        return fail(PLX_E_UNSUPPORTED, "num_samples %d too large for the in-kernel transmittance cache; pass tcarry", a->march.num_samples);
+    return cuda_result(plx::launch_render_bwd(*a, (cudaStream_t)stream), "plx_render_bwd");
+}
+
+static plx::AdamScalars adam_scalars(double lr, double beta1, double beta2, double eps, int64_t step) {
+    // python-double scalar math of torch/optim/adam.py, cast to fp32 where ATen casts the Scalar
+    const double bc1 = 1.0 - std::pow(beta1, (double)step);
+    const double bc2 = 1.0 - std::pow(beta2, (double)step);
+    plx::AdamScalars s;
+    s.one_minus_beta1 = (float)(1.0 - beta1);
+    s.beta2 = (float)beta2;
+    s.one_minus_beta2 = (float)(1.0 - beta2);
+    s.bc2_sqrt = (float)std::sqrt(bc2);
+    s.eps = (float)eps;
+    s.neg_step_size = (float)(-(lr / bc1));
+    return s;
+}
+
+int plx_adam_step(float* p, float* g, float* m, float* v, float* gabs, int64_t n, double lr, double beta1, double beta2,
+                  double eps, int64_t step, int32_t zero_grad, void* stream) {
+    if (n < 0) return fail(PLX_E_SHAPE, "n < 0");
+    if (n > 0 && (!p || !g || !m || !v)) return fail(PLX_E_NULL, "p/g/m/v is NULL");
+    if (step < 1) return fail(PLX_E_SHAPE, "step counts from 1");
+    return cuda_result(plx::launch_adam(p, g, m, v, gabs, n, adam_scalars(lr, beta1, beta2, eps, step), zero_grad != 0,
+                                        (cudaStream_t)stream), "plx_adam_step");
+}
+
+int plx_generate_rays(const float* imgs, int32_t n_cams, int32_t img_h, int32_t img_w, const float* poses, float fov,
+                      const float* uv, int32_t rays_per_cam, int32_t n_side, float* dirs, float* targets, void* stream) {
+    if (n_cams < 0 || rays_per_cam < 0) return fail(PLX_E_SHAPE, "negative camera / ray count");
+    if (n_cams == 0 || rays_per_cam == 0) return PLX_OK;
+    if (!poses || !dirs) return fail(PLX_E_NULL, "poses/dirs is NULL");
+    if (!uv && (n_side <= 0 || n_side * n_side != rays_per_cam))
+        return fail(PLX_E_SHAPE, "even-spread lattice needs rays_per_cam == n_side^2 (got %d, n_side %d)", rays_per_cam, n_side);
+    if (targets) {
+        if (!imgs) return fail(PLX_E_NULL, "imgs is NULL but targets requested");
+        if (img_h <= 0 || img_w <= 0) return fail(PLX_E_SHAPE, "bad image size");
+        // the reference scales u by shape[1] and v by shape[2] but indexes imgs[cam, v_pix, u_pix] (src/ray_sampling.py:238-248):
+        // only square images keep both indices in range for every uv
+        if (img_h != img_w) return fail(PLX_E_UNSUPPORTED, "non-square images index out of range in the reference (H=%d, W=%d)", img_h, img_w);
+        if ((uintptr_t)imgs % 16 || (uintptr_t)targets % 16) return fail(PLX_E_ALIGN, "imgs/targets must be 16-byte aligned");
+    }
+    return cuda_result(plx::launch_generate_rays(imgs, n_cams, img_h, img_w, poses, fov, uv, rays_per_cam, n_side, dirs,
+                                                 targets, (cudaStream_t)stream), "plx_generate_rays");
+}
+
+int plx_sample_points(const PlxRays* rays, int32_t num_samples, float delta_step, float* samples, void* stream) {
+    if (!rays) return fail(PLX_E_NULL, "rays is NULL");
+    int rc;
+    if ((rc = check_rays(*rays)) != PLX_OK) return rc;
+    if (num_samples < 0) return fail(PLX_E_SHAPE, "num_samples < 0");
+    if (rays->n_rays * num_samples > 0 && !samples) return fail(PLX_E_NULL, "samples is NULL");
+    return cuda_result(plx::launch_sample_points(*rays, num_samples, delta_step, samples, (cudaStream_t)stream), "plx_sample_points");
+}
+
+int plx_normalize_points(const float* samples, int64_t m, const float gmin[3], float points_distance, float* out, void* stream) {
+    if (m < 0) return fail(PLX_E_SHAPE, "m < 0");
+    if (m > 0 && (!samples || !out || !gmin)) return fail(PLX_E_NULL, "samples/out/gmin is NULL");
+    return cuda_result(plx::launch_normalize_points(samples, m, gmin[0], gmin[1], gmin[2], points_distance, out,
+                                                    (cudaStream_t)stream), "plx_normalize_points");
+}
+
+static int check_lookup(const float* ns, int64_t m, const void* grid, const int32_t* dims, const void* out) {
+    if (m < 0) return fail(PLX_E_SHAPE, "m < 0");
+    if (!dims) return fail(PLX_E_NULL, "dims is NULL");
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return fail(PLX_E_SHAPE, "grid dims must be positive");
+    if (m > 0 && (!ns || !grid || !out)) return fail(PLX_E_NULL, "ns/grid/out is NULL");
+    if ((uintptr_t)out % 16) return fail(PLX_E_ALIGN, "value buffers must be 16-byte aligned");
+    return PLX_OK;
+}
+
+int plx_gather_nearest(const float* ns, int64_t m, const float* grid, const int32_t dims[3], const int64_t strides[4],
+                       float* vals, uint8_t* inbounds, int64_t* idx_out, void* stream) {
+    int rc;
+    if ((rc = check_lookup(ns, m, grid, dims, vals)) != PLX_OK) return rc;
+    if (!strides) return fail(PLX_E_NULL, "strides is NULL");
+    return cuda_result(plx::launch_gather_nearest(ns, m, grid, dims, strides, vals, inbounds, idx_out, (cudaStream_t)stream),
+                       "plx_gather_nearest");
+}
+
+int plx_gather_nearest_bwd(const float* ns, int64_t m, const float* grad_vals, const int32_t dims[3], float* grad_grid, void* stream) {
+    int rc;
+    if ((rc = check_lookup(ns, m, grad_grid, dims, grad_vals)) != PLX_OK) return rc;
+    if ((uintptr_t)grad_grid % 16) return fail(PLX_E_ALIGN, "grad_grid must be 16-byte aligned");
+    return cuda_result(plx::launch_gather_nearest_bwd(ns, m, grad_vals, dims, grad_grid, (cudaStream_t)stream), "plx_gather_nearest_bwd");
+}
+
+int plx_trilinear_fwd(const float* ns, int64_t m, const float* grid, const int32_t dims[3], const int64_t strides[4],
+                      int32_t masked, float* vals, uint8_t* inbounds, void* stream) {
+    int rc;
+    if ((rc = check_lookup(ns, m, grid, dims, vals)) != PLX_OK) return rc;
+    if (!strides) return fail(PLX_E_NULL, "strides is NULL");
+    return cuda_result(plx::launch_trilinear_fwd(ns, m, grid, dims, strides, masked, vals, inbounds, (cudaStream_t)stream),
+                       "plx_trilinear_fwd");
+}
+
+int plx_trilinear_bwd(const float* ns, int64_t m, const float* grad_vals, const int32_t dims[3], int32_t masked,
+                      float* grad_grid, void* stream) {
+    int rc;
+    if ((rc = check_lookup(ns, m, grad_grid, dims, grad_vals)) != PLX_OK) return rc;
+    if ((uintptr_t)grad_grid % 16) return fail(PLX_E_ALIGN, "grad_grid must be 16-byte aligned");
+    return cuda_result(plx::launch_trilinear_bwd(ns, m, grad_vals, dims, masked, grad_grid, (cudaStream_t)stream), "plx_trilinear_bwd");
+}
+
+int plx_composite_fwd(const float* samples, int64_t n_rays, int32_t num_samples, float* out, void* stream) {
+    if (n_rays < 0 || num_samples < 0) return fail(PLX_E_SHAPE, "negative size");
+    if (n_rays > 0 && (!out || (num_samples > 0 && !samples))) return fail(PLX_E_NULL, "samples/out is NULL");
+    if ((uintptr_t)samples % 16 || (uintptr_t)out % 16) return fail(PLX_E_ALIGN, "samples/out must be 16-byte aligned");
+    return cuda_result(plx::launch_composite_fwd(samples, n_rays, num_samples, out, (cudaStream_t)stream), "plx_composite_fwd");
+}
+
+int plx_composite_bwd(const float* samples, int64_t n_rays, int32_t num_samples, const float* grad_out, float* grad_samples, void* stream) {
+    if (n_rays < 0 || num_samples < 0) return fail(PLX_E_SHAPE, "negative size");
+    if (n_rays > 0 && num_samples > 0 && (!samples || !grad_out || !grad_samples)) return fail(PLX_E_NULL, "samples/grad_out/grad_samples is NULL");
+    if ((uintptr_t)samples % 16 || (uintptr_t)grad_out % 16 || (uintptr_t)grad_samples % 16)
+        return fail(PLX_E_ALIGN, "composite buffers must be 16-byte aligned");
+    if ((size_t)((num_samples + 31) / 32) * 8 * sizeof(float) > 200 * 1024) return fail(PLX_E_UNSUPPORTED, "num_samples too large");
+    return cuda_result(plx::launch_composite_bwd(samples, n_rays, num_samples, grad_out, grad_samples, (cudaStream_t)stream),
+                       "plx_composite_bwd");
+}
+
+int plx_train_step(const PlxTrainStep* a, int32_t phase, void* stream) {
+    if (!a) return fail(PLX_E_NULL, "args is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    const int64_t n_rays = (int64_t)a->n_cams * a->rays_per_cam;
+    if (phase & PLX_STEP_RENDER) {
+        if (!a->uv || !a->dirs || !a->targets || !a->rgba || !a->grad_rgba || !a->loss || !a->grad)
+            return fail(PLX_E_NULL, "train step: uv/scratch/loss/grad pointer is NULL");
+        if (a->n_rays_global < n_rays) return fail(PLX_E_SHAPE, "n_rays_global < local ray count");
+        if ((rc = plx_generate_rays(a->imgs, a->n_cams, a->img_h, a->img_w, a->poses, a->fov, a->uv, a->rays_per_cam, 0,
+                                    a->dirs, a->targets, stream)) != PLX_OK) return rc;
+        if ((rc = cuda_result(cudaMemsetAsync(a->loss, 0, sizeof(float), st), "memset loss")) != PLX_OK) return rc;
+        PlxRenderFwd f;
+        f.march = a->march;
+        // camera positions = poses[:, :3, 3] (src/ray_sampling.py:159), read in place through the strided view
+        f.rays.origins = a->poses + 3;
+        f.rays.origin_stride = 16;
+        f.rays.origin_comp_stride = 4;
+        f.rays.dirs = a->dirs;
+        f.rays.n_rays = n_rays;
+        f.rays.rays_per_origin = a->rays_per_cam;
+        f.grid = a->grid;
+        f.rgba = a->rgba; f.depth = nullptr; f.count = nullptr; f.sample_index = nullptr; f.tcarry = a->tcarry;
+        f.targets = a->targets; f.grad_rgba = a->grad_rgba; f.loss = a->loss;
+        f.grad_scale = (float)(2.0 / (4.0 * (double)a->n_rays_global));
+        f.loss_scale = (float)(1.0 / (4.0 * (double)a->n_rays_global));
+        if ((rc = plx_render_fwd(&f, stream)) != PLX_OK) return rc;
+        PlxRenderBwd b;
+        b.march = a->march; b.rays = f.rays; b.grid = a->grid; b.grad_rgba = a->grad_rgba; b.tcarry = a->tcarry;
+        b.grad_grid = a->grad; b.beta_over_m = a->beta_over_m;
+        if ((rc = plx_render_bwd(&b, stream)) != PLX_OK) return rc;
+    }
+    if (phase & PLX_STEP_OPTIM) {
+        const int64_t n = (int64_t)a->march.nx * a->march.ny * a->march.nz * 4;
+        if ((rc = plx_adam_step(a->grid, a->grad, a->exp_avg, a->exp_avg_sq, a->grad_abs_sum, n, a->lr, a->beta1, a->beta2,
+                                a->eps, a->step, 1, stream)) != PLX_OK) return rc;
+    }
+    return PLX_OK;
+}
+
+int plx_train_step_host(const PlxTrainStep* a, const float* uv_host, float* loss_host, int32_t phase, void* stream) {
+    if (!a) return fail(PLX_E_NULL, "args is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (phase & PLX_STEP_RENDER) {
+        if (!uv_host || !a->uv) return fail(PLX_E_NULL, "uv_host / uv is NULL");
+        const size_t bytes = (size_t)a->n_cams * a->rays_per_cam * 2 * sizeof(float);
+        if ((rc = cuda_result(cudaMemcpyAsync((void*)a->uv, uv_host, bytes, cudaMemcpyHostToDevice, st), "uv H2D")) != PLX_OK) return rc;
+    }
+    if ((rc = plx_train_step(a, phase, stream)) != PLX_OK) return rc;
+    if ((phase & PLX_STEP_RENDER) && loss_host) {
+        if ((rc = cuda_result(cudaMemcpyAsync(loss_host, a->loss, sizeof(float), cudaMemcpyDeviceToHost, st), "loss D2H")) != PLX_OK) return rc;
+    }
+    return PLX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// plx_launch.h — internal launcher prototypes (one per kernel family); the extern "C" layer in plx_abi.cu validates
+// arguments and calls these.  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/plenoxel_abi.h"
+
+namespace plx {
+
+cudaError_t launch_render_fwd(const PlxRenderFwd& a, cudaStream_t st);
+cudaError_t launch_render_bwd(const PlxRenderBwd& a, cudaStream_t st);
+
+struct AdamScalars {
+    float one_minus_beta1;   // lerp weight
+    float beta2;
+    float one_minus_beta2;
+    float bc2_sqrt;          // sqrt(1 - beta2^step)
+    float eps;
+    float neg_step_size;     // -lr / (1 - beta1^step)
+};
+cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int64_t n, const AdamScalars& s,
+                        bool zero_grad, cudaStream_t st);
+
+cudaError_t launch_generate_rays(const float* imgs, int n_cams, int img_h, int img_w, const float* poses, float fov,
+                                 const float* uv, int rays_per_cam, int n_side, float* dirs, float* targets,
+                                 cudaStream_t st);
+cudaError_t launch_sample_points(const PlxRays& rays, int S, float delta, float* out, cudaStream_t st);
+cudaError_t launch_normalize_points(const float* in, int64_t m, float gx, float gy, float gz, float pd, float* out,
+                                    cudaStream_t st);
+cudaError_t launch_gather_nearest(const float* ns, int64_t m, const float* grid, const int32_t* dims,
+                                  const int64_t* strides, float* vals, uint8_t* inb, int64_t* idx_out, cudaStream_t st);
+cudaError_t launch_gather_nearest_bwd(const float* ns, int64_t m, const float* grad_vals, const int32_t* dims,
+                                      float* grad_grid, cudaStream_t st);
+cudaError_t launch_trilinear_fwd(const float* ns, int64_t m, const float* grid, const int32_t* dims,
+                                 const int64_t* strides, int masked, float* vals, uint8_t* inb, cudaStream_t st);
+cudaError_t launch_trilinear_bwd(const float* ns, int64_t m, const float* grad_vals, const int32_t* dims, int masked,
+                                 float* grad_grid, cudaStream_t st);
+cudaError_t launch_composite_fwd(const float* samples, int64_t n_rays, int S, float* out, cudaStream_t st);
+cudaError_t launch_composite_bwd(const float* samples, int64_t n_rays, int S, const float* grad_out, float* grad_samples,
+                                 cudaStream_t st);
+
+}  // namespace plx

@@ -1,0 +1,290 @@
+"""torch.autograd wrappers over the C ABI (include/plenoxel_abi.h).
+
+Tensors in, tensors out; every function launches hand-written sm_100a kernels through `libplenoxel_b200.so`
+on the current CUDA stream.  No ATen arithmetic on the hot path: torch is used to own device memory.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+# --------------------------------------------------------------------------------------------- geometry helpers
+def grid_origin(dims, points_distance: float, start_index: int = 0):
+    """World coordinate of cell (start_index,)*3 as three fp32 values, computed on the host exactly as
+    `generate_grid` builds them (src/grid_functions.py:205-209): fl32(i - ceil(s/2) + 1) * fl32(pd).
+    Equals `grid_indices.min(0)[0]` of src/ray_sampling.py:13 for pd > 0 without the (G^3,3) reduction."""
+    pd32 = np.float32(points_distance)
+    return tuple(float(np.float32(start_index - math.ceil(int(s) / 2) + 1) * pd32) for s in dims[:3])
+
+
+# --------------------------------------------------------------------------------------------- fused march (K1 / K2)
+class _RenderRays(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, grid, origins, dirs, rays_per_origin, num_samples, delta_step, gmin, points_distance, mode, clamp,
+                want_depth, want_count, beta_over_m):
+        dev = L.require_cuda(grid, origins, dirs)
+        lib = L.load()
+        n = dirs.shape[0]
+        march = L.make_march(grid, num_samples, delta_step, gmin, points_distance, mode, clamp)
+        rays = L.make_rays(origins, dirs, rays_per_origin)
+        rgba = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        depth = torch.empty((n,), dtype=torch.float32, device=dev) if want_depth else None
+        count = torch.empty((n,), dtype=torch.int32, device=dev) if want_count else None
+        need_grad = grid.requires_grad
+        tcarry = torch.empty((n, lib.plx_num_chunks(num_samples)), dtype=torch.float32, device=dev) if need_grad else None
+        a = L.PlxRenderFwd()
+        a.march, a.rays = march, rays
+        a.grid, a.rgba, a.depth, a.count = grid.data_ptr(), rgba.data_ptr(), L.ptr(depth), L.ptr(count)
+        a.sample_index, a.tcarry, a.targets, a.grad_rgba, a.loss = None, L.ptr(tcarry), None, None, None
+        with torch.cuda.device(dev):
+            L.check(lib.plx_render_fwd(C.byref(a), L.stream_ptr(dev)), "plx_render_fwd")
+        ctx.march_args = (rays_per_origin, num_samples, delta_step, gmin, points_distance, mode, clamp, beta_over_m)
+        ctx.save_for_backward(grid, origins, dirs, tcarry)
+        outs = (rgba,)
+        if want_depth:
+            ctx.mark_non_differentiable(depth)
+            outs += (depth,)
+        if want_count:
+            ctx.mark_non_differentiable(count)
+            outs += (count,)
+        return outs if len(outs) > 1 else rgba
+
+    @staticmethod
+    def backward(ctx, grad_rgba, *unused):
+        grid, origins, dirs, tcarry = ctx.saved_tensors
+        rays_per_origin, num_samples, delta_step, gmin, points_distance, mode, clamp, beta_over_m = ctx.march_args
+        dev = grid.device
+        lib = L.load()
+        grad_grid = torch.zeros(grid.shape, dtype=torch.float32, device=dev)       # contiguous (X,Y,Z,4)
+        b = L.PlxRenderBwd()
+        b.march = L.make_march(grid, num_samples, delta_step, gmin, points_distance, mode, clamp)
+        b.rays = L.make_rays(origins, dirs, rays_per_origin)
+        g = grad_rgba.contiguous().float()
+        b.grid, b.grad_rgba, b.tcarry, b.grad_grid = grid.data_ptr(), g.data_ptr(), L.ptr(tcarry), grad_grid.data_ptr()
+        b.beta_over_m = float(beta_over_m)
+        with torch.cuda.device(dev):
+            L.check(lib.plx_render_bwd(C.byref(b), L.stream_ptr(dev)), "plx_render_bwd")
+        return (grad_grid,) + (None,) * 12
+
+
+def render_rays(grid, origins, dirs, num_samples, delta_step, gmin, points_distance, mode="nearest", clamp=True,
+                rays_per_origin=1, return_depth=False, return_count=False, beta_over_m=0.0):
+    """Fused march: rgba (N,4) [, depth (N,), count (N,) int32] of rays through `grid` (X,Y,Z,4).
+
+    One kernel for the sequence scripts/train.py:130-151: sample_camera_rays_batched (src/ray_sampling.py:161-167),
+    normalize_samples_for_indecies (:13), get_nearest_voxels on grid.clip(0,1) (src/grid_functions.py:103-114) or the
+    trilinear lookup (:7-44,:220-246), mask multiply, compute_alpha_weighted_pixels (src/ray_sampling.py:172-192).
+    Differentiable w.r.t. `grid` (K2).  `beta_over_m` = beta / M adds the gradient of the sparsity loss of
+    scripts/train.py:170-177 in the backward pass (its value is not part of the returned pixels).
+    """
+    return _RenderRays.apply(grid, origins, dirs, int(rays_per_origin), int(num_samples), float(delta_step),
+                             tuple(float(x) for x in gmin), float(points_distance), mode, bool(clamp),
+                             bool(return_depth), bool(return_count), float(beta_over_m))
+
+
+def sample_indices(grid, origins, dirs, num_samples, delta_step, gmin, points_distance, mode="nearest",
+                   rays_per_origin=1):
+    """Parity/debug dump: (N,S) int32 linear cell index ((ix*Y+iy)*Z+iz) of every sample, -1 when out of bounds,
+    plus the per-ray in-bounds count (N,) int32 — the exact index arithmetic of K1 without clipping."""
+    dev = L.require_cuda(grid, origins, dirs)
+    lib = L.load()
+    n = dirs.shape[0]
+    idx = torch.empty((n, num_samples), dtype=torch.int32, device=dev)
+    rgba = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    count = torch.empty((n,), dtype=torch.int32, device=dev)
+    a = L.PlxRenderFwd()
+    a.march = L.make_march(grid, num_samples, delta_step, gmin, points_distance, mode, True)
+    a.rays = L.make_rays(origins, dirs, rays_per_origin)
+    a.grid, a.rgba, a.count, a.sample_index = grid.data_ptr(), rgba.data_ptr(), count.data_ptr(), idx.data_ptr()
+    with torch.cuda.device(dev):
+        L.check(lib.plx_render_fwd(C.byref(a), L.stream_ptr(dev)), "plx_render_fwd")
+    return idx, count
+
+
+# --------------------------------------------------------------------------------------------- optimiser (K3)
+def adam_step(p, g, m, v, gabs, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, zero_grad=True):
+    """In-place Adam step + `gabs += |g|` + optional `g = 0` (scripts/train.py:180-184) over contiguous fp32 tensors."""
+    dev = L.require_cuda(p, g, m, v, gabs)
+    for t in (p, g, m, v, gabs):
+        if t is not None and (not t.is_contiguous() or t.dtype != torch.float32 or t.numel() != p.numel()):
+            raise L.PlxError("adam_step needs contiguous float32 tensors of equal size")
+    with torch.cuda.device(dev):
+        L.check(L.load().plx_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), L.ptr(gabs), p.numel(),
+                                       float(lr), float(beta1), float(beta2), float(eps), int(step), int(zero_grad),
+                                       L.stream_ptr(dev)), "plx_adam_step")
+
+
+# --------------------------------------------------------------------------------------------- ray generation
+def generate_rays(imgs, poses, fov, uv=None, rays_per_cam=None, want_targets=True):
+    """dirs (C*R,3), targets (C*R,4) — generate_rays_batched (src/ray_sampling.py:195-264) for given uv (C,R,2),
+    or the even-spread lattice (uv=None, rays_per_cam = n_side^2)."""
+    dev = L.require_cuda(imgs, poses, uv)
+    poses = poses.contiguous().float()
+    C_ = poses.shape[0]
+    if uv is not None:
+        uv = uv.contiguous().float()
+        R, n_side = uv.shape[1], 0
+    else:
+        R = int(rays_per_cam)
+        n_side = int(round(math.sqrt(R)))
+    dirs = torch.empty((C_ * R, 3), dtype=torch.float32, device=dev)
+    targets = None
+    H = W = 0
+    if want_targets:
+        if imgs.dtype != torch.float32 or not imgs.is_contiguous():
+            imgs = imgs.contiguous().float()
+        H, W = imgs.shape[1], imgs.shape[2]
+        targets = torch.empty((C_ * R, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().plx_generate_rays(L.ptr(imgs) if want_targets else None, C_, H, W, poses.data_ptr(), float(fov),
+                                           L.ptr(uv), R, n_side, dirs.data_ptr(), L.ptr(targets), L.stream_ptr(dev)),
+                "plx_generate_rays")
+    return dirs, targets
+
+
+# --------------------------------------------------------------------------------------------- eager kernels
+def sample_points(origins, dirs, num_samples, delta_step, rays_per_origin=1):
+    """(N*S,3) sample positions — src/ray_sampling.py:161-167."""
+    dev = L.require_cuda(origins, dirs)
+    n = dirs.shape[0]
+    out = torch.empty((n * num_samples, 3), dtype=torch.float32, device=dev)
+    rays = L.make_rays(origins, dirs, rays_per_origin)
+    with torch.cuda.device(dev):
+        L.check(L.load().plx_sample_points(C.byref(rays), int(num_samples), float(delta_step), out.data_ptr(),
+                                           L.stream_ptr(dev)), "plx_sample_points")
+    return out
+
+
+def normalize_points(samples, gmin, points_distance):
+    """(samples - gmin) / pd — src/ray_sampling.py:13."""
+    dev = L.require_cuda(samples)
+    s = samples.contiguous().float()
+    out = torch.empty_like(s)
+    g = (C.c_float * 3)(*[float(x) for x in gmin])
+    with torch.cuda.device(dev):
+        L.check(L.load().plx_normalize_points(s.data_ptr(), s.numel() // 3, g, float(points_distance), out.data_ptr(),
+                                              L.stream_ptr(dev)), "plx_normalize_points")
+    return out
+
+
+def _dims_strides(grid):
+    dims = (C.c_int32 * 3)(*[int(s) for s in grid.shape[:3]])
+    strides = (C.c_int64 * 4)(*[int(s) for s in grid.stride()])
+    return dims, strides
+
+
+class _GatherNearest(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ns, grid):
+        dev = L.require_cuda(ns, grid)
+        ns = ns.contiguous().float()
+        m = ns.shape[0]
+        vals = torch.empty((m, 4), dtype=torch.float32, device=dev)
+        inb = torch.empty((m,), dtype=torch.uint8, device=dev)
+        dims, strides = _dims_strides(grid)
+        with torch.cuda.device(dev):
+            L.check(L.load().plx_gather_nearest(ns.data_ptr(), m, grid.data_ptr(), dims, strides, vals.data_ptr(),
+                                                inb.data_ptr(), None, L.stream_ptr(dev)), "plx_gather_nearest")
+        ctx.save_for_backward(ns)
+        ctx.grid_shape = tuple(grid.shape)
+        mask = inb.view(torch.bool)
+        ctx.mark_non_differentiable(mask)
+        return vals, mask
+
+    @staticmethod
+    def backward(ctx, grad_vals, _):
+        (ns,) = ctx.saved_tensors
+        dev = ns.device
+        gg = torch.zeros(ctx.grid_shape, dtype=torch.float32, device=dev)
+        gv = grad_vals.contiguous().float()
+        dims = (C.c_int32 * 3)(*ctx.grid_shape[:3])
+        with torch.cuda.device(dev):
+            L.check(L.load().plx_gather_nearest_bwd(ns.data_ptr(), ns.shape[0], gv.data_ptr(), dims, gg.data_ptr(),
+                                                    L.stream_ptr(dev)), "plx_gather_nearest_bwd")
+        return None, gg
+
+
+def gather_nearest(ns, grid):
+    """`get_nearest_voxels` (src/grid_functions.py:103-114): values at wrapped indices (M,4) + in-bounds mask (M,) bool."""
+    if grid.dtype != torch.float32 or grid.dim() != 4 or grid.shape[3] != 4:
+        raise L.PlxError(f"grid must be float32 (X,Y,Z,4), got {grid.dtype} {tuple(grid.shape)}")
+    return _GatherNearest.apply(ns, grid)
+
+
+class _Trilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ns, grid, masked):
+        dev = L.require_cuda(ns, grid)
+        ns = ns.contiguous().float()
+        m = ns.shape[0]
+        vals = torch.empty((m, 4), dtype=torch.float32, device=dev)
+        inb = torch.empty((m,), dtype=torch.uint8, device=dev)
+        dims, strides = _dims_strides(grid)
+        with torch.cuda.device(dev):
+            L.check(L.load().plx_trilinear_fwd(ns.data_ptr(), m, grid.data_ptr(), dims, strides, int(masked),
+                                               vals.data_ptr(), inb.data_ptr(), L.stream_ptr(dev)), "plx_trilinear_fwd")
+        ctx.save_for_backward(ns)
+        ctx.grid_shape, ctx.masked = tuple(grid.shape), int(masked)
+        mask = inb.view(torch.bool)
+        ctx.mark_non_differentiable(mask)
+        return vals, mask
+
+    @staticmethod
+    def backward(ctx, grad_vals, _):
+        (ns,) = ctx.saved_tensors
+        dev = ns.device
+        gg = torch.zeros(ctx.grid_shape, dtype=torch.float32, device=dev)
+        gv = grad_vals.contiguous().float()
+        dims = (C.c_int32 * 3)(*ctx.grid_shape[:3])
+        with torch.cuda.device(dev):
+            L.check(L.load().plx_trilinear_bwd(ns.data_ptr(), ns.shape[0], gv.data_ptr(), dims, ctx.masked, gg.data_ptr(),
+                                               L.stream_ptr(dev)), "plx_trilinear_bwd")
+        return None, gg, None
+
+
+def trilinear_lookup(ns, grid, masked=True):
+    """Trilinear lookup at normalised coordinates (M,3): 8 periodically wrapped corners, nested lerps
+    (src/grid_functions.py:7-44, :220-246, :66-79); `masked` multiplies by the float in-bounds test."""
+    if grid.dtype != torch.float32 or grid.dim() != 4 or grid.shape[3] != 4:
+        raise L.PlxError(f"grid must be float32 (X,Y,Z,4), got {grid.dtype} {tuple(grid.shape)}")
+    return _Trilinear.apply(ns, grid, masked)
+
+
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, samples):
+        dev = L.require_cuda(samples)
+        s = samples.contiguous().float()
+        lead, S = s.shape[:-2], s.shape[-2]
+        n = int(np.prod(lead)) if len(lead) else 1
+        out = torch.empty(lead + (4,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            L.check(L.load().plx_composite_fwd(s.data_ptr(), n, S, out.data_ptr(), L.stream_ptr(dev)), "plx_composite_fwd")
+        ctx.save_for_backward(s)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (s,) = ctx.saved_tensors
+        dev = s.device
+        lead, S = s.shape[:-2], s.shape[-2]
+        n = int(np.prod(lead)) if len(lead) else 1
+        go = grad_out.contiguous().float()
+        gs = torch.zeros_like(s)
+        with torch.cuda.device(dev):
+            L.check(L.load().plx_composite_bwd(s.data_ptr(), n, S, go.data_ptr(), gs.data_ptr(), L.stream_ptr(dev)),
+                    "plx_composite_bwd")
+        return gs
+
+
+def composite(samples):
+    """`compute_alpha_weighted_pixels` (src/ray_sampling.py:172-192): (..., S, 4) -> (..., 4)."""
+    if samples.shape[-1] != 4:
+        raise L.PlxError(f"samples must end in 4 channels, got {tuple(samples.shape)}")
+    return _Composite.apply(samples)

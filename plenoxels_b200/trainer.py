@@ -1,0 +1,145 @@
+"""Fused training step driver: the loop body of `fit()` (scripts/train.py:104-191, tv = 0) as four kernel launches
+issued by ONE C-ABI call per step (plx_train_step): ray generation -> K1 forward + MSE -> K2 backward -> K3 Adam.
+
+Multi-GPU: rays are independent, so every rank holds a full grid replica, renders its own ray batch,
+and the dense gradient (X,Y,Z,4) is SUM-all-reduced over NCCL between K2 and K3.  The loss/gradient scale uses the
+GLOBAL ray count so a plain SUM reproduces the single-GPU mean-MSE gradient exactly (up to summation order).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from . import ops
+
+
+def shard_cameras(n_cams: int, rank: int, world: int) -> range:
+    """Contiguous block of cameras owned by `rank` (ray r of camera c lives with the camera: the reference's rays are
+    camera-major, src/ray_sampling.py:243-245).  Blocks differ by at most one camera."""
+    base, extra = divmod(n_cams, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def all_reduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
+    """SUM-all-reduce in place when a process group is up and has more than one rank."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+class VoxelTrainer:
+    """State + scratch of one grid replica and the single-call step.
+
+    grid (X,Y,Z,4) fp32 raw values (clipped to [0,1] on lookup, scripts/train.py:146); Adam state and the running
+    sum of |grad| (`grid_cells_full_grad`, :184) live next to it.  `imgs` (C,H,W,4) and `poses` (C,4,4) stay resident
+    on the device as in the reference (:75); per step only the (C,R,2) uv draw changes.
+    """
+
+    def __init__(self, grid, points_distance, poses, fov, imgs, rays_per_cam, num_samples, delta_step, lr,
+                 mode="nearest", beta=0.0, betas=(0.9, 0.999), eps=1e-8, n_rays_global=None, group=None):
+        dev = L.require_cuda(grid, poses, imgs)
+        self.lib = L.load()
+        self.device = dev
+        self.group = group
+        self.grid = grid.detach().to(torch.float32).contiguous().clone()
+        self.grad = torch.zeros_like(self.grid)
+        self.exp_avg = torch.zeros_like(self.grid)
+        self.exp_avg_sq = torch.zeros_like(self.grid)
+        self.grad_abs_sum = torch.zeros_like(self.grid)
+        self.poses = poses.detach().to(torch.float32).contiguous()
+        self.imgs = imgs.detach().to(torch.float32).contiguous()
+        self.fov = float(fov)
+        self.points_distance = float(points_distance)
+        self.rays_per_cam, self.num_samples, self.delta_step = int(rays_per_cam), int(num_samples), float(delta_step)
+        self.lr, self.betas, self.eps, self.mode, self.beta = float(lr), betas, float(eps), mode, float(beta)
+        self.step_count = 0
+        C_ = self.poses.shape[0]
+        n = C_ * self.rays_per_cam
+        self.n_rays = n
+        self.n_rays_global = int(n_rays_global) if n_rays_global is not None else n
+        self.gmin = ops.grid_origin(self.grid.shape, points_distance)
+        # scratch
+        self.uv = torch.empty((C_, self.rays_per_cam, 2), dtype=torch.float32, device=dev)
+        self.dirs = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        self.targets = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        self.rgba = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        self.grad_rgba = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        self.tcarry = torch.empty((n, self.lib.plx_num_chunks(self.num_samples)), dtype=torch.float32, device=dev)
+        self.loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self.loss_host = torch.zeros((1,), dtype=torch.float32).pin_memory()
+        self._args = self._make_args()
+        self.launches_per_step = 4        # generate_rays, render_fwd, render_bwd, adam (memset/memcpy are not kernels)
+
+    def _make_args(self) -> L.PlxTrainStep:
+        a = L.PlxTrainStep()
+        a.march = L.make_march(self.grid, self.num_samples, self.delta_step, self.gmin, self.points_distance, self.mode, True)
+        a.imgs, a.n_cams, a.img_h, a.img_w = self.imgs.data_ptr(), self.imgs.shape[0], self.imgs.shape[1], self.imgs.shape[2]
+        a.poses, a.fov = self.poses.data_ptr(), self.fov
+        a.uv, a.rays_per_cam = self.uv.data_ptr(), self.rays_per_cam
+        a.n_rays_global = self.n_rays_global
+        a.grid, a.grad = self.grid.data_ptr(), self.grad.data_ptr()
+        a.exp_avg, a.exp_avg_sq, a.grad_abs_sum = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.grad_abs_sum.data_ptr()
+        a.lr, a.beta1, a.beta2, a.eps = self.lr, self.betas[0], self.betas[1], self.eps
+        a.step = 0
+        m_global = self.n_rays_global * self.num_samples
+        a.beta_over_m = self.beta / m_global if (self.beta and m_global) else 0.0
+        a.dirs, a.targets, a.rgba = self.dirs.data_ptr(), self.targets.data_ptr(), self.rgba.data_ptr()
+        a.grad_rgba, a.tcarry, a.loss = self.grad_rgba.data_ptr(), self.tcarry.data_ptr(), self.loss.data_ptr()
+        return a
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _distributed(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def step(self, uv: torch.Tensor | None = None) -> torch.Tensor:
+        """One step with the uv draw already on the device (`uv` (C,R,2) cuda, or the trainer's own `self.uv`).
+        Returns the device loss tensor (1,) without synchronising.  With a process group: this rank's partial loss."""
+        if uv is not None:
+            if uv.data_ptr() != self.uv.data_ptr():
+                self._args.uv = uv.data_ptr()
+        self.step_count += 1
+        self._args.step = self.step_count
+        st = L.stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            if self._distributed():
+                L.check(self.lib.plx_train_step(C.byref(self._args), L.PLX_STEP_RENDER, st), "plx_train_step(render)")
+                all_reduce_sum_(self.grad, self.group)
+                L.check(self.lib.plx_train_step(C.byref(self._args), L.PLX_STEP_OPTIM, st), "plx_train_step(optim)")
+            else:
+                L.check(self.lib.plx_train_step(C.byref(self._args), L.PLX_STEP_ALL, st), "plx_train_step")
+        self._args.uv = self.uv.data_ptr()
+        return self.loss
+
+    def step_host(self, uv_host: torch.Tensor) -> torch.Tensor:
+        """End-to-end step from HOST memory: `uv_host` (C,R,2) pinned fp32 is copied to the device, the step runs, and
+        the loss scalar is copied back into pinned `self.loss_host` — all asynchronous on the current stream."""
+        if uv_host.is_cuda or uv_host.dtype != torch.float32 or not uv_host.is_contiguous() or \
+                uv_host.numel() != self.uv.numel():
+            raise L.PlxError("uv_host must be a contiguous float32 host tensor of shape (C,R,2)")
+        self.step_count += 1
+        self._args.step = self.step_count
+        st = L.stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            if self._distributed():
+                L.check(self.lib.plx_train_step_host(C.byref(self._args), uv_host.data_ptr(), self.loss_host.data_ptr(),
+                                                     L.PLX_STEP_RENDER, st), "plx_train_step_host(render)")
+                all_reduce_sum_(self.grad, self.group)
+                L.check(self.lib.plx_train_step_host(C.byref(self._args), None, None, L.PLX_STEP_OPTIM, st),
+                        "plx_train_step_host(optim)")
+            else:
+                L.check(self.lib.plx_train_step_host(C.byref(self._args), uv_host.data_ptr(), self.loss_host.data_ptr(),
+                                                     L.PLX_STEP_ALL, st), "plx_train_step_host")
+        return self.loss_host
+
+    def checkpoint(self, extra_param: dict | None = None) -> dict:
+        """The reference's `.pth` payload (scripts/train.py:194-210): {grid, grid_grad, param{...}} on the CPU."""
+        param = {"device": str(self.device), "number_of_rays": self.rays_per_cam, "num_samples": self.num_samples,
+                 "delta_step": self.delta_step, "even_spread": False, "camera_ray": False,
+                 "points_distance": self.points_distance, "gridsize": list(self.grid.shape[:3])}
+        if extra_param:
+            param.update(extra_param)
+        return {"grid": self.grid.detach().cpu(), "grid_grad": self.grad_abs_sum.detach().cpu(), "param": param}

@@ -1,0 +1,118 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on small seeded inputs.
+
+Build-container only (the GPU box has no /root/reference):   python tests/golden/make_golden.py
+The fixtures hold both the inputs and the reference's outputs, so the checks in tests/ need neither the reference nor
+torch's RNG to reproduce them.  The reference ships no golden vectors of its own; these are its outputs.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("PLX_REFERENCE", "/root/reference")
+sys.path.insert(0, REPO)
+sys.path.insert(1, REF)
+
+import src.grid_functions as rgf      # noqa: E402  reference
+import src.ray_sampling as rrs        # noqa: E402  reference
+from plenoxels_b200 import synth      # noqa: E402
+
+assert rgf.__file__.startswith(REF)
+
+
+def reference_step(grid, pd, poses, fov, imgs, R, S, delta, uv, mode, even_spread=False):
+    """scripts/train.py:130-157 + :181 with the reference's own functions; uv injected in place of torch.rand."""
+    dims = grid.shape[:3]
+    coords, _, _, _ = rgf.generate_grid(*dims, points_distance=pd, info_size=4, device="cpu")
+    real_rand = torch.rand
+    torch.rand = lambda *a, **k: uv.clone()
+    try:
+        samples, targets, cam_pos, dirs = rrs.sample_camera_rays_batched(
+            transform_matrices=poses, camera_angle_x=fov, imgs=imgs, number_of_rays=R, num_samples=S, delta_step=delta,
+            even_spread=even_spread, camera_ray=False, device="cpu")
+    finally:
+        torch.rand = real_rand
+    R_eff = dirs.shape[0] // poses.shape[0]
+    ns = rrs.normalize_samples_for_indecies(coords, samples, pd)
+    g = grid.detach().clone().requires_grad_(True)
+    if mode == "nearest":
+        idx = torch.round(ns).to(torch.long)
+        inb = rgf.find_out_of_bound(idx, g)
+        lin = torch.where(inb, (idx[:, 0] * dims[1] + idx[:, 1]) * dims[2] + idx[:, 2], torch.full_like(idx[:, 0], -1))
+        vals, inb2 = rgf.get_nearest_voxels(ns, g.clip(0, 1))
+        assert torch.equal(inb, inb2)
+        vals = vals * inb.unsqueeze(-1)
+    else:
+        inb = rgf.find_out_of_bound(ns, g)
+        pts = rgf.get_grid_points_indices(ns)
+        rgf.fix_out_of_bounds(pts.reshape(-1, 3), g)
+        lin = torch.where(inb, torch.zeros_like(inb, dtype=torch.long), torch.full_like(inb, -1, dtype=torch.long))
+        vals = rgf.trilinear_interpolation(ns, pts, g.clip(0, 1)) * inb.unsqueeze(-1)
+    pix = rrs.compute_alpha_weighted_pixels(vals.reshape(poses.shape[0], R_eff, S, 4)).reshape(-1, 4)
+    loss = torch.nn.functional.mse_loss(pix, targets)
+    loss.backward()
+    return dict(gmin=coords.min(0)[0].numpy(), dirs=dirs.numpy(), targets=targets.numpy(),
+                lin=lin.reshape(-1, S).numpy().astype(np.int32), inb=inb.reshape(-1, S).numpy(),
+                vals=vals.detach().numpy().astype(np.float32), pix=pix.detach().numpy(), loss=np.float64(loss.item()),
+                grad=g.grad.numpy())
+
+
+def make_case(name, G, C, H, R, S, delta, kind, mode, seed):
+    torch.manual_seed(seed)
+    pd = synth.GRID_EXTENT / G
+    grid = {"ball": synth.ball_grid, "dense": synth.dense_grid, "soft": synth.soft_grid}[kind](G, seed=seed)
+    poses, imgs, uv = synth.lookat_poses(C), synth.random_images(C, H, H, seed=seed + 1), synth.random_uv(C, R, seed=seed + 2)
+    out = reference_step(grid, pd, poses, synth.CAMERA_ANGLE_X, imgs, R, S, delta, uv, mode)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), grid=grid.numpy(), poses=poses.numpy(), imgs=imgs.numpy(),
+                        uv=uv.numpy(), fov=np.float64(synth.CAMERA_ANGLE_X), pd=np.float64(pd), delta=np.float64(delta),
+                        S=np.int64(S), R=np.int64(R), mode=np.array(mode), **out)
+    print(name, "in-bounds", float(out["inb"].mean()), "loss", float(out["loss"]))
+
+
+def make_even_spread(name):
+    """even_spread=True ray lattice (src/ray_sampling.py:220-223) incl. S = 0 (scripts/visulize_camera_and_grid.py:36-46)."""
+    poses, imgs = synth.lookat_poses(2), synth.random_images(2, 24, 24, seed=7)
+    samples, targets, cam_pos, dirs = rrs.sample_camera_rays_batched(
+        transform_matrices=poses, camera_angle_x=synth.CAMERA_ANGLE_X, imgs=imgs, number_of_rays=100, num_samples=5,
+        delta_step=0.3, even_spread=True, camera_ray=False, device="cpu")
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), poses=poses.numpy(), imgs=imgs.numpy(),
+                        fov=np.float64(synth.CAMERA_ANGLE_X), dirs=dirs.numpy(), targets=targets.numpy(),
+                        samples=samples.numpy(), cam_pos=cam_pos.numpy())
+    print(name, dirs.shape)
+
+
+def make_adam(name):
+    """Three torch.optim.Adam steps (scripts/train.py:89,:182) on a small parameter vector + |grad| accumulation (:184)."""
+    torch.manual_seed(5)
+    n = 4096
+    p0 = torch.rand(n) * 1.4 - 0.2
+    p = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p], lr=0.0075)
+    grads, params = [], []
+    gabs = torch.zeros(n)
+    for _ in range(3):
+        g = torch.randn(n) * 1e-3 * (torch.rand(n) < 0.6)
+        p.grad = g.clone()
+        opt.step()
+        gabs += g.abs()
+        grads.append(g.numpy().copy())
+        params.append(p.detach().numpy().copy())
+    st = opt.state[p]
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), p0=p0.numpy(), grads=np.stack(grads), params=np.stack(params),
+                        exp_avg=st["exp_avg"].numpy(), exp_avg_sq=st["exp_avg_sq"].numpy(), gabs=gabs.numpy(),
+                        lr=np.float64(0.0075))
+    print(name)
+
+
+if __name__ == "__main__":
+    make_case("nn_dense_g24", 24, 2, 8, 64, 48, 6.0 / 48, "dense", "nearest", seed=11)
+    make_case("nn_ball_g32", 32, 3, 12, 48, 96, 6.0 / 96, "ball", "nearest", seed=12)
+    make_case("tri_ball_g24", 24, 2, 8, 48, 64, 6.0 / 64, "ball", "trilinear", seed=13)
+    make_case("tri_dense_g16", 16, 2, 8, 32, 40, 6.0 / 40, "dense", "trilinear", seed=14)
+    make_even_spread("even_spread")
+    make_adam("adam3")

@@ -1,0 +1,107 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/plenoxel_abi.h declares, the ctypes
+structs have the C layout, host-side geometry matches the oracle, and the product path refuses to run without CUDA."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import plenoxel_oracle as po
+from plenoxels_b200 import _lib as L
+from plenoxels_b200 import build, ops
+from plenoxels_b200.trainer import shard_cameras
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(REPO, "include", "plenoxel_abi.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(plx_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = declared_symbols()
+    for s in ("plx_render_fwd", "plx_render_bwd", "plx_adam_step", "plx_generate_rays", "plx_train_step",
+              "plx_train_step_host", "plx_gather_nearest", "plx_trilinear_fwd", "plx_composite_fwd"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(plx_lib):
+    raw = C.CDLL(build.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(raw, s), f"{s} declared in plenoxel_abi.h but not exported"
+        assert s in L.PROTOTYPES, f"{s} has no ctypes prototype"
+    assert plx_lib.plx_version() == 1
+    assert plx_lib.plx_num_chunks(600) >= 19 and plx_lib.plx_num_chunks(0) >= 1
+
+
+def test_ctypes_structs_match_c_layout(tmp_path):
+    prog = tmp_path / "layout.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "plenoxel_abi.h"\nint main(){'
+                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(PlxMarch), sizeof(PlxRays), sizeof(PlxRenderFwd),'
+                    'sizeof(PlxRenderBwd), sizeof(PlxTrainStep), offsetof(PlxRenderFwd, loss), offsetof(PlxTrainStep, lr),'
+                    'offsetof(PlxTrainStep, loss));return 0;}')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), str(prog), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(L.PlxMarch), C.sizeof(L.PlxRays), C.sizeof(L.PlxRenderFwd), C.sizeof(L.PlxRenderBwd),
+            C.sizeof(L.PlxTrainStep), L.PlxRenderFwd.loss.offset, L.PlxTrainStep.lr.offset, L.PlxTrainStep.loss.offset]
+    assert got == want
+
+
+def test_argument_errors_are_reported_not_thrown(plx_lib):
+    a = L.PlxRenderFwd()
+    assert plx_lib.plx_render_fwd(C.byref(a), None) == -1            # PLX_E_NULL: grid
+    assert b"grid" in plx_lib.plx_last_error()
+    assert plx_lib.plx_adam_step(None, None, None, None, None, 8, 1e-3, 0.9, 0.999, 1e-8, 1, 1, None) == -1
+    assert plx_lib.plx_adam_step(None, None, None, None, None, 0, 1e-3, 0.9, 0.999, 1e-8, 0, 1, None) == -2   # step < 1
+    assert plx_lib.plx_generate_rays(None, 1, 4, 4, None, 0.5, None, 4, 2, None, None, None) == -1
+
+
+@pytest.mark.parametrize("G,pd", [(64, 0.05), (128, 0.025), (256, 0.0125), (93, 0.0125), (7, 0.3)])
+def test_grid_origin_matches_oracle(G, pd):
+    assert np.array_equal(np.float32(ops.grid_origin((G, G, G), pd)), po.grid_origin((G, G, G), pd))
+    assert np.array_equal(np.float32(ops.grid_origin((G, G + 1, G + 2), pd, 3)), po.grid_origin((G, G + 1, G + 2), pd, 3))
+
+
+def test_cpu_tensors_are_refused(plx_lib):
+    grid = torch.zeros(4, 4, 4, 4)
+    o, d = torch.zeros(1, 3), torch.ones(2, 3)
+    with pytest.raises(L.PlxError, match="no CPU fallback"):
+        ops.render_rays(grid, o, d, 8, 0.1, (0, 0, 0), 0.5)
+    with pytest.raises(L.PlxError, match="no CPU fallback"):
+        ops.composite(torch.zeros(1, 2, 3, 4))
+    with pytest.raises(L.PlxError):
+        ops.adam_step(grid, grid, grid, grid, grid, 1, 1e-3)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(build, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(L.PlxError, match="no CPU / PyTorch fallback"):
+        L.load()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "plenoxels_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
+
+
+@pytest.mark.parametrize("n,world", [(100, 1), (100, 2), (100, 8), (7, 4), (3, 8)])
+def test_shard_cameras_partitions(n, world):
+    seen = []
+    for r in range(world):
+        seen += list(shard_cameras(n, r, world))
+    assert seen == list(range(n))
+    sizes = [len(shard_cameras(n, r, world)) for r in range(world)]
+    assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,203 @@
+"""GPU parity: the sm_100a kernels (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): nearest-neighbour indices and per-ray sample counts bit-exact; RGB(A), depth, loss and
+grid gradients within 1e-5 relative (fp32).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import plenoxel_oracle as po
+from plenoxels_b200 import ops, synth
+from plenoxels_b200.trainer import VoxelTrainer
+from tests.helpers import Case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+CASES = {
+    "c1-dense": dict(G=64, C=1, H=64, R=4096, S=64, delta=6.0 / 64, kind="dense"),       # BASELINE config #1 shape
+    "ball-64": dict(G=64, C=4, H=32, R=256, S=64, delta=6.0 / 64, kind="ball"),
+    "c2-small": dict(G=128, C=6, H=40, R=64, S=600, delta=0.0125, kind="ball"),          # config #2 geometry, fewer rays
+    "soft-32": dict(G=32, C=3, H=16, R=128, S=96, delta=6.0 / 96, kind="soft"),
+    "ragged": dict(G=24, C=5, H=8, R=37, S=45, delta=6.0 / 45, kind="dense"),            # N, S not multiples of 32/8
+}
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request, plx_lib):
+    return Case(**CASES[request.param])
+
+
+def test_indices_and_counts_bit_exact(case):
+    d = case.cuda()
+    idx, count = ops.sample_indices(d["grid"], d["origins"], d["dirs"], case.S, case.delta, case.gmin, case.pd,
+                                    rays_per_origin=case.R)
+    _, _, ocount, olin = case.oracle_forward()
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), olin), "linear voxel indices differ from the oracle"
+    assert np.array_equal(count.cpu().numpy(), ocount)
+
+
+@pytest.mark.parametrize("mode", ["nearest", "trilinear"])
+def test_forward_rgba_depth_count(case, mode):
+    d = case.cuda()
+    rgba, depth, count = ops.render_rays(d["grid"], d["origins"], d["dirs"], case.S, case.delta, case.gmin, case.pd,
+                                         mode=mode, rays_per_origin=case.R, return_depth=True, return_count=True)
+    orgba, odepth, ocount, _ = case.oracle_forward(mode)
+    assert np.array_equal(count.cpu().numpy(), ocount), "clipped march lost / gained in-bounds samples"
+    assert rel_err(rgba.cpu().numpy(), orgba) <= TOL
+    assert rel_err(depth.cpu().numpy(), odepth) <= TOL
+    # the clipped + early-terminated march (no count requested) gives the same pixels
+    rgba2 = ops.render_rays(d["grid"], d["origins"], d["dirs"], case.S, case.delta, case.gmin, case.pd, mode=mode,
+                            rays_per_origin=case.R)
+    assert rel_err(rgba2.cpu().numpy(), orgba) <= TOL
+
+
+@pytest.mark.parametrize("mode", ["nearest", "trilinear"])
+@pytest.mark.parametrize("beta", [0.0, 5e-3])
+def test_backward_grid_gradient(case, mode, beta):
+    d = case.cuda()
+    grid = d["grid"].clone().requires_grad_(True)
+    bom = beta / (case.N * case.S)
+    rgba = ops.render_rays(grid, d["origins"], d["dirs"], case.S, case.delta, case.gmin, case.pd, mode=mode,
+                           rays_per_origin=case.R, beta_over_m=bom)
+    loss = torch.nn.functional.mse_loss(rgba, d["targets"])
+    loss.backward()
+    orgba, _, _, _ = case.oracle_forward(mode)
+    oloss, gpix = po.mse_loss(orgba, case.targets)
+    ograd = case.oracle_backward(gpix, mode, beta=beta)
+    assert abs(float(loss) - oloss) <= TOL * abs(oloss)
+    assert rel_err(grid.grad.cpu().numpy(), ograd) <= TOL
+
+
+def test_backward_without_saved_carry_matches(case):
+    """K2's in-kernel first pass (tcarry = NULL) must agree with the path that reuses K1's chunk transmittances."""
+    import ctypes as C
+    from plenoxels_b200 import _lib as L
+    d = case.cuda()
+    grid = d["grid"].clone().requires_grad_(True)
+    rgba = ops.render_rays(grid, d["origins"], d["dirs"], case.S, case.delta, case.gmin, case.pd, rays_per_origin=case.R)
+    g = torch.randn_like(rgba)
+    rgba.backward(g)
+    gg = torch.zeros_like(d["grid"])
+    b = L.PlxRenderBwd()
+    b.march = L.make_march(d["grid"], case.S, case.delta, case.gmin, case.pd, "nearest", True)
+    b.rays = L.make_rays(d["origins"], d["dirs"], case.R)
+    b.grid, b.grad_rgba, b.tcarry, b.grad_grid = d["grid"].data_ptr(), g.data_ptr(), None, gg.data_ptr()
+    L.check(L.load().plx_render_bwd(C.byref(b), L.stream_ptr(gg.device)))
+    torch.cuda.synchronize()
+    assert rel_err(gg.cpu().numpy(), grid.grad.cpu().numpy()) <= 2e-6
+
+
+def test_generate_rays_matches_oracle(case):
+    d = case.cuda()
+    dirs, targets = ops.generate_rays(d["imgs"], d["poses"], case.fov, uv=d["uv"])
+    assert np.array_equal(targets.cpu().numpy(), case.targets), "target pixel lookup differs"
+    assert np.abs(dirs.cpu().numpy() - case.dirs).max() <= 1.2e-7        # 1 ulp of a unit vector component
+    assert np.array_equal(dirs.cpu().numpy(), case.dirs), "directions are expected to be bit-exact too"
+
+
+def test_even_spread_lattice():
+    poses = synth.lookat_poses(3).cuda()
+    imgs = synth.random_images(3, 64, 64).cuda()
+    dirs, targets = ops.generate_rays(imgs, poses, 0.6911112070083618, uv=None, rays_per_cam=4096)
+    uv = po.even_spread_uv(3, 4096)
+    odirs, otargets, _ = po.generate_rays(imgs.cpu().numpy(), poses.cpu().numpy(), 0.6911112070083618, uv)
+    assert np.array_equal(targets.cpu().numpy(), otargets)
+    assert np.array_equal(dirs.cpu().numpy(), odirs)
+
+
+def test_eager_sample_normalize_gather(case):
+    d = case.cuda()
+    pos = ops.sample_points(d["origins"], d["dirs"], case.S, case.delta, rays_per_origin=case.R)
+    opos = po.sample_positions(case.origins_per_ray, case.dirs, case.S, case.delta).reshape(-1, 3)
+    assert np.array_equal(pos.cpu().numpy(), opos)
+    ns = ops.normalize_points(pos, case.gmin, case.pd)
+    ons = po.normalize_positions(opos, case.gmin, case.pd)
+    assert np.array_equal(ns.cpu().numpy(), ons)
+    clipped = d["grid"].clip(0, 1)
+    vals, mask = ops.gather_nearest(ns, clipped)
+    ovals, oinb = po.gather_nearest(ons, np.clip(case.grid.numpy(), 0, 1))
+    assert np.array_equal(mask.cpu().numpy(), oinb)
+    assert np.array_equal(vals.cpu().numpy(), ovals), "gathered values (wrapped, unmasked) must be bit-exact"
+    tvals, tmask = ops.trilinear_lookup(ns, clipped)
+    otv, otm = po.trilinear_lookup(ons, np.clip(case.grid.numpy(), 0, 1))
+    assert np.array_equal(tmask.cpu().numpy(), otm)
+    assert np.array_equal(tvals.cpu().numpy(), otv), "trilinear values must be bit-exact (same op order)"
+
+
+def test_eager_composite_fwd_bwd(case):
+    torch.manual_seed(3)
+    s = torch.rand(case.C, case.R, case.S, 4, device="cuda")
+    s[..., 3] *= 0.3
+    s[torch.rand(case.C, case.R, case.S, device="cuda") < 0.02] = torch.tensor([0.5, 0.25, 0.75, 1.0], device="cuda")
+    s.requires_grad_(True)
+    out = ops.composite(s)
+    g = torch.randn_like(out)
+    out.backward(g)
+    sn = s.detach().cpu().numpy()
+    assert rel_err(out.detach().cpu().numpy(), po.composite(sn, dtype=np.float64)) <= TOL
+    assert rel_err(s.grad.cpu().numpy(), po.composite_backward(sn, g.cpu().numpy())) <= TOL
+
+
+def test_eager_chain_autograd_matches_fused(case):
+    """The unfused path (reference call sequence on eager kernels + torch glue) and the fused K1/K2 agree."""
+    d = case.cuda()
+    g1 = d["grid"].clone().requires_grad_(True)
+    pos = ops.sample_points(d["origins"], d["dirs"], case.S, case.delta, rays_per_origin=case.R)
+    ns = ops.normalize_points(pos, case.gmin, case.pd)
+    vals, mask = ops.gather_nearest(ns, g1.clip(0, 1))
+    vals = vals * mask.unsqueeze(-1)
+    pix = ops.composite(vals.reshape(case.C, case.R, case.S, 4)).reshape(-1, 4)
+    torch.nn.functional.mse_loss(pix, d["targets"]).backward()
+    g2 = d["grid"].clone().requires_grad_(True)
+    pix2 = ops.render_rays(g2, d["origins"], d["dirs"], case.S, case.delta, case.gmin, case.pd, rays_per_origin=case.R)
+    torch.nn.functional.mse_loss(pix2, d["targets"]).backward()
+    assert rel_err(pix.detach().cpu().numpy(), pix2.detach().cpu().numpy()) <= 2e-6
+    assert rel_err(g1.grad.cpu().numpy(), g2.grad.cpu().numpy()) <= 2e-6
+
+
+def test_adam_step_matches_oracle():
+    torch.manual_seed(0)
+    n = 64 * 64 * 16 * 4 + 4
+    p = (torch.rand(n) * 1.4 - 0.2)
+    m, v, ga = torch.zeros(n), torch.zeros(n), torch.zeros(n)
+    pc, mc, vc, gac = (t.cuda() for t in (p, m, v, ga))
+    pn, mn, vn, gan = (t.numpy().copy() for t in (p, m, v, ga))
+    for step in range(1, 5):
+        g = torch.randn(n) * 1e-3 * (torch.rand(n) < 0.6)
+        gc = g.cuda()
+        ops.adam_step(pc, gc, mc, vc, gac, step, lr=0.0075)
+        pn, mn, vn, gan = po.adam_step(pn, g.numpy(), mn, vn, gan, 0.0075, step)
+        assert float(gc.abs().max()) == 0.0, "gradient must be cleared for the next step"
+    assert np.array_equal(mc.cpu().numpy(), mn)
+    assert np.array_equal(vc.cpu().numpy(), vn)
+    assert np.array_equal(gac.cpu().numpy(), gan)
+    assert np.array_equal(pc.cpu().numpy(), pn), "Adam parameters are bit-exact against the fp32 oracle"
+
+
+@pytest.mark.parametrize("mode", ["nearest", "trilinear"])
+def test_train_steps_match_oracle(mode):
+    """Three whole steps (ray generation -> forward -> MSE -> backward -> Adam) through plx_train_step."""
+    case = Case(G=32, C=4, H=16, R=96, S=80, delta=6.0 / 80, kind="ball")
+    d = case.cuda()
+    tr = VoxelTrainer(d["grid"], case.pd, d["poses"], case.fov, d["imgs"], case.R, case.S, case.delta, lr=0.0075, mode=mode)
+    grid = case.grid.numpy().copy()
+    m, v, ga = np.zeros_like(grid), np.zeros_like(grid), np.zeros_like(grid)
+    for step in range(1, 4):
+        uv = synth.random_uv(case.C, case.R, seed=10 + step)
+        dirs, targets, _ = po.generate_rays(case.imgs.numpy(), case.poses.numpy(), case.fov, uv.numpy())
+        loss_o, grad_o, grid, m, v, ga = po.train_step(grid, m, v, ga, case.origins_per_ray, dirs, targets, case.S, case.delta,
+                                                       case.gmin, case.pd, 0.0075, step, mode=mode)
+        if step % 2:
+            loss = float(tr.step(uv.cuda()))
+        else:
+            loss_host = tr.step_host(uv.pin_memory())
+            torch.cuda.synchronize()
+            loss = float(loss_host)
+        assert abs(loss - loss_o) <= TOL * abs(loss_o)
+        assert rel_err(tr.grad_abs_sum.cpu().numpy(), ga) <= TOL
+        # Adam's first steps are +-lr*sign(g): cells whose gradient is O(rounding noise) may flip; compare the bulk
+        diff = np.abs(tr.grid.cpu().numpy() - grid)
+        assert np.quantile(diff, 0.999) <= 1e-5, f"step {step}: {np.quantile(diff, 0.999)}"

@@ -174,6 +174,14 @@ int plx_composite_bwd(const float* samples, int64_t n_rays, int32_t num_samples,
                       float* grad_samples, void* stream);
 
 /*
+ * Self-test of the library's exact fp32 helpers: evaluates the hoisted-reciprocal quotient x / y (the march's divisor
+ * path), the inlined square root and the per-element quotient (Adam) on `n` pseudo-random inputs and counts results
+ * that differ in any bit from CUDA's IEEE intrinsics (__fdiv_rn / __fsqrt_rn).  `mismatches` = 3 device uint64 counters
+ * (caller zeroes them): [0] x / y, [1] sqrt, [2] x / d.  Parity infrastructure; not used by the product path.
+ */
+int plx_selftest_arith(float y, uint64_t n, uint64_t seed, uint64_t* mismatches, void* stream);
+
+/*
  * One whole training step of scripts/train.py:130-184 (tv = 0) in a single host call:
  *   plx_generate_rays -> plx_render_fwd (+MSE epilogue) -> plx_render_bwd -> [caller's collective] -> plx_adam_step.
  * `phase` selects which part runs so a multi-GPU caller can put the gradient all-reduce between the two halves:

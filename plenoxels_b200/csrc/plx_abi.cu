@@ -197,6 +197,12 @@ int plx_composite_bwd(const float* samples, int64_t n_rays, int32_t num_samples,
                        "plx_composite_bwd");
 }
 
+int plx_selftest_arith(float y, uint64_t n, uint64_t seed, uint64_t* mismatches, void* stream) {
+    if (!mismatches) return fail(PLX_E_NULL, "mismatches is NULL");
+    if (!(y == y) || y == 0.f) return fail(PLX_E_SHAPE, "divisor must be a non-zero number");
+    return cuda_result(plx::launch_selftest(y, n, seed, (unsigned long long*)mismatches, (cudaStream_t)stream), "plx_selftest_arith");
+}
+
 int plx_train_step(const PlxTrainStep* a, int32_t phase, void* stream) {
     if (!a) return fail(PLX_E_NULL, "args is NULL");
     cudaStream_t st = (cudaStream_t)stream;

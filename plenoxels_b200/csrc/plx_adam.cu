@@ -13,11 +13,13 @@
 
 namespace plx {
 
-__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamScalars& s) {
+// `bc` = hoisted reciprocal of bc2_sqrt (plx_device.cuh): both quotients and the square root are the correctly rounded
+// IEEE results, computed with the same expansions ptxas uses but without the per-element range-check branches.
+__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamScalars& s, const FastDiv& bc) {
     m = fmaf(s.one_minus_beta1, __fsub_rn(g, m), m);
     v = fmaf(__fmul_rn(s.one_minus_beta2, g), g, __fmul_rn(v, s.beta2));
-    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), s.bc2_sqrt), s.eps);
-    p = __fadd_rn(p, __fdiv_rn(__fmul_rn(s.neg_step_size, m), denom));
+    const float denom = __fadd_rn(fdiv_exact(fsqrt_exact(v), bc), s.eps);
+    p = __fadd_rn(p, fdiv_var(__fmul_rn(s.neg_step_size, m), denom));
 }
 
 template <bool HAS_ABS, bool ZERO>
@@ -25,15 +27,16 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
                                               float4* __restrict__ v, float4* __restrict__ ga, int64_t n4,
                                               const AdamScalars s) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const FastDiv bc = make_fastdiv(s.bc2_sqrt);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 P = p[i];
         const float4 G = __ldcs(g + i);
         float4 M = __ldcs(m + i);
         float4 V = __ldcs(v + i);
-        adam1(P.x, G.x, M.x, V.x, s);
-        adam1(P.y, G.y, M.y, V.y, s);
-        adam1(P.z, G.z, M.z, V.z, s);
-        adam1(P.w, G.w, M.w, V.w, s);
+        adam1(P.x, G.x, M.x, V.x, s, bc);
+        adam1(P.y, G.y, M.y, V.y, s, bc);
+        adam1(P.z, G.z, M.z, V.z, s, bc);
+        adam1(P.w, G.w, M.w, V.w, s, bc);
         p[i] = P;                       // the grid is re-read by the next step's march: default (L2-resident) policy
         __stcs(m + i, M);
         __stcs(v + i, V);
@@ -51,10 +54,11 @@ template <bool HAS_ABS, bool ZERO>
 __global__ void k_adam_scalar(float* p, float* g, float* m, float* v, float* ga, int64_t begin, int64_t n,
                               const AdamScalars s) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const FastDiv bc = make_fastdiv(s.bc2_sqrt);
     for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float P = p[i], M = m[i], V = v[i];
         const float G = g[i];
-        adam1(P, G, M, V, s);
+        adam1(P, G, M, V, s, bc);
         p[i] = P; m[i] = M; v[i] = V;
         if (HAS_ABS) ga[i] += fabsf(G);
         if (ZERO) g[i] = 0.f;

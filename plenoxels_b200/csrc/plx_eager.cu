@@ -333,6 +333,44 @@ __global__ void __launch_bounds__(CWARPS * 32) k_composite_bwd(const float4* __r
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// self-test of the hoisted exact arithmetic (plx_device.cuh) against the compiler's IEEE intrinsics
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return (uint32_t)((z ^ (z >> 31)) >> 16);
+}
+
+__global__ void __launch_bounds__(256) k_selftest(float y, uint64_t n, uint64_t seed, unsigned long long* bad) {
+    const FastDiv d = make_fastdiv(y);
+    unsigned b0 = 0, b1 = 0, b2 = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t h = mix32(seed * 0x100000001B3ull + i), h2 = mix32(~seed + 3 * i);
+        float x;
+        if (i & 1) {
+            x = ((float)(h & 0xffffff) / 16777216.f - 0.5f) * 1024.f;            // grid-coordinate-like magnitudes
+        } else {
+            const uint32_t e = 127 - 40 + (h2 % 80);                               // exponents 2^-40 .. 2^39
+            x = __uint_as_float(((h >> 8) & 0x80000000u) | (e << 23) | (h & 0x7fffff));
+        }
+        if (__float_as_uint(fdiv_exact(x, d)) != __float_as_uint(__fdiv_rn(x, y))) ++b0;
+        const float a = fabsf(x);
+        if (__float_as_uint(fsqrt_exact(a)) != __float_as_uint(__fsqrt_rn(a))) ++b1;
+        const float den = __uint_as_float((127 - 30 + (h2 >> 8) % 40) << 23 | (h2 & 0x7fffff));   // 2^-30 .. 2^9
+        if (__float_as_uint(fdiv_var(x, den)) != __float_as_uint(__fdiv_rn(x, den))) ++b2;
+    }
+    if (b0) atomicAdd(bad + 0, (unsigned long long)b0);
+    if (b1) atomicAdd(bad + 1, (unsigned long long)b1);
+    if (b2) atomicAdd(bad + 2, (unsigned long long)b2);
+}
+
+cudaError_t launch_selftest(float y, uint64_t n, uint64_t seed, unsigned long long* bad, cudaStream_t st) {
+    k_selftest<<<148 * 8, 256, 0, st>>>(y, n, seed, bad);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_composite_bwd(const float* samples, int64_t n_rays, int S, const float* grad_out, float* grad_samples,
                                  cudaStream_t st) {
     if (n_rays == 0 || S == 0) return cudaSuccess;

@@ -37,6 +37,7 @@ cudaError_t launch_trilinear_fwd(const float* ns, int64_t m, const float* grid, 
 cudaError_t launch_trilinear_bwd(const float* ns, int64_t m, const float* grad_vals, const int32_t* dims, int masked,
                                  float* grad_grid, cudaStream_t st);
 cudaError_t launch_composite_fwd(const float* samples, int64_t n_rays, int S, float* out, cudaStream_t st);
+cudaError_t launch_selftest(float y, uint64_t n, uint64_t seed, unsigned long long* bad, cudaStream_t st);
 cudaError_t launch_composite_bwd(const float* samples, int64_t n_rays, int S, const float* grad_out, float* grad_samples,
                                  cudaStream_t st);
 

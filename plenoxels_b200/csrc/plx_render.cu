@@ -5,40 +5,98 @@
 // (M,.) temporary: sample placement (src/ray_sampling.py:161-167), normalisation (:13), lookup through
 // clip(0,1) with the in-bounds mask (src/grid_functions.py:103-114 / :7-44,:220-246), compositing
 // (src/ray_sampling.py:181-191).
+//
+// Template axes:  MODE  nearest / trilinear lookup
+//                 FAST  contiguous 16-byte-aligned grid + divisor in the hoisted-reciprocal range: cells are addressed
+//                       by their linear index with one 128-bit load, the quotient costs 3 FMAs (plx_device.cuh);
+//                       !FAST = arbitrary strides (channel-planar pooled grids), scalar loads, __fdiv_rn
+//                 DBG   (forward only) full march for the per-ray count / per-sample index dump
+#include <cstdlib>
+
 #include "plx_device.cuh"
 #include "plx_launch.h"
 
 namespace plx {
 
-constexpr int WARPS_PER_BLOCK = 8;
-constexpr int THREADS = WARPS_PER_BLOCK * 32;
+constexpr int MAX_WARPS_PER_BLOCK = 8;
+
+// launch-invariant geometry, derived once per thread from the PlxMarch argument
+struct Geo {
+    float fnx, fny, fnz;     // grid dims as floats (the in-bounds test runs on the rounded float)
+    int ny, nz;
+    float gx, gy, gz, delta;
+    FastDiv div;
+    bool clamp;
+};
+
+__device__ __forceinline__ Geo make_geo(const PlxMarch& m) {
+    Geo g;
+    g.fnx = (float)m.nx; g.fny = (float)m.ny; g.fnz = (float)m.nz;
+    g.ny = m.ny; g.nz = m.nz;
+    g.gx = m.gmin[0]; g.gy = m.gmin[1]; g.gz = m.gmin[2];
+    g.delta = m.delta_step;
+    g.div = make_fastdiv(m.points_distance);
+    g.clamp = (m.flags & PLX_CLAMP01) != 0;
+    return g;
+}
+
+// every numerator of the ray stays below the hoisted-division range (tiny numerators only ever round to index 0)
+__device__ __forceinline__ bool ray_in_fast_range(const PlxMarch& m, const Ray& r) {
+    const float reach = fabsf(m.delta_step) * (float)m.num_samples;
+    const float big = fmaxf(fmaxf(fabsf(r.ox), fabsf(r.oy)), fabsf(r.oz)) +
+                      reach * fmaxf(fmaxf(fabsf(r.dx), fabsf(r.dy)), fabsf(r.dz)) +
+                      fmaxf(fmaxf(fabsf(m.gmin[0]), fabsf(m.gmin[1])), fabsf(m.gmin[2]));
+    return big <= 1e17f;      // false for NaN / inf too
+}
+
+template <bool FAST>
+__device__ __forceinline__ void norm3(const PlxMarch& m, const Geo& g, const Ray& r, bool fast_ray, float t, float& nx,
+                                      float& ny, float& nz) {
+    const float x = __fsub_rn(__fadd_rn(r.ox, __fmul_rn(r.dx, t)), g.gx);     // src/ray_sampling.py:167, :13
+    const float y = __fsub_rn(__fadd_rn(r.oy, __fmul_rn(r.dy, t)), g.gy);
+    const float z = __fsub_rn(__fadd_rn(r.oz, __fmul_rn(r.dz, t)), g.gz);
+    if (FAST && fast_ray) {
+        nx = fdiv_hoisted(x, g.div); ny = fdiv_hoisted(y, g.div); nz = fdiv_hoisted(z, g.div);
+    } else {
+        nx = __fdiv_rn(x, m.points_distance); ny = __fdiv_rn(y, m.points_distance); nz = __fdiv_rn(z, m.points_distance);
+    }
+}
+
+template <bool FAST>
+__device__ __forceinline__ float4 cell_at(const PlxMarch& m, const float* __restrict__ grid, int ix, int iy, int iz, int lin) {
+    if (FAST) return __ldg(reinterpret_cast<const float4*>(grid) + lin);
+    const int64_t off = ix * m.sx + iy * m.sy + iz * m.sz;
+    return make_float4(__ldg(grid + off), __ldg(grid + off + m.sc), __ldg(grid + off + 2 * m.sc), __ldg(grid + off + 3 * m.sc));
+}
+
+__device__ __forceinline__ float4 clamp4(float4 c) {
+    return make_float4(__saturatef(c.x), __saturatef(c.y), __saturatef(c.z), __saturatef(c.w));
+}
 
 // One sample's lookup result.
 struct Sample {
-    float4 c;        // (clamped) cell value, 0 when out of bounds
+    float4 c;        // (clamped) value, 0 when out of bounds
+    float4 raw;      // nearest mode: the unclamped cell (for the clip pass-mask)
     bool inb;        // the reference's mask (True = inside)
-    int64_t off;     // element offset of the (nearest / floor-corner) cell in the *strided* grid
-    int32_t lin;     // contiguous linear cell index (ix*ny+iy)*nz+iz of that cell, -1 when out of bounds
+    int lin;         // linear index (ix*ny+iy)*nz+iz of the nearest / floor-corner cell, -1 when out of bounds
 };
 
 // ---- nearest neighbour: src/grid_functions.py:111 (round half even), :58-61 (mask) -------------------------
-template <bool VEC>
-__device__ __forceinline__ Sample lookup_nearest(const PlxMarch& m, const float* __restrict__ grid, float nx, float ny,
-                                                 float nz, bool valid, bool need_value) {
+template <bool FAST>
+__device__ __forceinline__ Sample lookup_nearest(const PlxMarch& m, const Geo& g, const float* __restrict__ grid, float nx,
+                                                 float ny, float nz, bool valid, bool need_value) {
     Sample s;
     s.c = make_float4(0.f, 0.f, 0.f, 0.f);
+    s.raw = s.c;
     const float rx = rintf(nx), ry = rintf(ny), rz = rintf(nz);
-    s.inb = valid && rx >= 0.f && rx < (float)m.nx && ry >= 0.f && ry < (float)m.ny && rz >= 0.f && rz < (float)m.nz;
-    s.off = 0;
+    s.inb = valid && rx >= 0.f && rx < g.fnx && ry >= 0.f && ry < g.fny && rz >= 0.f && rz < g.fnz;
     s.lin = -1;
     if (s.inb) {
         const int ix = (int)rx, iy = (int)ry, iz = (int)rz;
-        s.lin = (ix * m.ny + iy) * m.nz + iz;
-        s.off = ix * m.sx + iy * m.sy + iz * m.sz;
+        s.lin = (ix * g.ny + iy) * g.nz + iz;
         if (need_value) {
-            float4 c = load_cell<VEC>(grid, s.off, m.sc);
-            if (m.flags & PLX_CLAMP01) { c.x = clamp01(c.x); c.y = clamp01(c.y); c.z = clamp01(c.z); c.w = clamp01(c.w); }
-            s.c = c;
+            s.raw = cell_at<FAST>(m, grid, ix, iy, iz, s.lin);
+            s.c = g.clamp ? clamp4(s.raw) : s.raw;
         }
     }
     return s;
@@ -50,20 +108,20 @@ struct TriGeom {
     float f[3];           // frac per axis
 };
 
-__device__ __forceinline__ bool tri_geom(const PlxMarch& m, float nx, float ny, float nz, TriGeom& g) {
+__device__ __forceinline__ bool tri_geom(const Geo& g, float nx, float ny, float nz, TriGeom& t) {
     const float n[3] = {nx, ny, nz};
-    const int dim[3] = {m.nx, m.ny, m.nz};
+    const float dim[3] = {g.fnx, g.fny, g.fnz};
     bool inb = true;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) inb = inb && (n[a] >= 0.f) && (n[a] < (float)dim[a]);   // float test, :58-61
+    for (int a = 0; a < 3; ++a) inb = inb && (n[a] >= 0.f) && (n[a] < dim[a]);      // float test, :58-61
     if (!inb) return false;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const float fl = floorf(n[a]);
-        g.lo[a] = (int)fl;
-        int hi = (int)ceilf(n[a]);
-        g.hi[a] = hi >= dim[a] ? hi - dim[a] : hi;            // periodic wrap of the ceil corner, :75-77
-        g.f[a] = __fsub_rn(n[a], fl);                          // torch.frac for n >= 0, :29
+        const float ce = ceilf(n[a]);
+        t.lo[a] = (int)fl;
+        t.hi[a] = ce >= dim[a] ? 0 : (int)ce;                  // periodic wrap of the ceil corner, :75-77
+        t.f[a] = __fsub_rn(n[a], fl);                          // torch.frac for n >= 0, :29
     }
     return true;
 }
@@ -76,69 +134,64 @@ __device__ __forceinline__ float4 lerp4(float4 hi, float4 lo, float f) {
     return make_float4(lerp_ref(hi.x, lo.x, f), lerp_ref(hi.y, lo.y, f), lerp_ref(hi.z, lo.z, f), lerp_ref(hi.w, lo.w, f));
 }
 
-template <bool VEC>
-__device__ __forceinline__ float4 tri_cell(const PlxMarch& m, const float* __restrict__ grid, int ix, int iy, int iz) {
-    float4 c = load_cell<VEC>(grid, ix * m.sx + iy * m.sy + iz * m.sz, m.sc);
-    if (m.flags & PLX_CLAMP01) { c.x = clamp01(c.x); c.y = clamp01(c.y); c.z = clamp01(c.z); c.w = clamp01(c.w); }
-    return c;
+template <bool FAST>
+__device__ __forceinline__ float4 tri_cell(const PlxMarch& m, const Geo& g, const float* __restrict__ grid, int ix, int iy, int iz) {
+    const float4 c = cell_at<FAST>(m, grid, ix, iy, iz, (ix * g.ny + iy) * g.nz + iz);
+    return g.clamp ? clamp4(c) : c;
 }
 
-template <bool VEC>
-__device__ __forceinline__ float4 tri_interp(const PlxMarch& m, const float* __restrict__ grid, const TriGeom& g) {
+template <bool FAST>
+__device__ __forceinline__ float4 tri_interp(const PlxMarch& m, const Geo& g, const float* __restrict__ grid, const TriGeom& t) {
     // x-lerp of the four (y,z) edges, then y, then z — corner order of src/grid_functions.py:238-243
-    float4 x_cc = lerp4(tri_cell<VEC>(m, grid, g.hi[0], g.hi[1], g.hi[2]), tri_cell<VEC>(m, grid, g.lo[0], g.hi[1], g.hi[2]), g.f[0]);
-    float4 x_cf = lerp4(tri_cell<VEC>(m, grid, g.hi[0], g.hi[1], g.lo[2]), tri_cell<VEC>(m, grid, g.lo[0], g.hi[1], g.lo[2]), g.f[0]);
-    float4 x_fc = lerp4(tri_cell<VEC>(m, grid, g.hi[0], g.lo[1], g.hi[2]), tri_cell<VEC>(m, grid, g.lo[0], g.lo[1], g.hi[2]), g.f[0]);
-    float4 x_ff = lerp4(tri_cell<VEC>(m, grid, g.hi[0], g.lo[1], g.lo[2]), tri_cell<VEC>(m, grid, g.lo[0], g.lo[1], g.lo[2]), g.f[0]);
-    float4 y_c = lerp4(x_cc, x_fc, g.f[1]);
-    float4 y_f = lerp4(x_cf, x_ff, g.f[1]);
-    return lerp4(y_c, y_f, g.f[2]);
+    const float4 x_cc = lerp4(tri_cell<FAST>(m, g, grid, t.hi[0], t.hi[1], t.hi[2]), tri_cell<FAST>(m, g, grid, t.lo[0], t.hi[1], t.hi[2]), t.f[0]);
+    const float4 x_cf = lerp4(tri_cell<FAST>(m, g, grid, t.hi[0], t.hi[1], t.lo[2]), tri_cell<FAST>(m, g, grid, t.lo[0], t.hi[1], t.lo[2]), t.f[0]);
+    const float4 x_fc = lerp4(tri_cell<FAST>(m, g, grid, t.hi[0], t.lo[1], t.hi[2]), tri_cell<FAST>(m, g, grid, t.lo[0], t.lo[1], t.hi[2]), t.f[0]);
+    const float4 x_ff = lerp4(tri_cell<FAST>(m, g, grid, t.hi[0], t.lo[1], t.lo[2]), tri_cell<FAST>(m, g, grid, t.lo[0], t.lo[1], t.lo[2]), t.f[0]);
+    const float4 y_c = lerp4(x_cc, x_fc, t.f[1]);
+    const float4 y_f = lerp4(x_cf, x_ff, t.f[1]);
+    return lerp4(y_c, y_f, t.f[2]);
 }
 
-template <bool VEC>
-__device__ __forceinline__ Sample lookup_trilinear(const PlxMarch& m, const float* __restrict__ grid, float nx, float ny,
-                                                   float nz, bool valid, bool need_value, TriGeom& g) {
+template <int MODE, bool FAST>
+__device__ __forceinline__ Sample lookup(const PlxMarch& m, const Geo& g, const float* __restrict__ grid, const Ray& r,
+                                         bool fast_ray, int k, bool valid, bool need_value, float& t, TriGeom& tg) {
+    t = __fmul_rn(g.delta, (float)k);                                       // src/ray_sampling.py:161
+    float nx, ny, nz;
+    norm3<FAST>(m, g, r, fast_ray, t, nx, ny, nz);
+    if (MODE == PLX_NEAREST) return lookup_nearest<FAST>(m, g, grid, nx, ny, nz, valid, need_value);
     Sample s;
     s.c = make_float4(0.f, 0.f, 0.f, 0.f);
-    s.off = 0;
+    s.raw = s.c;
     s.lin = -1;
-    s.inb = valid && tri_geom(m, nx, ny, nz, g);
+    s.inb = valid && tri_geom(g, nx, ny, nz, tg);
     if (s.inb) {
-        s.lin = (g.lo[0] * m.ny + g.lo[1]) * m.nz + g.lo[2];
-        if (need_value) s.c = tri_interp<VEC>(m, grid, g);
+        s.lin = (tg.lo[0] * g.ny + tg.lo[1]) * g.nz + tg.lo[2];
+        if (need_value) s.c = tri_interp<FAST>(m, g, grid, tg);
     }
     return s;
-}
-
-template <int MODE, bool VEC>
-__device__ __forceinline__ Sample lookup(const PlxMarch& m, const float* __restrict__ grid, const Ray& r, int k, bool valid,
-                                         bool need_value, float& t, TriGeom& g) {
-    t = step_t(m.delta_step, k);
-    const float nx = norm_coord(r.ox, r.dx, t, m.gmin[0], m.points_distance);
-    const float ny = norm_coord(r.oy, r.dy, t, m.gmin[1], m.points_distance);
-    const float nz = norm_coord(r.oz, r.dz, t, m.gmin[2], m.points_distance);
-    if (MODE == PLX_NEAREST) return lookup_nearest<VEC>(m, grid, nx, ny, nz, valid, need_value);
-    return lookup_trilinear<VEC>(m, grid, nx, ny, nz, valid, need_value, g);
 }
 
 // =================================================================================================================
 // K1 — forward
 // =================================================================================================================
-template <int MODE, bool VEC>
-__global__ void __launch_bounds__(THREADS) k_render_fwd(const PlxRenderFwd a) {
-    __shared__ float s_loss[WARPS_PER_BLOCK];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t ray = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wib;
+template <int MODE, bool FAST, bool DBG>
+__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) k_render_fwd(const PlxRenderFwd a) {
+    __shared__ float s_loss[MAX_WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int64_t ray = (int64_t)blockIdx.x * wpb + wib;
     const PlxMarch& m = a.march;
     float ray_loss = 0.f;
     if (ray < a.rays.n_rays) {
+        const Geo g = make_geo(m);
         const Ray r = load_ray(a.rays, ray);
-        const bool dump = a.sample_index != nullptr;
-        const bool full = dump || a.count != nullptr || (m.flags & PLX_NO_EARLY_STOP);
+        const bool fast_ray = FAST && ray_in_fast_range(m, r);
+        const bool dump = DBG && a.sample_index != nullptr;
+        const bool full = DBG;                 // count / dump / PLX_NO_EARLY_STOP: march to the end of the range
         int k0, k1;
         clip_range(m, r, k0, k1);
         if (dump) { k0 = 1; k1 = m.num_samples; }
         const int nch_all = num_chunks(m.num_samples);
+        float* tc = a.tcarry ? a.tcarry + ray * nch_all : nullptr;
         float T = 1.f;                       // transmittance in front of the current chunk
         float ar = 0.f, ag = 0.f, ab = 0.f, aa = 0.f, ad = 0.f;
         int cnt = 0;
@@ -147,12 +200,14 @@ __global__ void __launch_bounds__(THREADS) k_render_fwd(const PlxRenderFwd a) {
         for (int kb = k0; kb <= k1; kb += CHUNK, ++c) {
             const int k = kb + lane;
             const bool valid = k <= k1;
-            if (a.tcarry && lane == 0) a.tcarry[ray * nch_all + c] = T;
+            if (tc && lane == 0) tc[c] = T;
             float t;
-            TriGeom g;
-            const Sample s = lookup<MODE, VEC>(m, a.grid, r, k, valid, alive, t, g);
-            cnt += s.inb ? 1 : 0;
-            if (dump && valid) a.sample_index[ray * (int64_t)m.num_samples + (k - 1)] = s.lin;
+            TriGeom tg;
+            const Sample s = lookup<MODE, FAST>(m, g, a.grid, r, fast_ray, k, valid, alive, t, tg);
+            if (DBG) {
+                cnt += s.inb ? 1 : 0;
+                if (dump && valid) a.sample_index[ray * (int64_t)m.num_samples + (k - 1)] = s.lin;
+            }
             if (alive) {
                 float total;
                 const float ex = warp_excl_prod(1.f - s.c.w, lane, total);
@@ -167,19 +222,19 @@ __global__ void __launch_bounds__(THREADS) k_render_fwd(const PlxRenderFwd a) {
                 }
             }
         }
-        if (a.tcarry) {                      // chunks never reached carry zero transmittance (or are unused)
-            for (int cc = c + lane; cc < nch_all; cc += 32) a.tcarry[ray * nch_all + cc] = alive ? T : 0.f;
+        if (tc) {                            // chunks never reached carry zero transmittance (or are unused)
+            for (int cc = c + lane; cc < nch_all; cc += 32) tc[cc] = alive ? T : 0.f;
         }
         ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); aa = warp_sum(aa);
         if (a.depth) ad = warp_sum(ad);
-        if (a.count) cnt = warp_sum_int(cnt);
+        if (DBG && a.count) cnt = warp_sum_int(cnt);
         if (lane == 0) {
             reinterpret_cast<float4*>(a.rgba)[ray] = make_float4(ar, ag, ab, aa);
             if (a.depth) a.depth[ray] = ad;
-            if (a.count) a.count[ray] = cnt;
+            if (DBG && a.count) a.count[ray] = cnt;
             if (a.targets) {                 // mean-MSE over N*4 incl. alpha, scripts/train.py:156
-                const float4 tg = __ldg(reinterpret_cast<const float4*>(a.targets) + ray);
-                const float dr = ar - tg.x, dg = ag - tg.y, db = ab - tg.z, da = aa - tg.w;
+                const float4 tgt = __ldg(reinterpret_cast<const float4*>(a.targets) + ray);
+                const float dr = ar - tgt.x, dg = ag - tgt.y, db = ab - tgt.z, da = aa - tgt.w;
                 reinterpret_cast<float4*>(a.grad_rgba)[ray] =
                     make_float4(dr * a.grad_scale, dg * a.grad_scale, db * a.grad_scale, da * a.grad_scale);
                 ray_loss = (dr * dr + dg * dg + db * db + da * da) * a.loss_scale;
@@ -191,8 +246,7 @@ __global__ void __launch_bounds__(THREADS) k_render_fwd(const PlxRenderFwd a) {
         __syncthreads();
         if (threadIdx.x == 0) {
             float sum = 0.f;
-#pragma unroll
-            for (int i = 0; i < WARPS_PER_BLOCK; ++i) sum += s_loss[i];
+            for (int i = 0; i < wpb; ++i) sum += s_loss[i];
             atomicAdd(a.loss, sum);
         }
     }
@@ -201,17 +255,19 @@ __global__ void __launch_bounds__(THREADS) k_render_fwd(const PlxRenderFwd a) {
 // =================================================================================================================
 // K2 — backward
 // =================================================================================================================
-template <int MODE, bool VEC>
-__global__ void __launch_bounds__(THREADS) k_render_bwd(const PlxRenderBwd a) {
-    extern __shared__ float s_tc[];          // [WARPS_PER_BLOCK][nch_all], only used when a.tcarry == NULL
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t ray = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wib;
+template <int MODE, bool FAST>
+__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) k_render_bwd(const PlxRenderBwd a) {
+    extern __shared__ float s_tc[];          // [warps per block][nch_all], only used when a.tcarry == NULL
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int64_t ray = (int64_t)blockIdx.x * wpb + wib;
     const PlxMarch& m = a.march;
     if (ray >= a.rays.n_rays) return;
-    const float4 g = __ldg(reinterpret_cast<const float4*>(a.grad_rgba) + ray);
+    const float4 gr = __ldg(reinterpret_cast<const float4*>(a.grad_rgba) + ray);
     const float bom = a.beta_over_m;
-    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f && bom == 0.f) return;
+    if (gr.x == 0.f && gr.y == 0.f && gr.z == 0.f && gr.w == 0.f && bom == 0.f) return;
+    const Geo g = make_geo(m);
     const Ray r = load_ray(a.rays, ray);
+    const bool fast_ray = FAST && ray_in_fast_range(m, r);
     int k0, k1;
     clip_range(m, r, k0, k1);
     if (k0 > k1) return;
@@ -231,7 +287,7 @@ __global__ void __launch_bounds__(THREADS) k_render_bwd(const PlxRenderBwd a) {
                 const int k = k0 + c * CHUNK + lane;
                 float t;
                 TriGeom tg;
-                const Sample s = lookup<MODE, VEC>(m, a.grid, r, k, k <= k1, true, t, tg);
+                const Sample s = lookup<MODE, FAST>(m, g, a.grid, r, fast_ray, k, k <= k1, true, t, tg);
                 float f = 1.f - s.c.w;
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) f *= __shfl_xor_sync(FULL, f, d);
@@ -250,22 +306,19 @@ __global__ void __launch_bounds__(THREADS) k_render_bwd(const PlxRenderBwd a) {
         const float Tc = tc[c];
         float t;
         TriGeom tg;
-        const Sample s = lookup<MODE, VEC>(m, a.grid, r, k, valid, true, t, tg);
+        const Sample s = lookup<MODE, FAST>(m, g, a.grid, r, fast_ray, k, valid, true, t, tg);
         const float alpha = s.c.w;
-        const float v = fmaf(s.c.x, g.x, fmaf(s.c.y, g.y, fmaf(s.c.z, g.z, g.w)));     // c_k . g_rgb + g_A
+        const float v = fmaf(s.c.x, gr.x, fmaf(s.c.y, gr.y, fmaf(s.c.z, gr.z, gr.w)));     // c_k . g_rgb + g_A
         const float behind = warp_behind(alpha * v, 1.f - alpha, lane, behind_carry);
         if (Tc == 0.f && bom == 0.f) continue;               // every T_k of this chunk is 0: no gradient here
         float total;
         const float Tk = Tc * warp_excl_prod(1.f - alpha, lane, total);
         const float wgt = alpha * Tk;
-        float dr = wgt * g.x, dg = wgt * g.y, db = wgt * g.z;
+        float dr = wgt * gr.x, dg = wgt * gr.y, db = wgt * gr.z;
         float da = Tk * (v - behind);
         if (bom != 0.f) da += bom * (1.f / (alpha + 1e-4f) + 1.f / (1.f - alpha + 1e-4f));   // scripts/train.py:170-177
         if (MODE == PLX_NEAREST) {
-            if (s.inb && (m.flags & PLX_CLAMP01)) {
-                const float4 raw = load_cell<VEC>(a.grid, s.off, m.sc);
-                dr *= pass01(raw.x); dg *= pass01(raw.y); db *= pass01(raw.z); da *= pass01(raw.w);
-            }
+            if (g.clamp) { dr *= pass01(s.raw.x); dg *= pass01(s.raw.y); db *= pass01(s.raw.z); da *= pass01(s.raw.w); }
             warp_scatter_add(a.grad_grid, s.inb, (int64_t)s.lin * 4, dr, dg, db, da, lane);
         } else {
             if (s.inb && (dr != 0.f || dg != 0.f || db != 0.f || da != 0.f)) {
@@ -276,13 +329,13 @@ __global__ void __launch_bounds__(THREADS) k_render_bwd(const PlxRenderBwd a) {
                     const float w = (cx ? 1.f - tg.f[0] : tg.f[0]) * (cy ? 1.f - tg.f[1] : tg.f[1]) *
                                     (cz ? 1.f - tg.f[2] : tg.f[2]);
                     if (w == 0.f) continue;
+                    const int lin = (ix * g.ny + iy) * g.nz + iz;
                     float px = 1.f, py = 1.f, pz = 1.f, pw = 1.f;
-                    if (m.flags & PLX_CLAMP01) {
-                        const float4 raw = load_cell<VEC>(a.grid, ix * m.sx + iy * m.sy + iz * m.sz, m.sc);
+                    if (g.clamp) {
+                        const float4 raw = cell_at<FAST>(m, a.grid, ix, iy, iz, lin);
                         px = pass01(raw.x); py = pass01(raw.y); pz = pass01(raw.z); pw = pass01(raw.w);
                     }
-                    const int64_t lin = ((int64_t)ix * m.ny + iy) * m.nz + iz;
-                    red_add_v4(a.grad_grid + lin * 4, dr * w * px, dg * w * py, db * w * pz, da * w * pw);
+                    red_add_v4(a.grad_grid + (int64_t)lin * 4, dr * w * px, dg * w * py, db * w * pz, da * w * pw);
                 }
             }
         }
@@ -292,42 +345,57 @@ __global__ void __launch_bounds__(THREADS) k_render_bwd(const PlxRenderBwd a) {
 // =================================================================================================================
 // launchers
 // =================================================================================================================
-static inline bool vec_ok(const PlxMarch& m, const float* grid) {
-    return m.sc == 1 && (m.sx % 4 == 0) && (m.sy % 4 == 0) && (m.sz % 4 == 0) && ((uintptr_t)grid % 16 == 0);
+static inline bool fast_ok(const PlxMarch& m, const float* grid) {
+    return m.sc == 1 && m.sz == 4 && m.sy == 4 * (int64_t)m.nz && m.sx == 4 * (int64_t)m.nz * m.ny &&
+           ((uintptr_t)grid % 16 == 0) && fastdiv_ok(m.points_distance);
+}
+
+static int warps_per_block(const char* env, int dflt) {
+    const char* e = std::getenv(env);
+    if (e) {
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= MAX_WARPS_PER_BLOCK) return v;
+    }
+    return dflt;
 }
 
 cudaError_t launch_render_fwd(const PlxRenderFwd& a, cudaStream_t st) {
     if (a.rays.n_rays == 0) return cudaSuccess;
-    const unsigned blocks = (unsigned)((a.rays.n_rays + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    const bool vec = vec_ok(a.march, a.grid);
-    if (a.march.mode == PLX_NEAREST) {
-        if (vec) k_render_fwd<PLX_NEAREST, true><<<blocks, THREADS, 0, st>>>(a);
-        else     k_render_fwd<PLX_NEAREST, false><<<blocks, THREADS, 0, st>>>(a);
-    } else {
-        if (vec) k_render_fwd<PLX_TRILINEAR, true><<<blocks, THREADS, 0, st>>>(a);
-        else     k_render_fwd<PLX_TRILINEAR, false><<<blocks, THREADS, 0, st>>>(a);
-    }
+    static const int wpb = warps_per_block("PLX_FWD_WPB", 4);
+    const unsigned blocks = (unsigned)((a.rays.n_rays + wpb - 1) / wpb);
+    const bool fast = fast_ok(a.march, a.grid);
+    const bool dbg = a.count || a.sample_index || (a.march.flags & PLX_NO_EARLY_STOP);
+#define PLX_FWD(MODE)                                                                                     \
+    do {                                                                                                  \
+        if (fast) { if (dbg) k_render_fwd<MODE, true, true><<<blocks, wpb * 32, 0, st>>>(a);              \
+                    else     k_render_fwd<MODE, true, false><<<blocks, wpb * 32, 0, st>>>(a); }           \
+        else      { if (dbg) k_render_fwd<MODE, false, true><<<blocks, wpb * 32, 0, st>>>(a);             \
+                    else     k_render_fwd<MODE, false, false><<<blocks, wpb * 32, 0, st>>>(a); }          \
+    } while (0)
+    if (a.march.mode == PLX_NEAREST) PLX_FWD(PLX_NEAREST); else PLX_FWD(PLX_TRILINEAR);
+#undef PLX_FWD
     return cudaGetLastError();
 }
 
 cudaError_t launch_render_bwd(const PlxRenderBwd& a, cudaStream_t st) {
     if (a.rays.n_rays == 0) return cudaSuccess;
-    const unsigned blocks = (unsigned)((a.rays.n_rays + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    const size_t smem = a.tcarry ? 0 : (size_t)WARPS_PER_BLOCK * num_chunks(a.march.num_samples) * sizeof(float);
-    const bool vec = vec_ok(a.march, a.grid);
-#define PLX_BWD(MODE, VEC)                                                                                            \
-    do {                                                                                                              \
-        if (smem > 48 * 1024) {                                                                                       \
-            cudaError_t e = cudaFuncSetAttribute(k_render_bwd<MODE, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                 (int)smem);                                                          \
-            if (e != cudaSuccess) return e;                                                                           \
-        }                                                                                                             \
-        k_render_bwd<MODE, VEC><<<blocks, THREADS, smem, st>>>(a);                                                   \
+    static const int wpb = warps_per_block("PLX_BWD_WPB", 4);
+    const unsigned blocks = (unsigned)((a.rays.n_rays + wpb - 1) / wpb);
+    const size_t smem = a.tcarry ? 0 : (size_t)wpb * num_chunks(a.march.num_samples) * sizeof(float);
+    const bool fast = fast_ok(a.march, a.grid);
+#define PLX_BWD(MODE, FASTP)                                                                                            \
+    do {                                                                                                                \
+        if (smem > 48 * 1024) {                                                                                         \
+            cudaError_t e = cudaFuncSetAttribute(k_render_bwd<MODE, FASTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                 (int)smem);                                                            \
+            if (e != cudaSuccess) return e;                                                                             \
+        }                                                                                                               \
+        k_render_bwd<MODE, FASTP><<<blocks, wpb * 32, smem, st>>>(a);                                                  \
     } while (0)
     if (a.march.mode == PLX_NEAREST) {
-        if (vec) PLX_BWD(PLX_NEAREST, true); else PLX_BWD(PLX_NEAREST, false);
+        if (fast) PLX_BWD(PLX_NEAREST, true); else PLX_BWD(PLX_NEAREST, false);
     } else {
-        if (vec) PLX_BWD(PLX_TRILINEAR, true); else PLX_BWD(PLX_TRILINEAR, false);
+        if (fast) PLX_BWD(PLX_TRILINEAR, true); else PLX_BWD(PLX_TRILINEAR, false);
     }
 #undef PLX_BWD
     return cudaGetLastError();

@@ -15,12 +15,13 @@ from . import _lib as L
 
 
 # --------------------------------------------------------------------------------------------- geometry helpers
-def grid_origin(dims, points_distance: float, start_index: int = 0):
-    """World coordinate of cell (start_index,)*3 as three fp32 values, computed on the host exactly as
+def grid_origin(dims, points_distance: float, start_index=0):
+    """World coordinate of cell `start_index` (an int or one int per axis) as three fp32 values, computed on the host exactly as
     `generate_grid` builds them (src/grid_functions.py:205-209): fl32(i - ceil(s/2) + 1) * fl32(pd).
     Equals `grid_indices.min(0)[0]` of src/ray_sampling.py:13 for pd > 0 without the (G^3,3) reduction."""
     pd32 = np.float32(points_distance)
-    return tuple(float(np.float32(start_index - math.ceil(int(s) / 2) + 1) * pd32) for s in dims[:3])
+    starts = (start_index,) * 3 if isinstance(start_index, int) else tuple(start_index)
+    return tuple(float(np.float32(int(i) - math.ceil(int(s) / 2) + 1) * pd32) for i, s in zip(starts, dims[:3]))
 
 
 # --------------------------------------------------------------------------------------------- fused march (K1 / K2)

@@ -90,6 +90,26 @@ def test_backward_without_saved_carry_matches(case):
     assert rel_err(gg.cpu().numpy(), grid.grad.cpu().numpy()) <= 2e-6
 
 
+@pytest.mark.parametrize("mode", ["nearest", "trilinear"])
+def test_channel_planar_grid_matches_contiguous(case, mode):
+    """Pooled grids reach the lookup channel-planar: the strided path must give the contiguous result
+    and route the gradient back through the view."""
+    d = case.cuda()
+    planar = d["grid"].permute(3, 0, 1, 2).contiguous().requires_grad_(True)       # (4,X,Y,Z) storage
+    view = planar.permute(1, 2, 3, 0)                                              # (X,Y,Z,4) with strides (YZ, Z, 1, XYZ)
+    assert not view.is_contiguous()
+    a = ops.render_rays(view, d["origins"], d["dirs"], case.S, case.delta, case.gmin, case.pd, mode=mode,
+                        rays_per_origin=case.R)
+    g = torch.randn_like(a)
+    a.backward(g)
+    ref = d["grid"].clone().requires_grad_(True)
+    b = ops.render_rays(ref, d["origins"], d["dirs"], case.S, case.delta, case.gmin, case.pd, mode=mode,
+                        rays_per_origin=case.R)
+    b.backward(g)
+    assert rel_err(a.detach().cpu().numpy(), b.detach().cpu().numpy()) <= 2e-6
+    assert rel_err(planar.grad.permute(1, 2, 3, 0).cpu().numpy(), ref.grad.cpu().numpy()) <= 2e-6
+
+
 def test_generate_rays_matches_oracle(case):
     d = case.cuda()
     dirs, targets = ops.generate_rays(d["imgs"], d["poses"], case.fov, uv=d["uv"])
@@ -156,6 +176,15 @@ def test_eager_chain_autograd_matches_fused(case):
     torch.nn.functional.mse_loss(pix2, d["targets"]).backward()
     assert rel_err(pix.detach().cpu().numpy(), pix2.detach().cpu().numpy()) <= 2e-6
     assert rel_err(g1.grad.cpu().numpy(), g2.grad.cpu().numpy()) <= 2e-6
+
+
+@pytest.mark.parametrize("pd", [0.0125, 0.025, 0.05, 0.00625, 3.2 / 24, 3.2 / 93, 0.1 * 4, 1.0, 7.3e-4])
+def test_selftest_exact_arithmetic(plx_lib, pd):
+    """The hoisted-reciprocal quotient, inlined sqrt and per-element quotient are bit-identical to __fdiv_rn/__fsqrt_rn."""
+    bad = torch.zeros(3, dtype=torch.int64, device="cuda")
+    from plenoxels_b200 import _lib as L
+    L.check(plx_lib.plx_selftest_arith(pd, 1 << 26, 12345, bad.data_ptr(), L.stream_ptr(bad.device)))
+    assert bad.tolist() == [0, 0, 0], f"mismatches (div, sqrt, var-div) = {bad.tolist()}"
 
 
 def test_adam_step_matches_oracle():

@@ -275,37 +275,48 @@ def run_gpu_arm(args):
     tr3 = new_trainer()
     lib = _lib.load()
     st = _lib.stream_ptr(dev)
-    names = ["generate_rays", "render_fwd", "render_bwd", "adam"]
+    fused = os.environ.get("PLX_TRAIN_FUSED", "1") != "0"
+    names = ["render_train", "adam"] if fused else ["generate_rays", "render_fwd", "render_bwd", "adam"]
     n_inst = min(K, 64)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(n_inst)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(n_inst)]
     a = tr3._args
-    fwd, bwd = _lib.PlxRenderFwd(), _lib.PlxRenderBwd()
+    fwd, bwd, trn = _lib.PlxRenderFwd(), _lib.PlxRenderBwd(), _lib.PlxRenderTrain()
     rays = _lib.make_rays(tr3.poses[:, :3, 3], tr3.dirs, R)
+    gs, ls = 2.0 / (4.0 * n_rays * world), 1.0 / (4.0 * n_rays * world)
     fwd.march, fwd.rays, fwd.grid, fwd.rgba, fwd.tcarry = a.march, rays, a.grid, a.rgba, a.tcarry
     fwd.targets, fwd.grad_rgba, fwd.loss = a.targets, a.grad_rgba, a.loss
-    fwd.grad_scale, fwd.loss_scale = 2.0 / (4.0 * n_rays * world), 1.0 / (4.0 * n_rays * world)
+    fwd.grad_scale, fwd.loss_scale = gs, ls
     bwd.march, bwd.rays, bwd.grid, bwd.grad_rgba, bwd.tcarry, bwd.grad_grid = a.march, rays, a.grid, a.grad_rgba, a.tcarry, a.grad
+    trn.march, trn.grid, trn.grad_grid, trn.rgba, trn.loss = a.march, a.grid, a.grad, a.rgba, a.loss
+    trn.rays.n_rays = n_rays
+    trn.gen.imgs, trn.gen.n_cams, trn.gen.img_h, trn.gen.img_w = a.imgs, a.n_cams, a.img_h, a.img_w
+    trn.gen.poses, trn.gen.fov, trn.gen.rays_per_cam = a.poses, a.fov, R
+    trn.grad_scale, trn.loss_scale = gs, ls
     for w_ in range(3):
         tr3.step(uv_dev[w_ % n_batches])
     sampler.start()
     for i in range(n_inst):
         u = uv_dev[(W + i) % n_batches]
         ev = evs[i]
-        ev[0].record()
-        _lib.check(lib.plx_generate_rays(a.imgs, a.n_cams, a.img_h, a.img_w, a.poses, a.fov, u.data_ptr(), R, 0, a.dirs,
-                                         a.targets, st))
-        ev[1].record()
         tr3.loss.zero_()
-        _lib.check(lib.plx_render_fwd(C.byref(fwd), st))
-        ev[2].record()
-        _lib.check(lib.plx_render_bwd(C.byref(bwd), st))
-        ev[3].record()
+        ev[0].record()
+        if fused:
+            trn.gen.uv = u.data_ptr()
+            _lib.check(lib.plx_render_train(C.byref(trn), st))
+        else:
+            _lib.check(lib.plx_generate_rays(a.imgs, a.n_cams, a.img_h, a.img_w, a.poses, a.fov, u.data_ptr(), R, 0, a.dirs,
+                                             a.targets, st))
+            ev[1].record()
+            _lib.check(lib.plx_render_fwd(C.byref(fwd), st))
+            ev[2].record()
+            _lib.check(lib.plx_render_bwd(C.byref(bwd), st))
+        ev[-2].record()
         if world > 1:
             dist.all_reduce(tr3.grad)
         tr3.step_count += 1
         _lib.check(lib.plx_adam_step(a.grid, a.grad, a.exp_avg, a.exp_avg_sq, a.grad_abs_sum, cells * 4, sc.lr, 0.9, 0.999,
                                      1e-8, tr3.step_count, 1, st))
-        ev[4].record()
+        ev[-1].record()
     torch.cuda.synchronize(dev)
     sampler.stop()
     kms = {n: float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(n_inst)])) for j, n in enumerate(names)}
@@ -316,7 +327,7 @@ def run_gpu_arm(args):
     # ---- roofline of the dominant kernel + of the whole step (SURVEY.md §8d byte model)
     peak, peak_src = measured_peak()
     alg = {"generate_rays": 8.0 * n_rays + 28.0 * n_rays, "render_fwd": 16.0 * m_in + 40.0 * n_rays,
-           "render_bwd": 48.0 * m_in + 56.0 * n_rays, "adam": 160.0 * cells}
+           "render_bwd": 48.0 * m_in + 56.0 * n_rays, "render_train": 64.0 * m_in + 96.0 * n_rays, "adam": 160.0 * cells}
     timed = {k: v for k, v in kms.items() if v}
     dom = max(timed, key=timed.get)
     achieved = alg[dom] / (timed[dom] * 1e-3) / 1e9
@@ -359,7 +370,7 @@ def run_gpu_arm(args):
                     "ms_per_step": 1e3 * e2e_s / K,
                     "note": "uv draw copied from pinned host memory and loss read back + stream-synchronised every step; "
                             "images/poses/grid stay resident as in the reference (scripts/train.py:75)"},
-            "gpu_launches": 4 * K,
+            "gpu_launches": len(names) * K,
             "clocks": sampler.summary(),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -126,6 +126,34 @@ typedef struct PlxRenderBwd {
 int plx_render_bwd(const PlxRenderBwd* args, void* stream);
 
 /*
+ * K12 — fused training march (nearest lookup + mean-MSE): per ray, in one kernel,
+ *   [generate the ray from (pose, uv)] -> forward march -> MSE gradient -> reverse march -> scatter-add into grad_grid.
+ * Equivalent to plx_generate_rays + plx_render_fwd (MSE epilogue) + plx_render_bwd, i.e. scripts/train.py:130-157 + :181,
+ * without the intermediate (N,.) buffers.  Rays come either from `rays` + `targets` (gen.uv == NULL) or are generated
+ * in the kernel from gen.{imgs,poses,fov,uv} (src/ray_sampling.py:212-264; origins = poses[:, :3, 3]); then
+ * rays.n_rays must equal gen.n_cams * gen.rays_per_cam.  `rgba` (n_rays,4) is optional.  loss[0] is accumulated into.
+ * Returns PLX_E_UNSUPPORTED for trilinear mode or when num_samples exceeds the shared-memory index cache
+ * (use K1 + K2 then; plx_train_step does that automatically).
+ */
+typedef struct PlxRayGen {
+    const float* imgs; int32_t n_cams, img_h, img_w;
+    const float* poses; float fov;
+    const float* uv; int32_t rays_per_cam;
+} PlxRayGen;
+typedef struct PlxRenderTrain {
+    PlxMarch march;
+    PlxRays rays;
+    const float* targets;
+    PlxRayGen gen;
+    const float* grid;
+    float* grad_grid;
+    float* rgba;
+    float* loss;
+    float grad_scale, loss_scale, beta_over_m;
+} PlxRenderTrain;
+int plx_render_train(const PlxRenderTrain* args, void* stream);
+
+/*
  * K3 — optimiser: one torch.optim.Adam step over n fp32 values (torch/optim/adam.py `_single_tensor_adam`, as used
  * at scripts/train.py:89,:180-182) fused with `grid_grad += |grad|` (:184) and, with zero_grad != 0, clearing `g` for
  * the next step (:180).  Scalars are formed in double like the Python code (bias corrections 1 - beta^step).

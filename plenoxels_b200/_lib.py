@@ -48,6 +48,17 @@ class PlxRenderBwd(C.Structure):
                 ("grad_grid", c_void), ("beta_over_m", C.c_float)]
 
 
+class PlxRayGen(C.Structure):
+    _fields_ = [("imgs", c_void), ("n_cams", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
+                ("poses", c_void), ("fov", C.c_float), ("uv", c_void), ("rays_per_cam", C.c_int32)]
+
+
+class PlxRenderTrain(C.Structure):
+    _fields_ = [("march", PlxMarch), ("rays", PlxRays), ("targets", c_void), ("gen", PlxRayGen), ("grid", c_void),
+                ("grad_grid", c_void), ("rgba", c_void), ("loss", c_void), ("grad_scale", C.c_float),
+                ("loss_scale", C.c_float), ("beta_over_m", C.c_float)]
+
+
 class PlxTrainStep(C.Structure):
     _fields_ = [("march", PlxMarch),
                 ("imgs", c_void), ("n_cams", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
@@ -70,6 +81,7 @@ PROTOTYPES = {
     "plx_num_chunks": (C.c_int32, [C.c_int32]),
     "plx_render_fwd": (C.c_int, [C.POINTER(PlxRenderFwd), c_void]),
     "plx_render_bwd": (C.c_int, [C.POINTER(PlxRenderBwd), c_void]),
+    "plx_render_train": (C.c_int, [C.POINTER(PlxRenderTrain), c_void]),
     "plx_adam_step": (C.c_int, [c_void, c_void, c_void, c_void, c_void, C.c_int64, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_int64, C.c_int32, c_void]),
     "plx_generate_rays": (C.c_int, [c_void, C.c_int32, C.c_int32, C.c_int32, c_void, C.c_float, c_void, C.c_int32,

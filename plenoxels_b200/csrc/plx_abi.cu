@@ -3,6 +3,8 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include "plx_device.cuh"
 #include "plx_launch.h"
@@ -78,6 +80,29 @@ int plx_render_bwd(const PlxRenderBwd* a, void* stream) {
     if (!a->tcarry && (size_t)plx::num_chunks(a->march.num_samples) * 8 * sizeof(float) > 200 * 1024)
         return fail(PLX_E_UNSUPPORTED, "num_samples %d too large for the in-kernel transmittance cache; pass tcarry", a->march.num_samples);
     return cuda_result(plx::launch_render_bwd(*a, (cudaStream_t)stream), "plx_render_bwd");
+}
+
+int plx_render_train(const PlxRenderTrain* a, void* stream) {
+    if (!a) return fail(PLX_E_NULL, "args is NULL");
+    int rc;
+    if ((rc = check_march(a->march, a->grid)) != PLX_OK) return rc;
+    if (a->rays.n_rays < 0) return fail(PLX_E_SHAPE, "n_rays < 0");
+    if (a->rays.n_rays == 0) return PLX_OK;
+    if (!a->grad_grid) return fail(PLX_E_NULL, "grad_grid is NULL");
+    if ((uintptr_t)a->grad_grid % 16 || (uintptr_t)a->rgba % 16) return fail(PLX_E_ALIGN, "grad_grid/rgba must be 16-byte aligned");
+    if (a->gen.uv) {
+        if (!a->gen.imgs || !a->gen.poses) return fail(PLX_E_NULL, "gen.imgs/gen.poses is NULL");
+        if (a->gen.img_h <= 0 || a->gen.img_h != a->gen.img_w)
+            return fail(PLX_E_UNSUPPORTED, "in-kernel ray generation needs square images (src/ray_sampling.py:238-248), got %dx%d", a->gen.img_h, a->gen.img_w);
+        if ((int64_t)a->gen.n_cams * a->gen.rays_per_cam != a->rays.n_rays) return fail(PLX_E_SHAPE, "n_rays != n_cams * rays_per_cam");
+        if ((uintptr_t)a->gen.imgs % 16) return fail(PLX_E_ALIGN, "imgs must be 16-byte aligned");
+    } else {
+        if ((rc = check_rays(a->rays)) != PLX_OK) return rc;
+        if (!a->targets) return fail(PLX_E_NULL, "targets is NULL");
+        if ((uintptr_t)a->targets % 16) return fail(PLX_E_ALIGN, "targets must be 16-byte aligned");
+    }
+    if (!plx::render_train_supported(*a)) return fail(PLX_E_UNSUPPORTED, "fused training march: nearest mode and num_samples within the shared-memory cache only");
+    return cuda_result(plx::launch_render_train(*a, (cudaStream_t)stream), "plx_render_train");
 }
 
 static plx::AdamScalars adam_scalars(double lr, double beta1, double beta2, double eps, int64_t step) {
@@ -212,9 +237,25 @@ int plx_train_step(const PlxTrainStep* a, int32_t phase, void* stream) {
         if (!a->uv || !a->dirs || !a->targets || !a->rgba || !a->grad_rgba || !a->loss || !a->grad)
             return fail(PLX_E_NULL, "train step: uv/scratch/loss/grad pointer is NULL");
         if (a->n_rays_global < n_rays) return fail(PLX_E_SHAPE, "n_rays_global < local ray count");
+        if ((rc = cuda_result(cudaMemsetAsync(a->loss, 0, sizeof(float), st), "memset loss")) != PLX_OK) return rc;
+        const float grad_scale = (float)(2.0 / (4.0 * (double)a->n_rays_global));
+        const float loss_scale = (float)(1.0 / (4.0 * (double)a->n_rays_global));
+        // preferred: one fused kernel (ray generation + forward + loss + backward); PLX_TRAIN_FUSED=0 forces the 3-kernel path
+        static const bool allow_fused = !(std::getenv("PLX_TRAIN_FUSED") && std::getenv("PLX_TRAIN_FUSED")[0] == '0');
+        PlxRenderTrain t;
+        std::memset(&t, 0, sizeof(t));
+        t.march = a->march;
+        t.rays.n_rays = n_rays;
+        t.gen.imgs = a->imgs; t.gen.n_cams = a->n_cams; t.gen.img_h = a->img_h; t.gen.img_w = a->img_w;
+        t.gen.poses = a->poses; t.gen.fov = a->fov; t.gen.uv = a->uv; t.gen.rays_per_cam = a->rays_per_cam;
+        t.grid = a->grid; t.grad_grid = a->grad; t.rgba = a->rgba; t.loss = a->loss;
+        t.grad_scale = grad_scale; t.loss_scale = loss_scale; t.beta_over_m = a->beta_over_m;
+        if (allow_fused && a->img_h == a->img_w && plx::render_train_supported(t)) {
+            if ((rc = plx_render_train(&t, stream)) != PLX_OK) return rc;
+            goto optim;
+        }
         if ((rc = plx_generate_rays(a->imgs, a->n_cams, a->img_h, a->img_w, a->poses, a->fov, a->uv, a->rays_per_cam, 0,
                                     a->dirs, a->targets, stream)) != PLX_OK) return rc;
-        if ((rc = cuda_result(cudaMemsetAsync(a->loss, 0, sizeof(float), st), "memset loss")) != PLX_OK) return rc;
         PlxRenderFwd f;
         f.march = a->march;
         // camera positions = poses[:, :3, 3] (src/ray_sampling.py:159), read in place through the strided view
@@ -227,14 +268,15 @@ int plx_train_step(const PlxTrainStep* a, int32_t phase, void* stream) {
         f.grid = a->grid;
         f.rgba = a->rgba; f.depth = nullptr; f.count = nullptr; f.sample_index = nullptr; f.tcarry = a->tcarry;
         f.targets = a->targets; f.grad_rgba = a->grad_rgba; f.loss = a->loss;
-        f.grad_scale = (float)(2.0 / (4.0 * (double)a->n_rays_global));
-        f.loss_scale = (float)(1.0 / (4.0 * (double)a->n_rays_global));
+        f.grad_scale = grad_scale;
+        f.loss_scale = loss_scale;
         if ((rc = plx_render_fwd(&f, stream)) != PLX_OK) return rc;
         PlxRenderBwd b;
         b.march = a->march; b.rays = f.rays; b.grid = a->grid; b.grad_rgba = a->grad_rgba; b.tcarry = a->tcarry;
         b.grad_grid = a->grad; b.beta_over_m = a->beta_over_m;
         if ((rc = plx_render_bwd(&b, stream)) != PLX_OK) return rc;
     }
+optim:
     if (phase & PLX_STEP_OPTIM) {
         const int64_t n = (int64_t)a->march.nx * a->march.ny * a->march.nz * 4;
         if ((rc = plx_adam_step(a->grid, a->grad, a->exp_avg, a->exp_avg_sq, a->grad_abs_sum, n, a->lr, a->beta1, a->beta2,

@@ -3,7 +3,7 @@
 // These back the stand-alone Python functions (src/ray_sampling.py, src/grid_functions.py) when a caller uses them
 // outside the fused march: ray generation, sample placement, normalisation, nearest / trilinear lookup (+ autograd),
 // compositing (+ autograd).  Same exact-fp32 arithmetic as the fused kernels (plx_device.cuh).
-#include "plx_device.cuh"
+#include "plx_raygen.cuh"
 #include "plx_launch.h"
 
 namespace plx {
@@ -17,20 +17,6 @@ static inline unsigned blocks_for(int64_t n, int threads) {
 // ---------------------------------------------------------------------------------------------------------------
 // generate_rays_batched — src/ray_sampling.py:195-264
 // ---------------------------------------------------------------------------------------------------------------
-// torch.linspace(0, 1, n)[i] as ATen's CPU kernel evaluates it (lower half step*i, upper half fma(-step, n-1-i, 1))
-__device__ __forceinline__ float linspace01(int i, int n) {
-    if (n <= 1) return 0.f;
-    const float step = __fdiv_rn(1.f, (float)(n - 1));
-    return i < n / 2 ? __fmul_rn(step, (float)i) : fmaf(-step, (float)(n - 1 - i), 1.f);
-}
-
-__device__ __forceinline__ float norm3_plain(float x, float y, float z) {     // strided pose columns: mul/add in order
-    return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
-}
-__device__ __forceinline__ float norm3_fused(float x, float y, float z) {     // contiguous last axis: x^2 then two FMAs
-    return __fsqrt_rn(fmaf(z, z, fmaf(y, y, __fmul_rn(x, x))));
-}
-
 __global__ void __launch_bounds__(256) k_generate_rays(const float* __restrict__ imgs, int n_cams, int H, int W,
                                                        const float* __restrict__ poses, float fov,
                                                        const float* __restrict__ uv, int R, int n_side,
@@ -41,26 +27,12 @@ __global__ void __launch_bounds__(256) k_generate_rays(const float* __restrict__
         float u, v;
         if (uv) { u = __ldg(uv + ray * 2); v = __ldg(uv + ray * 2 + 1); }
         else { u = linspace01(j / n_side, n_side); v = linspace01(j % n_side, n_side); }     // cartesian_prod, u-major (:223)
-        const float* P = poses + (int64_t)cam * 16;
-        const float Xx = __ldg(P + 0), Xy = __ldg(P + 4), Xz = __ldg(P + 8);
-        const float Yx = __ldg(P + 1), Yy = __ldg(P + 5), Yz = __ldg(P + 9);
-        const float Zx = -__ldg(P + 2), Zy = -__ldg(P + 6), Zz = -__ldg(P + 10);
-        const float aspect = __fdiv_rn(norm3_plain(Xx, Xy, Xz), norm3_plain(Yx, Yy, Yz));               // :218
-        const float ua = __fmul_rn(fov, __fsub_rn(u, 0.5f));                                              // :234
-        const float va = -__fmul_rn(__fmul_rn(fov, __fdiv_rn(1.f, aspect)), __fsub_rn(v, 0.5f));          // :235
-        if (targets) {
-            const int up = (int)fminf(rintf(__fmul_rn((float)H, u)), (float)(H - 1));                    // :238
-            const int vp = (int)fminf(rintf(__fmul_rn((float)W, v)), (float)(W - 1));                    // :239
-            const float4 t = __ldg(reinterpret_cast<const float4*>(imgs) + ((int64_t)cam * H + vp) * W + up);   // :248
-            reinterpret_cast<float4*>(targets)[ray] = t;
-        }
-        const float dx = __fadd_rn(__fadd_rn(__fmul_rn(ua, Xx), __fmul_rn(va, Yx)), Zx);                  // :261
-        const float dy = __fadd_rn(__fadd_rn(__fmul_rn(ua, Xy), __fmul_rn(va, Yy)), Zy);
-        const float dz = __fadd_rn(__fadd_rn(__fmul_rn(ua, Xz), __fmul_rn(va, Yz)), Zz);
-        const float nrm = norm3_fused(dx, dy, dz);
-        dirs[ray * 3 + 0] = __fdiv_rn(dx, nrm);                                                          // :262
-        dirs[ray * 3 + 1] = __fdiv_rn(dy, nrm);
-        dirs[ray * 3 + 2] = __fdiv_rn(dz, nrm);
+        const RayOut o = ray_from_uv(poses + (int64_t)cam * 16, fov, u, v, H, W);
+        if (targets)                                                                                      // :248
+            reinterpret_cast<float4*>(targets)[ray] = __ldg(reinterpret_cast<const float4*>(imgs) + ((int64_t)cam * H + o.vp) * W + o.up);
+        dirs[ray * 3 + 0] = o.dx;
+        dirs[ray * 3 + 1] = o.dy;
+        dirs[ray * 3 + 2] = o.dz;
     }
 }
 

@@ -8,8 +8,12 @@
 
 namespace plx {
 
+constexpr int MAX_WARPS_PER_BLOCK = 8;
+
 cudaError_t launch_render_fwd(const PlxRenderFwd& a, cudaStream_t st);
 cudaError_t launch_render_bwd(const PlxRenderBwd& a, cudaStream_t st);
+bool render_train_supported(const PlxRenderTrain& a);
+cudaError_t launch_render_train(const PlxRenderTrain& a, cudaStream_t st);
 
 struct AdamScalars {
     float one_minus_beta1;   // lerp weight

@@ -1,0 +1,279 @@
+// plx_train.cu — K12: the whole per-ray training work in ONE kernel (nearest lookup, MSE loss), sm_100a.
+//
+//   [ray generation] -> forward march + compositing -> MSE gradient of this ray -> reverse march + scatter-add
+//
+// i.e. scripts/train.py:130-157 and the autograd of :181 for one ray per warp, without the round trips the separate
+// K1 / K2 launches need (directions, targets, rgba, grad_rgba, chunk transmittances, a second index computation):
+//   * the forward pass caches each sample's linear cell index in shared memory; the reverse pass reads the index back,
+//     re-loads the 16-byte cell (L1/L2 hit) and needs no coordinate arithmetic;
+//   * each lane owns SPL consecutive samples, so one warp scan serves 32*SPL samples and samples that fall into the
+//     same cell (runs along the ray) are merged in registers before the 16-byte vector reduction;
+//   * exact early termination in BOTH directions: once the transmittance is exactly 0 (an alpha == 1 sample k*),
+//     later samples have zero gradient; the only later quantity the gradient of k* needs is the colour seen behind it,
+//     S_k* = sum_{j>k*} alpha_j v_j prod_{k*<i<j} (1-alpha_i), which is linear in the pixel gradient g, so the forward
+//     pass keeps compositing a second accumulator behind k* (until that one saturates too) and S_k* = acc2 . g.
+// Same exact index arithmetic as K1 (plx_march.cuh), so indices match the reference bit for bit.
+#include <cstdlib>
+
+#include "plx_march.cuh"
+#include "plx_raygen.cuh"
+#include "plx_launch.h"
+
+namespace plx {
+
+template <int SPL>
+struct Seg {            // one iteration's SPL samples of a lane
+    float4 c[SPL];      // clamped cell values (0 when out of bounds / past the range)
+};
+
+// composite one iteration: acc += sum_j alpha_j T_j c_j, T <- T * prod(1 - alpha); returns the product of the iteration
+template <int SPL>
+__device__ __forceinline__ void composite_iter(const float4 (&c)[SPL], int lane, float& T, float4& acc) {
+    float pf[SPL];
+    pf[0] = 1.f;
+#pragma unroll
+    for (int j = 1; j < SPL; ++j) pf[j] = pf[j - 1] * (1.f - c[j - 1].w);
+    const float P = pf[SPL - 1] * (1.f - c[SPL - 1].w);
+    float total;
+    const float base = T * warp_excl_prod(P, lane, total);
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const float w = c[j].w * (base * pf[j]);          // alpha_k * T_k, src/ray_sampling.py:184
+        acc.x = fmaf(w, c[j].x, acc.x); acc.y = fmaf(w, c[j].y, acc.y); acc.z = fmaf(w, c[j].z, acc.z);
+        acc.w += w;
+    }
+    T *= total;
+}
+
+template <bool FAST, int SPL>
+__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) k_render_train(const PlxRenderTrain a, int lin_words, int warp_words) {
+    extern __shared__ __align__(16) int s_dyn[];   // per warp (warp_words ints, 16-byte multiple): lin cache [lin_words], then chunk transmittances
+    __shared__ float s_loss;
+    __shared__ int s_done;
+    constexpr int W = 32 * SPL;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int64_t ray = (int64_t)blockIdx.x * wpb + wib;
+    const PlxMarch& m = a.march;
+    if (threadIdx.x == 0) { s_loss = 0.f; s_done = 0; }
+    __syncthreads();                         // every warp arrives here at once: free
+    float ray_loss = 0.f;
+    if (ray < a.rays.n_rays) {
+        int* lc = s_dyn + wib * warp_words;
+        float* tcs = reinterpret_cast<float*>(lc + lin_words);
+        const Geo g = make_geo(m);
+        // ---- this ray: precomputed, or generated here from (pose, uv) — src/ray_sampling.py:212-264
+        Ray r;
+        float4 tgt;
+        if (a.gen.uv) {
+            const int R = a.gen.rays_per_cam;
+            const int cam = (int)(ray / R);
+            const float* P = a.gen.poses + (int64_t)cam * 16;
+            const RayOut o = ray_from_uv(P, a.gen.fov, __ldg(a.gen.uv + ray * 2), __ldg(a.gen.uv + ray * 2 + 1), a.gen.img_h, a.gen.img_w);
+            tgt = __ldg(reinterpret_cast<const float4*>(a.gen.imgs) + ((int64_t)cam * a.gen.img_h + o.vp) * a.gen.img_w + o.up);
+            r.ox = __ldg(P + 3); r.oy = __ldg(P + 7); r.oz = __ldg(P + 11);          // camera position, :159
+            r.dx = o.dx; r.dy = o.dy; r.dz = o.dz;
+        } else {
+            r = load_ray(a.rays, ray);
+            tgt = __ldg(reinterpret_cast<const float4*>(a.targets) + ray);
+        }
+        const bool fast_ray = FAST && ray_in_fast_range(m, r);
+        const float bom = a.beta_over_m;
+        const bool full = bom != 0.f;        // the sparsity term touches every in-bounds sample: no early stop
+        int k0, k1;
+        clip_range(m, r, k0, k1);
+        const int n_it = k0 <= k1 ? (k1 - k0) / W + 1 : 0;
+
+        // ---------------------------------------------------------------------------------------- forward
+        float T = 1.f, T2 = 1.f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = acc;
+        bool opaque = false;                 // segment 1 ended on an alpha == 1 sample at (zl, zj)
+        int zl = 0, zj = 0;
+        int it = 0;
+        for (; it < n_it; ++it) {
+            const int kb = k0 + it * W + lane * SPL;
+            float4 c[SPL];
+            int lin[SPL];
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                float t;
+                TriGeom tg;
+                const Sample s = lookup<PLX_NEAREST, FAST>(m, g, a.grid, r, fast_ray, kb + j, kb + j <= k1, true, t, tg);
+                c[j] = s.c;
+                lin[j] = s.lin;
+            }
+            if (SPL == 1) lc[it * W + lane] = lin[0];
+            else *reinterpret_cast<int2*>(lc + it * W + lane * 2) = make_int2(lin[0], lin[SPL - 1]);
+            if (lane == 0) tcs[it] = T;
+            composite_iter<SPL>(c, lane, T, acc);
+            if (T == 0.f && !full) {
+                // first sample whose factor is exactly 0 (alpha == 1); none => the product merely underflowed
+                int jz = SPL;
+#pragma unroll
+                for (int j = SPL - 1; j >= 0; --j) if (c[j].w == 1.f) jz = j;
+                const unsigned hit = __ballot_sync(FULL, jz < SPL);
+                if (hit) {
+                    opaque = true;
+                    zl = __ffs(hit) - 1;
+                    zj = __shfl_sync(FULL, jz, zl);
+                    float4 c2[SPL];
+#pragma unroll
+                    for (int j = 0; j < SPL; ++j) {
+                        const bool after = lane > zl || (lane == zl && j > zj);
+                        c2[j] = after ? c[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    composite_iter<SPL>(c2, lane, T2, acc2);
+                }
+                ++it;
+                break;
+            }
+        }
+        const int n_fwd = it;                // iterations of segment 1 (their indices are cached)
+        if (opaque) {                        // keep compositing behind k* until that segment saturates or the range ends
+            for (int i2 = n_fwd; i2 < n_it && T2 != 0.f; ++i2) {
+                const int kb = k0 + i2 * W + lane * SPL;
+                float4 c[SPL];
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    float t;
+                    TriGeom tg;
+                    c[j] = lookup<PLX_NEAREST, FAST>(m, g, a.grid, r, fast_ray, kb + j, kb + j <= k1, true, t, tg).c;
+                }
+                composite_iter<SPL>(c, lane, T2, acc2);
+            }
+        }
+        acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+
+        // ---------------------------------------------------------------------------------------- loss, scripts/train.py:156
+        const float er = acc.x - tgt.x, eg = acc.y - tgt.y, eb = acc.z - tgt.z, ea = acc.w - tgt.w;
+        const float4 gr = make_float4(er * a.grad_scale, eg * a.grad_scale, eb * a.grad_scale, ea * a.grad_scale);
+        ray_loss = (er * er + eg * eg + eb * eb + ea * ea) * a.loss_scale;
+        if (lane == 0 && a.rgba) reinterpret_cast<float4*>(a.rgba)[ray] = acc;
+        float s_star = 0.f;                  // colour behind k*, dotted with the pixel gradient
+        if (opaque) {
+            acc2.x = warp_sum(acc2.x); acc2.y = warp_sum(acc2.y); acc2.z = warp_sum(acc2.z); acc2.w = warp_sum(acc2.w);
+            s_star = fmaf(acc2.x, gr.x, fmaf(acc2.y, gr.y, fmaf(acc2.z, gr.z, acc2.w * gr.w)));
+        }
+
+        // ---------------------------------------------------------------------------------------- reverse
+        const bool any_grad = gr.x != 0.f || gr.y != 0.f || gr.z != 0.f || gr.w != 0.f || full;
+        float carry = 0.f;                   // S behind the last visited sample (0: end of ray, or irrelevant behind k*)
+        __syncwarp();
+        for (int ib = n_fwd - 1; ib >= 0 && any_grad; --ib) {
+            int lin[SPL];
+            if (SPL == 1) lin[0] = lc[ib * W + lane];
+            else { const int2 p = *reinterpret_cast<const int2*>(lc + ib * W + lane * 2); lin[0] = p.x; lin[SPL - 1] = p.y; }
+            float4 raw[SPL], c[SPL];
+            float v[SPL];
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                raw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lin[j] >= 0) raw[j] = FAST ? __ldg(reinterpret_cast<const float4*>(a.grid) + lin[j])
+                                               : cell_at<false>(m, a.grid, lin[j] / (g.ny * g.nz), (lin[j] / g.nz) % g.ny, lin[j] % g.nz, lin[j]);
+                c[j] = g.clamp ? clamp4(raw[j]) : raw[j];
+                v[j] = fmaf(c[j].x, gr.x, fmaf(c[j].y, gr.y, fmaf(c[j].z, gr.z, gr.w)));      // c_k . g_rgb + g_A
+            }
+            // lane aggregate of the affine maps s -> alpha v + (1 - alpha) s, last sample innermost
+            float A = 0.f, B = 1.f;
+#pragma unroll
+            for (int j = SPL - 1; j >= 0; --j) { A = fmaf(1.f - c[j].w, A, c[j].w * v[j]); B *= 1.f - c[j].w; }
+            float behind[SPL];
+            behind[SPL - 1] = warp_behind(A, B, lane, carry);
+#pragma unroll
+            for (int j = SPL - 1; j >= 1; --j) behind[j - 1] = fmaf(1.f - c[j].w, behind[j], c[j].w * v[j]);
+            if (opaque && ib == n_fwd - 1 && lane == zl) {
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) if (j == zj) behind[j] = s_star;
+            }
+            // T_k inside the iteration
+            float pf[SPL];
+            pf[0] = 1.f;
+#pragma unroll
+            for (int j = 1; j < SPL; ++j) pf[j] = pf[j - 1] * (1.f - c[j - 1].w);
+            float total;
+            const float base = tcs[ib] * warp_excl_prod(pf[SPL - 1] * (1.f - c[SPL - 1].w), lane, total);
+            float4 d[SPL];
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                const float Tk = base * pf[j];
+                const float wgt = c[j].w * Tk;
+                d[j] = make_float4(wgt * gr.x, wgt * gr.y, wgt * gr.z, Tk * (v[j] - behind[j]));
+                if (full) d[j].w += bom * (1.f / (c[j].w + 1e-4f) + 1.f / (1.f - c[j].w + 1e-4f));   // scripts/train.py:170-177
+                if (g.clamp) { d[j].x *= pass01(raw[j].x); d[j].y *= pass01(raw[j].y); d[j].z *= pass01(raw[j].z); d[j].w *= pass01(raw[j].w); }
+            }
+            if (SPL == 1) {
+                warp_scatter_add(a.grad_grid, lin[0] >= 0, (int64_t)lin[0] * 4, d[0].x, d[0].y, d[0].z, d[0].w, lane);
+            } else {
+                // merge runs inside the lane, then one 16-byte reduction per surviving entry
+#pragma unroll
+                for (int j = SPL - 1; j >= 1; --j) {
+                    if (lin[j] >= 0 && lin[j] == lin[j - 1]) {
+                        d[j - 1].x += d[j].x; d[j - 1].y += d[j].y; d[j - 1].z += d[j].z; d[j - 1].w += d[j].w;
+                        lin[j] = -1;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < SPL; ++j)
+                    if (lin[j] >= 0 && (d[j].x != 0.f || d[j].y != 0.f || d[j].z != 0.f || d[j].w != 0.f))
+                        red_add_v4(a.grad_grid + (int64_t)lin[j] * 4, d[j].x, d[j].y, d[j].z, d[j].w);
+            }
+        }
+    }
+    // ---- loss: shared-memory partial per block, the last warp to finish adds it to the global accumulator
+    if (a.loss && lane == 0) {
+        atomicAdd(&s_loss, ray_loss);
+        __threadfence_block();
+        if (atomicAdd(&s_done, 1) == wpb - 1) atomicAdd(a.loss, atomicAdd(&s_loss, 0.f));
+    }
+}
+
+static int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* e = std::getenv(name);
+    if (e) {
+        const int v = std::atoi(e);
+        if (v >= lo && v <= hi) return v;
+    }
+    return dflt;
+}
+
+// shared memory the fused kernel needs per block; 0 = not launchable (fall back to K1 + K2)
+size_t render_train_smem(int num_samples, int spl, int wpb) {
+    const int W = 32 * spl;
+    const int n_it_max = (num_samples + W - 1) / W + 1;
+    return (size_t)wpb * ((size_t)n_it_max * W + ((n_it_max + 3) & ~3)) * sizeof(int);
+}
+
+bool render_train_supported(const PlxRenderTrain& a) {
+    if (a.march.mode != PLX_NEAREST) return false;
+    if ((int64_t)a.march.nx * a.march.ny * a.march.nz >= (1ll << 31) / 4) return false;
+    return render_train_smem(a.march.num_samples, 2, 1) <= 200 * 1024;
+}
+
+cudaError_t launch_render_train(const PlxRenderTrain& a, cudaStream_t st) {
+    if (a.rays.n_rays == 0) return cudaSuccess;
+    static const int spl_env = env_int("PLX_TRAIN_SPL", 0, 1, 2);
+    static const int wpb_env = env_int("PLX_TRAIN_WPB", 4, 1, MAX_WARPS_PER_BLOCK);
+    const int spl = spl_env ? spl_env : (a.march.num_samples >= 128 ? 2 : 1);
+    int wpb = wpb_env;
+    while (wpb > 1 && render_train_smem(a.march.num_samples, spl, wpb) > 200 * 1024) wpb >>= 1;
+    const size_t smem = render_train_smem(a.march.num_samples, spl, wpb);
+    const int W = 32 * spl;
+    const int n_it_max = (a.march.num_samples + W - 1) / W + 1;
+    const int lin_words = n_it_max * W;
+    const unsigned blocks = (unsigned)((a.rays.n_rays + wpb - 1) / wpb);
+    const bool fast = fast_ok(a.march, a.grid);
+#define PLX_TRAIN(FASTP, SPLV)                                                                                              \
+    do {                                                                                                                    \
+        if (smem > 48 * 1024) {                                                                                             \
+            cudaError_t e = cudaFuncSetAttribute(k_render_train<FASTP, SPLV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                                 (int)smem);                                                                \
+            if (e != cudaSuccess) return e;                                                                                 \
+        }                                                                                                                   \
+        k_render_train<FASTP, SPLV><<<blocks, wpb * 32, smem, st>>>(a, lin_words, lin_words + ((n_it_max + 3) & ~3));                                \
+    } while (0)
+    if (spl == 2) { if (fast) PLX_TRAIN(true, 2); else PLX_TRAIN(false, 2); }
+    else          { if (fast) PLX_TRAIN(true, 1); else PLX_TRAIN(false, 1); }
+#undef PLX_TRAIN
+    return cudaGetLastError();
+}
+
+}  // namespace plx

@@ -108,6 +108,45 @@ def sample_indices(grid, origins, dirs, num_samples, delta_step, gmin, points_di
     return idx, count
 
 
+def render_train(grid, grad_grid, num_samples, delta_step, gmin, points_distance, *, origins=None, dirs=None,
+                 targets=None, rays_per_origin=1, imgs=None, poses=None, fov=None, uv=None, n_rays_global=None,
+                 beta_over_m=0.0, clamp=True):
+    """K12, the fused training march (nearest lookup): forward + mean-MSE + backward in one kernel; the gradient is
+    ACCUMULATED into `grad_grid` (contiguous (X,Y,Z,4)).  Rays are either given (`origins`, `dirs`, `targets`) or
+    generated in the kernel from (`imgs`, `poses`, `fov`, `uv` (C,R,2)).  Returns (rgba (N,4), loss (1,) device tensor)
+    = the pixels and mean((rgba - targets)^2) of scripts/train.py:151-156."""
+    dev = L.require_cuda(grid, grad_grid, origins, dirs, targets, imgs, poses, uv)
+    lib = L.load()
+    a = L.PlxRenderTrain()
+    a.march = L.make_march(grid, num_samples, delta_step, gmin, points_distance, "nearest", clamp)
+    keep = []
+    if uv is not None:
+        uv = uv.contiguous().float()
+        poses = poses.contiguous().float()
+        imgs = imgs.contiguous().float()
+        keep += [uv, poses, imgs]
+        n = uv.shape[0] * uv.shape[1]
+        a.rays.n_rays = n
+        a.gen.imgs, a.gen.n_cams, a.gen.img_h, a.gen.img_w = imgs.data_ptr(), imgs.shape[0], imgs.shape[1], imgs.shape[2]
+        a.gen.poses, a.gen.fov, a.gen.uv, a.gen.rays_per_cam = poses.data_ptr(), float(fov), uv.data_ptr(), uv.shape[1]
+    else:
+        a.rays = L.make_rays(origins, dirs, rays_per_origin)
+        targets = targets.contiguous().float()
+        keep.append(targets)
+        n = dirs.shape[0]
+        a.targets = targets.data_ptr()
+    if not grad_grid.is_contiguous() or grad_grid.shape != grid.shape or grad_grid.dtype != torch.float32:
+        raise L.PlxError("grad_grid must be a contiguous float32 tensor of the grid's shape")
+    n_glob = n if n_rays_global is None else int(n_rays_global)
+    rgba = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+    a.grid, a.grad_grid, a.rgba, a.loss = grid.data_ptr(), grad_grid.data_ptr(), rgba.data_ptr(), loss.data_ptr()
+    a.grad_scale, a.loss_scale, a.beta_over_m = 2.0 / (4.0 * n_glob), 1.0 / (4.0 * n_glob), float(beta_over_m)
+    with torch.cuda.device(dev):
+        L.check(lib.plx_render_train(C.byref(a), L.stream_ptr(dev)), "plx_render_train")
+    return rgba, loss
+
+
 # --------------------------------------------------------------------------------------------- optimiser (K3)
 def adam_step(p, g, m, v, gabs, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, zero_grad=True):
     """In-place Adam step + `gabs += |g|` + optional `g = 0` (scripts/train.py:180-184) over contiguous fp32 tensors."""

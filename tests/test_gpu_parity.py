@@ -71,6 +71,51 @@ def test_backward_grid_gradient(case, mode, beta):
     assert rel_err(grid.grad.cpu().numpy(), ograd) <= TOL
 
 
+@pytest.mark.parametrize("beta", [0.0, 5e-3])
+@pytest.mark.parametrize("source", ["rays", "uv"])
+def test_fused_training_march_matches_oracle(case, beta, source):
+    """K12 (ray generation + forward + MSE + backward in one kernel) against the oracle's loss and gradient."""
+    d = case.cuda()
+    gg = torch.zeros_like(d["grid"])
+    bom = beta / (case.N * case.S)
+    if source == "rays":
+        rgba, loss = ops.render_train(d["grid"], gg, case.S, case.delta, case.gmin, case.pd, origins=d["origins"],
+                                      dirs=d["dirs"], targets=d["targets"], rays_per_origin=case.R, beta_over_m=bom)
+    else:
+        rgba, loss = ops.render_train(d["grid"], gg, case.S, case.delta, case.gmin, case.pd, imgs=d["imgs"],
+                                      poses=d["poses"], fov=case.fov, uv=d["uv"], beta_over_m=bom)
+    orgba, _, _, _ = case.oracle_forward()
+    oloss, gpix = po.mse_loss(orgba, case.targets)
+    ograd = case.oracle_backward(gpix, beta=beta)
+    assert rel_err(rgba.cpu().numpy(), orgba) <= TOL
+    assert abs(float(loss) - oloss) <= TOL * abs(oloss)
+    assert rel_err(gg.cpu().numpy(), ograd) <= TOL
+
+
+def test_fused_training_march_opaque_cells():
+    """Rays that saturate on alpha == 1 cells: the gradient of the opaque sample needs the colour BEHIND it."""
+    case = Case(G=32, C=3, H=16, R=200, S=160, delta=6.0 / 160, kind="ball")
+    grid = case.grid.clone()
+    occ = grid[..., 3] > 0
+    flip = occ & (torch.rand(grid.shape[:3], generator=torch.Generator().manual_seed(9)) < 0.15)
+    grid[..., 3][flip] = 1.25                                       # clips to exactly 1
+    d = case.cuda()
+    gcu = grid.cuda()
+    gg = torch.zeros_like(gcu)
+    rgba, loss = ops.render_train(gcu, gg, case.S, case.delta, case.gmin, case.pd, origins=d["origins"], dirs=d["dirs"],
+                                  targets=d["targets"], rays_per_origin=case.R)
+    orgba, _, _, _ = case.oracle_forward(grid=grid.numpy())
+    oloss, gpix = po.mse_loss(orgba, case.targets)
+    ograd = case.oracle_backward(gpix, grid=grid.numpy())
+    assert rel_err(rgba.cpu().numpy(), orgba) <= TOL
+    assert rel_err(gg.cpu().numpy(), ograd) <= TOL
+    # and the autograd pair K1/K2 agrees on the same scene
+    g2 = gcu.clone().requires_grad_(True)
+    pix = ops.render_rays(g2, d["origins"], d["dirs"], case.S, case.delta, case.gmin, case.pd, rays_per_origin=case.R)
+    torch.nn.functional.mse_loss(pix, d["targets"]).backward()
+    assert rel_err(g2.grad.cpu().numpy(), ograd) <= TOL
+
+
 def test_backward_without_saved_carry_matches(case):
     """K2's in-kernel first pass (tcarry = NULL) must agree with the path that reuses K1's chunk transmittances."""
     import ctypes as C

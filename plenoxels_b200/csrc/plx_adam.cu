@@ -8,6 +8,8 @@
 //   d  = sqrt(v) / sqrt(1 - b2^t) + eps              (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
 //   p  = p + ((-lr / (1 - b1^t)) * m) / d            param.addcdiv_(exp_avg, denom, value=-step_size)
 // Pure streaming: 5 reads + 5 writes of 16 bytes per cell = 160 B/cell, HBM-bound.
+#include <cstdlib>
+
 #include "plx_device.cuh"
 #include "plx_launch.h"
 
@@ -22,30 +24,44 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, con
     p = __fadd_rn(p, fdiv_var(__fmul_rn(s.neg_step_size, m), denom));
 }
 
-template <bool HAS_ABS, bool ZERO>
+template <bool HAS_ABS, bool ZERO, int UNROLL>
 __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                               float4* __restrict__ v, float4* __restrict__ ga, int64_t n4,
                                               const AdamScalars s) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const FastDiv bc = make_fastdiv(s.bc2_sqrt);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        float4 P = p[i];
-        const float4 G = __ldcs(g + i);
-        float4 M = __ldcs(m + i);
-        float4 V = __ldcs(v + i);
-        adam1(P.x, G.x, M.x, V.x, s, bc);
-        adam1(P.y, G.y, M.y, V.y, s, bc);
-        adam1(P.z, G.z, M.z, V.z, s, bc);
-        adam1(P.w, G.w, M.w, V.w, s, bc);
-        p[i] = P;                       // the grid is re-read by the next step's march: default (L2-resident) policy
-        __stcs(m + i, M);
-        __stcs(v + i, V);
-        if (HAS_ABS) {
-            float4 A = __ldcs(ga + i);
-            A.x += fabsf(G.x); A.y += fabsf(G.y); A.z += fabsf(G.z); A.w += fabsf(G.w);
-            __stcs(ga + i, A);
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * UNROLL) {
+        float4 P[UNROLL], G[UNROLL], M[UNROLL], V[UNROLL], A[UNROLL];
+        // all loads of the iteration are issued before the first use: 5 * UNROLL independent 16-byte requests per thread
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n4) {
+                P[u] = p[i];
+                G[u] = __ldcs(g + i);
+                M[u] = __ldcs(m + i);
+                V[u] = __ldcs(v + i);
+                if (HAS_ABS) A[u] = __ldcs(ga + i);
+            }
         }
-        if (ZERO) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n4) {
+                adam1(P[u].x, G[u].x, M[u].x, V[u].x, s, bc);
+                adam1(P[u].y, G[u].y, M[u].y, V[u].y, s, bc);
+                adam1(P[u].z, G[u].z, M[u].z, V[u].z, s, bc);
+                adam1(P[u].w, G[u].w, M[u].w, V[u].w, s, bc);
+                p[i] = P[u];                // the grid is re-read by the next step's march: default (L2-resident) policy
+                __stcs(m + i, M[u]);
+                __stcs(v + i, V[u]);
+                if (HAS_ABS) {
+                    A[u].x += fabsf(G[u].x); A[u].y += fabsf(G[u].y); A[u].z += fabsf(G[u].z); A[u].w += fabsf(G[u].w);
+                    __stcs(ga + i, A[u]);
+                }
+                if (ZERO) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
     }
 }
 
@@ -65,6 +81,29 @@ __global__ void k_adam_scalar(float* p, float* g, float* m, float* v, float* ga,
     }
 }
 
+template <bool HAS_ABS, bool ZERO, int UNROLL>
+static cudaError_t launch_adam_vec(float4* p, float4* g, float4* m, float4* v, float4* ga, int64_t n4, const AdamScalars& s,
+                                   int blocks_per_sm_cap, cudaStream_t st) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adam<HAS_ABS, ZERO, UNROLL>, 256, 0);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (blocks_per_sm_cap > 0 && per_sm > blocks_per_sm_cap) per_sm = blocks_per_sm_cap;
+    // one wave of resident blocks, grid-stride over the rest (no tail wave)
+    int64_t want = (n4 + 256 * UNROLL - 1) / (256 * UNROLL);
+    const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
+    const unsigned blocks = (unsigned)(want < resident ? want : resident);
+    k_adam<HAS_ABS, ZERO, UNROLL><<<blocks, 256, 0, st>>>(p, g, m, v, ga, n4, s);
+    return cudaGetLastError();
+}
+
+static int adam_env(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
 cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int64_t n, const AdamScalars& s,
                         bool zero_grad, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
@@ -72,24 +111,30 @@ cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int
                          ((uintptr_t)v % 16 == 0) && (!gabs || (uintptr_t)gabs % 16 == 0);
     const int64_t n4 = aligned ? n / 4 : 0;
     const int threads = 256;
-#define PLX_ADAM(K, ...)                                                        \
-    do {                                                                        \
-        if (gabs) { if (zero_grad) K<true, true> __VA_ARGS__; else K<true, false> __VA_ARGS__; } \
-        else      { if (zero_grad) K<false, true> __VA_ARGS__; else K<false, false> __VA_ARGS__; } \
-    } while (0)
+    static const int unroll = adam_env("PLX_ADAM_UNROLL", 1);
+    static const int cap = adam_env("PLX_ADAM_BLOCKS_PER_SM", 4);
     if (n4 > 0) {
-        // 148 SMs x 8 resident blocks of 256 threads; grid-stride over the rest
-        int64_t want = (n4 + threads - 1) / threads;
-        const unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);
-        PLX_ADAM(k_adam, <<<blocks, threads, 0, st>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v, (float4*)gabs, n4, s));
+        cudaError_t e;
+#define PLX_ADAM_V(U)                                                                                                         \
+        do {                                                                                                                  \
+            if (gabs) { e = zero_grad ? launch_adam_vec<true, true, U>((float4*)p, (float4*)g, (float4*)m, (float4*)v, (float4*)gabs, n4, s, cap, st)   \
+                                      : launch_adam_vec<true, false, U>((float4*)p, (float4*)g, (float4*)m, (float4*)v, (float4*)gabs, n4, s, cap, st); } \
+            else      { e = zero_grad ? launch_adam_vec<false, true, U>((float4*)p, (float4*)g, (float4*)m, (float4*)v, nullptr, n4, s, cap, st)        \
+                                      : launch_adam_vec<false, false, U>((float4*)p, (float4*)g, (float4*)m, (float4*)v, nullptr, n4, s, cap, st); }    \
+        } while (0)
+        if (unroll == 1) PLX_ADAM_V(1); else if (unroll == 4) PLX_ADAM_V(4); else PLX_ADAM_V(2);
+#undef PLX_ADAM_V
+        if (e != cudaSuccess) return e;
     }
     if (n4 * 4 < n) {
         const int64_t rem = n - n4 * 4;
         int64_t want = (rem + threads - 1) / threads;
         const unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);
-        PLX_ADAM(k_adam_scalar, <<<blocks, threads, 0, st>>>(p, g, m, v, gabs, n4 * 4, n, s));
+        if (gabs) { if (zero_grad) k_adam_scalar<true, true><<<blocks, threads, 0, st>>>(p, g, m, v, gabs, n4 * 4, n, s);
+                    else           k_adam_scalar<true, false><<<blocks, threads, 0, st>>>(p, g, m, v, gabs, n4 * 4, n, s); }
+        else      { if (zero_grad) k_adam_scalar<false, true><<<blocks, threads, 0, st>>>(p, g, m, v, gabs, n4 * 4, n, s);
+                    else           k_adam_scalar<false, false><<<blocks, threads, 0, st>>>(p, g, m, v, gabs, n4 * 4, n, s); }
     }
-#undef PLX_ADAM
     return cudaGetLastError();
 }
 

@@ -45,8 +45,8 @@ __device__ __forceinline__ void composite_iter(const float4 (&c)[SPL], int lane,
     T *= total;
 }
 
-template <bool FAST, int SPL>
-__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) k_render_train(const PlxRenderTrain a, int lin_words, int warp_words) {
+template <bool FAST, int SPL, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain a, int lin_words, int warp_words) {
     extern __shared__ __align__(16) int s_dyn[];   // per warp (warp_words ints, 16-byte multiple): lin cache [lin_words], then chunk transmittances
     __shared__ float s_loss;
     __shared__ int s_done;
@@ -251,7 +251,8 @@ bool render_train_supported(const PlxRenderTrain& a) {
 cudaError_t launch_render_train(const PlxRenderTrain& a, cudaStream_t st) {
     if (a.rays.n_rays == 0) return cudaSuccess;
     static const int spl_env = env_int("PLX_TRAIN_SPL", 0, 1, 2);
-    static const int wpb_env = env_int("PLX_TRAIN_WPB", 4, 1, MAX_WARPS_PER_BLOCK);
+    static const int wpb_env = env_int("PLX_TRAIN_WPB", 4, 1, 4);
+    static const int minb = env_int("PLX_TRAIN_MINB", 8, 8, 12);
     const int spl = spl_env ? spl_env : (a.march.num_samples >= 128 ? 2 : 1);
     int wpb = wpb_env;
     while (wpb > 1 && render_train_smem(a.march.num_samples, spl, wpb) > 200 * 1024) wpb >>= 1;
@@ -261,17 +262,18 @@ cudaError_t launch_render_train(const PlxRenderTrain& a, cudaStream_t st) {
     const int lin_words = n_it_max * W;
     const unsigned blocks = (unsigned)((a.rays.n_rays + wpb - 1) / wpb);
     const bool fast = fast_ok(a.march, a.grid);
-#define PLX_TRAIN(FASTP, SPLV)                                                                                              \
+#define PLX_TRAIN(FASTP, SPLV, MB)                                                                                              \
     do {                                                                                                                    \
         if (smem > 48 * 1024) {                                                                                             \
-            cudaError_t e = cudaFuncSetAttribute(k_render_train<FASTP, SPLV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+            cudaError_t e = cudaFuncSetAttribute(k_render_train<FASTP, SPLV, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                                  (int)smem);                                                                \
             if (e != cudaSuccess) return e;                                                                                 \
         }                                                                                                                   \
-        k_render_train<FASTP, SPLV><<<blocks, wpb * 32, smem, st>>>(a, lin_words, lin_words + ((n_it_max + 3) & ~3));                                \
+        k_render_train<FASTP, SPLV, MB><<<blocks, wpb * 32, smem, st>>>(a, lin_words, lin_words + ((n_it_max + 3) & ~3));   \
     } while (0)
-    if (spl == 2) { if (fast) PLX_TRAIN(true, 2); else PLX_TRAIN(false, 2); }
-    else          { if (fast) PLX_TRAIN(true, 1); else PLX_TRAIN(false, 1); }
+    if (!fast) { if (spl == 2) PLX_TRAIN(false, 2, 8); else PLX_TRAIN(false, 1, 8); }
+    else if (spl == 2) { if (minb >= 12) PLX_TRAIN(true, 2, 12); else if (minb >= 10) PLX_TRAIN(true, 2, 10); else PLX_TRAIN(true, 2, 8); }
+    else               { if (minb >= 12) PLX_TRAIN(true, 1, 12); else if (minb >= 10) PLX_TRAIN(true, 1, 10); else PLX_TRAIN(true, 1, 8); }
 #undef PLX_TRAIN
     return cudaGetLastError();
 }

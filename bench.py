@@ -181,11 +181,16 @@ def run_reference_arm(args):
 def run_gpu_arm(args):
     import torch.distributed as dist
     from plenoxels_b200 import _lib, ops
-    from plenoxels_b200.trainer import VoxelTrainer
+    from plenoxels_b200.trainer import PeerVoxelTrainer, VoxelTrainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # the contract is ONE JSON line on stdout: libraries (NCCL's version banner) write to fd 1, so park the real stdout
+    # and point fd 1 at stderr until the line is ready
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
@@ -204,9 +209,12 @@ def run_gpu_arm(args):
     uv_host = [synth.random_uv(C_, R, seed=1000 + rank * 100003 + i).pin_memory() for i in range(n_batches)]
     uv_dev = [u.to(dev) for u in uv_host]
 
+    multi = os.environ.get("PLX_MULTI", "peer") if world > 1 else "single"
+
     def new_trainer():
-        return VoxelTrainer(sc.grid.to(dev), sc.points_distance, sc.poses.to(dev), sc.fov, imgs_dev, R, S, sc.delta_step,
-                            lr=sc.lr, n_rays_global=n_rays * world)
+        cls = PeerVoxelTrainer if multi == "peer" else VoxelTrainer
+        return cls(sc.grid.to(dev), sc.points_distance, sc.poses.to(dev), sc.fov, imgs_dev, R, S, sc.delta_step,
+                   lr=sc.lr, n_rays_global=n_rays * world)
 
     imgs_dev = sc.imgs.to(dev)
     tr = new_trainer()
@@ -276,59 +284,69 @@ def run_gpu_arm(args):
     lib = _lib.load()
     st = _lib.stream_ptr(dev)
     fused = os.environ.get("PLX_TRAIN_FUSED", "1") != "0"
-    names = ["render_train", "adam"] if fused else ["generate_rays", "render_fwd", "render_bwd", "adam"]
     n_inst = min(K, 64)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(n_inst)]
-    a = tr3._args
-    fwd, bwd, trn = _lib.PlxRenderFwd(), _lib.PlxRenderBwd(), _lib.PlxRenderTrain()
-    rays = _lib.make_rays(tr3.poses[:, :3, 3], tr3.dirs, R)
-    gs, ls = 2.0 / (4.0 * n_rays * world), 1.0 / (4.0 * n_rays * world)
-    fwd.march, fwd.rays, fwd.grid, fwd.rgba, fwd.tcarry = a.march, rays, a.grid, a.rgba, a.tcarry
-    fwd.targets, fwd.grad_rgba, fwd.loss = a.targets, a.grad_rgba, a.loss
-    fwd.grad_scale, fwd.loss_scale = gs, ls
-    bwd.march, bwd.rays, bwd.grid, bwd.grad_rgba, bwd.tcarry, bwd.grad_grid = a.march, rays, a.grid, a.grad_rgba, a.tcarry, a.grad
-    trn.march, trn.grid, trn.grad_grid, trn.rgba, trn.loss = a.march, a.grid, a.grad, a.rgba, a.loss
-    trn.rays.n_rays = n_rays
-    trn.gen.imgs, trn.gen.n_cams, trn.gen.img_h, trn.gen.img_w = a.imgs, a.n_cams, a.img_h, a.img_w
-    trn.gen.poses, trn.gen.fov, trn.gen.rays_per_cam = a.poses, a.fov, R
-    trn.grad_scale, trn.loss_scale = gs, ls
     for w_ in range(3):
         tr3.step(uv_dev[w_ % n_batches])
-    sampler.start()
-    for i in range(n_inst):
-        u = uv_dev[(W + i) % n_batches]
-        ev = evs[i]
-        tr3.loss.zero_()
-        ev[0].record()
-        if fused:
-            trn.gen.uv = u.data_ptr()
-            _lib.check(lib.plx_render_train(C.byref(trn), st))
-        else:
-            _lib.check(lib.plx_generate_rays(a.imgs, a.n_cams, a.img_h, a.img_w, a.poses, a.fov, u.data_ptr(), R, 0, a.dirs,
-                                             a.targets, st))
+    if world > 1:
+        # multi-GPU: the two phases of the step (render | gradient exchange + optimiser)
+        names = ["render_train", "exchange+adam"]
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_inst)]
+        barrier()
+        sampler.start()
+        for i in range(n_inst):
+            ev = evs[i]
+            ev[0].record()
+            tr3.render_phase(uv_dev[(W + i) % n_batches])
             ev[1].record()
-            _lib.check(lib.plx_render_fwd(C.byref(fwd), st))
+            tr3.update_phase()
             ev[2].record()
-            _lib.check(lib.plx_render_bwd(C.byref(bwd), st))
-        ev[-2].record()
-        if world > 1:
-            dist.all_reduce(tr3.grad)
-        tr3.step_count += 1
-        _lib.check(lib.plx_adam_step(a.grid, a.grad, a.exp_avg, a.exp_avg_sq, a.grad_abs_sum, cells * 4, sc.lr, 0.9, 0.999,
-                                     1e-8, tr3.step_count, 1, st))
-        ev[-1].record()
+    else:
+        names = ["render_train", "adam"] if fused else ["generate_rays", "render_fwd", "render_bwd", "adam"]
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(n_inst)]
+        a = tr3._args
+        fwd, bwd, trn = _lib.PlxRenderFwd(), _lib.PlxRenderBwd(), _lib.PlxRenderTrain()
+        rays = _lib.make_rays(tr3.poses[:, :3, 3], tr3.dirs, R)
+        gs, ls = 2.0 / (4.0 * n_rays * world), 1.0 / (4.0 * n_rays * world)
+        fwd.march, fwd.rays, fwd.grid, fwd.rgba, fwd.tcarry = a.march, rays, a.grid, a.rgba, a.tcarry
+        fwd.targets, fwd.grad_rgba, fwd.loss = a.targets, a.grad_rgba, a.loss
+        fwd.grad_scale, fwd.loss_scale = gs, ls
+        bwd.march, bwd.rays, bwd.grid, bwd.grad_rgba, bwd.tcarry, bwd.grad_grid = a.march, rays, a.grid, a.grad_rgba, a.tcarry, a.grad
+        trn.march, trn.grid, trn.grad_grid, trn.rgba, trn.loss = a.march, a.grid, a.grad, a.rgba, a.loss
+        trn.rays.n_rays = n_rays
+        trn.gen.imgs, trn.gen.n_cams, trn.gen.img_h, trn.gen.img_w = a.imgs, a.n_cams, a.img_h, a.img_w
+        trn.gen.poses, trn.gen.fov, trn.gen.rays_per_cam = a.poses, a.fov, R
+        trn.grad_scale, trn.loss_scale = gs, ls
+        sampler.start()
+        for i in range(n_inst):
+            u = uv_dev[(W + i) % n_batches]
+            ev = evs[i]
+            tr3.loss.zero_()
+            ev[0].record()
+            if fused:
+                trn.gen.uv = u.data_ptr()
+                _lib.check(lib.plx_render_train(C.byref(trn), st))
+            else:
+                _lib.check(lib.plx_generate_rays(a.imgs, a.n_cams, a.img_h, a.img_w, a.poses, a.fov, u.data_ptr(), R, 0, a.dirs,
+                                                 a.targets, st))
+                ev[1].record()
+                _lib.check(lib.plx_render_fwd(C.byref(fwd), st))
+                ev[2].record()
+                _lib.check(lib.plx_render_bwd(C.byref(bwd), st))
+            ev[-2].record()
+            tr3.step_count += 1
+            _lib.check(lib.plx_adam_step(a.grid, a.grad, a.exp_avg, a.exp_avg_sq, a.grad_abs_sum, cells * 4, sc.lr, 0.9, 0.999,
+                                         1e-8, tr3.step_count, 1, st))
+            ev[-1].record()
     torch.cuda.synchronize(dev)
     sampler.stop()
     kms = {n: float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(n_inst)])) for j, n in enumerate(names)}
-    if world > 1:
-        kms["adam"] = None      # includes the all-reduce in this instrumented pass; not used for the roofline
     del tr3
 
     # ---- roofline of the dominant kernel + of the whole step (SURVEY.md §8d byte model)
     peak, peak_src = measured_peak()
     alg = {"generate_rays": 8.0 * n_rays + 28.0 * n_rays, "render_fwd": 16.0 * m_in + 40.0 * n_rays,
            "render_bwd": 48.0 * m_in + 56.0 * n_rays, "render_train": 64.0 * m_in + 96.0 * n_rays, "adam": 160.0 * cells}
-    timed = {k: v for k, v in kms.items() if v}
+    timed = {k: v for k, v in kms.items() if v and k in alg}
     dom = max(timed, key=timed.get)
     achieved = alg[dom] / (timed[dom] * 1e-3) / 1e9
     traffic = None
@@ -364,18 +382,22 @@ def run_gpu_arm(args):
                        "l2": "no flush: each step streams 5 grid-sized state arrays (%.0f MB) plus gathers from a %.2f GB "
                              "image set, more than the 126 MB L2; a fresh uv batch every step" %
                              (5 * cells * 16 / 1e6, sc.imgs.numel() * 4 / 1e9),
-                       "parallelism": f"ray-sharded replicas x{world}, dense grad all-reduce (NCCL)" if world > 1 else "single GPU",
+                       "parallelism": ("single GPU" if world == 1 else
+                                       f"ray-sharded replicas x{world}, " +
+                                       ("gradient reduce-scatter + Adam + parameter all-gather fused in one kernel over NVLink peer memory"
+                                        if multi == "peer" else "dense gradient all-reduce (NCCL) + replicated Adam")),
                        "distinct_batches": n_batches, "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_rays * 8, "d2h_bytes_per_step": 4,
                     "ms_per_step": 1e3 * e2e_s / K,
                     "note": "uv draw copied from pinned host memory and loss read back + stream-synchronised every step; "
                             "images/poses/grid stay resident as in the reference (scripts/train.py:75)"},
-            "gpu_launches": len(names) * K,
+            "gpu_launches": (2 if fused else 4) * K,
             "clocks": sampler.summary(),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

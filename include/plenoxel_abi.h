@@ -163,6 +163,34 @@ int plx_adam_step(float* p, float* g, float* m, float* v, float* gabs, int64_t n
                   double eps, int64_t step, int32_t zero_grad, void* stream);
 
 /*
+ * K3p — the optimiser step fused with the gradient exchange over NVLink peer memory (multi-GPU).
+ * Every rank r holds a grid replica grids[r] and a local gradient buffer grads[r], all mapped into this process
+ * (symmetric / peer memory).  The rank owns the element range [begin, end) (multiples of 4).  For every owned element
+ * the kernel  (1) loads and sums the `world` partial gradients straight from the peers' buffers (reduce-scatter),
+ * (2) applies the Adam update of plx_adam_step with the local exp_avg / exp_avg_sq / grad_abs_sum (full-size arrays,
+ * only the owned range is touched), (3) stores the new parameter into ALL replicas (all-gather) — one pass, loads and
+ * stores in flight together, no staging copy and no atomics on the fabric.  The caller orders it between two
+ * cross-rank barriers (gradients complete before / parameters visible after) and clears its own gradient buffer.
+ */
+#define PLX_MAX_PEERS 8
+typedef struct PlxAdamPeer {
+    int32_t world, rank;
+    float* grids[PLX_MAX_PEERS];
+    const float* grads[PLX_MAX_PEERS];
+    float* exp_avg; float* exp_avg_sq; float* grad_abs_sum;
+    int64_t begin, end;
+    double lr, beta1, beta2, eps;
+    int64_t step;
+    /* Optional NVLS multicast addresses of the same two symmetric buffers (NULL = use the per-peer pointers above).
+     * With them the partial gradients are summed INSIDE the NVSwitch (`multimem.ld_reduce.add.v4.f32`: one 16-byte
+     * response per element instead of world-1) and the new parameters are written once and replicated by the switch
+     * (`multimem.st.v4.f32`), which halves the bytes every GPU moves over its NVLink ports. */
+    float* grid_mc;
+    const float* grad_mc;
+} PlxAdamPeer;
+int plx_adam_step_peer(const PlxAdamPeer* args, void* stream);
+
+/*
  * Ray generation — generate_rays_batched, src/ray_sampling.py:195-264.
  * imgs (C,H,W,4); poses (C,4,4) row-major camera-to-world; uv (C,R,2) in [0,1] (the `torch.rand` draw of :227) or NULL
  * for the even-spread lattice of :220-223 with R = n_side^2 rays (u-major, linspace(0,1,n_side)).

@@ -59,6 +59,16 @@ class PlxRenderTrain(C.Structure):
                 ("loss_scale", C.c_float), ("beta_over_m", C.c_float)]
 
 
+PLX_MAX_PEERS = 8
+
+
+class PlxAdamPeer(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("grids", c_void * PLX_MAX_PEERS),
+                ("grads", c_void * PLX_MAX_PEERS), ("exp_avg", c_void), ("exp_avg_sq", c_void), ("grad_abs_sum", c_void),
+                ("begin", C.c_int64), ("end", C.c_int64), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("eps", C.c_double), ("step", C.c_int64), ("grid_mc", c_void), ("grad_mc", c_void)]
+
+
 class PlxTrainStep(C.Structure):
     _fields_ = [("march", PlxMarch),
                 ("imgs", c_void), ("n_cams", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
@@ -84,6 +94,7 @@ PROTOTYPES = {
     "plx_render_train": (C.c_int, [C.POINTER(PlxRenderTrain), c_void]),
     "plx_adam_step": (C.c_int, [c_void, c_void, c_void, c_void, c_void, C.c_int64, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_int64, C.c_int32, c_void]),
+    "plx_adam_step_peer": (C.c_int, [C.POINTER(PlxAdamPeer), c_void]),
     "plx_generate_rays": (C.c_int, [c_void, C.c_int32, C.c_int32, C.c_int32, c_void, C.c_float, c_void, C.c_int32,
                                     C.c_int32, c_void, c_void, c_void]),
     "plx_sample_points": (C.c_int, [C.POINTER(PlxRays), C.c_int32, C.c_float, c_void, c_void]),

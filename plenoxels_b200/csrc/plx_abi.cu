@@ -128,6 +128,23 @@ int plx_adam_step(float* p, float* g, float* m, float* v, float* gabs, int64_t n
                                         (cudaStream_t)stream), "plx_adam_step");
 }
 
+int plx_adam_step_peer(const PlxAdamPeer* a, void* stream) {
+    if (!a) return fail(PLX_E_NULL, "args is NULL");
+    if (a->world < 1 || a->world > PLX_MAX_PEERS || a->rank < 0 || a->rank >= a->world)
+        return fail(PLX_E_SHAPE, "world must be 1..%d and 0 <= rank < world (got world %d, rank %d)", PLX_MAX_PEERS, a->world, a->rank);
+    if (a->begin < 0 || a->end < a->begin || a->begin % 4 || a->end % 4) return fail(PLX_E_SHAPE, "owned range must be multiples of 4 floats");
+    if (a->step < 1) return fail(PLX_E_SHAPE, "step counts from 1");
+    if (!a->exp_avg || !a->exp_avg_sq) return fail(PLX_E_NULL, "exp_avg/exp_avg_sq is NULL");
+    for (int r = 0; r < a->world; ++r) {
+        if (!a->grids[r] || !a->grads[r]) return fail(PLX_E_NULL, "grid/grad pointer of rank %d is NULL", r);
+        if ((uintptr_t)a->grids[r] % 16 || (uintptr_t)a->grads[r] % 16) return fail(PLX_E_ALIGN, "peer buffers must be 16-byte aligned");
+    }
+    if ((uintptr_t)a->exp_avg % 16 || (uintptr_t)a->exp_avg_sq % 16 || (uintptr_t)a->grad_abs_sum % 16)
+        return fail(PLX_E_ALIGN, "optimizer state must be 16-byte aligned");
+    return cuda_result(plx::launch_adam_peer(*a, adam_scalars(a->lr, a->beta1, a->beta2, a->eps, a->step), (cudaStream_t)stream),
+                       "plx_adam_step_peer");
+}
+
 int plx_generate_rays(const float* imgs, int32_t n_cams, int32_t img_h, int32_t img_w, const float* poses, float fov,
                       const float* uv, int32_t rays_per_cam, int32_t n_side, float* dirs, float* targets, void* stream) {
     if (n_cams < 0 || rays_per_cam < 0) return fail(PLX_E_SHAPE, "negative camera / ray count");

@@ -65,6 +65,176 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
     }
 }
 
+static int adam_env(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
+// K3p: reduce-scatter + Adam + all-gather over peer-mapped memory in one pass (see plenoxel_abi.h)
+struct PeerPtrs {
+    float4* grids[PLX_MAX_PEERS];
+    const float4* grads[PLX_MAX_PEERS];
+};
+
+template <int UNROLL>
+__global__ void __launch_bounds__(256) k_adam_peer(PeerPtrs pp, int world, int world_st, float4* __restrict__ m, float4* __restrict__ v,
+                                                   float4* __restrict__ ga, int64_t begin4, int64_t end4, const AdamScalars s) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const FastDiv bc = make_fastdiv(s.bc2_sqrt);
+    for (int64_t i0 = begin4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end4; i0 += stride * UNROLL) {
+        float4 G[UNROLL], P[UNROLL], M[UNROLL], V[UNROLL], A[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t i = i0 + u * stride;
+            G[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < end4) {
+                // all partial gradients requested before the first use: `world` independent 16-byte loads (world-1 over NVLink)
+                float4 part[PLX_MAX_PEERS];
+#pragma unroll
+                for (int r = 0; r < PLX_MAX_PEERS; ++r)
+                    if (r < world) part[r] = pp.grads[r][i];
+                P[u] = pp.grids[0][i];           // slot 0 is the local replica (all replicas hold the same parameters)
+                M[u] = __ldcs(m + i);
+                V[u] = __ldcs(v + i);
+                if (ga) A[u] = __ldcs(ga + i);
+#pragma unroll
+                for (int r = 0; r < PLX_MAX_PEERS; ++r)
+                    if (r < world) { G[u].x += part[r].x; G[u].y += part[r].y; G[u].z += part[r].z; G[u].w += part[r].w; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < end4) {
+                adam1(P[u].x, G[u].x, M[u].x, V[u].x, s, bc);
+                adam1(P[u].y, G[u].y, M[u].y, V[u].y, s, bc);
+                adam1(P[u].z, G[u].z, M[u].z, V[u].z, s, bc);
+                adam1(P[u].w, G[u].w, M[u].w, V[u].w, s, bc);
+#pragma unroll
+                for (int r = 0; r < PLX_MAX_PEERS; ++r)
+                    if (r < world_st) pp.grids[r][i] = P[u];
+                __stcs(m + i, M[u]);
+                __stcs(v + i, V[u]);
+                if (ga) {
+                    A[u].x += fabsf(G[u].x); A[u].y += fabsf(G[u].y); A[u].z += fabsf(G[u].z); A[u].w += fabsf(G[u].w);
+                    __stcs(ga + i, A[u]);
+                }
+            }
+        }
+    }
+}
+
+// NVLS variant: in-switch reduction of the partial gradients and in-switch replication of the new parameters
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4* mc) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+    return r;
+}
+__device__ __forceinline__ void multimem_st(float4* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(256) k_adam_mc(const float4* __restrict__ p_local, float4* p_mc, const float4* g_mc,
+                                                 float4* __restrict__ m, float4* __restrict__ v, float4* __restrict__ ga,
+                                                 int64_t begin4, int64_t end4, const AdamScalars s) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const FastDiv bc = make_fastdiv(s.bc2_sqrt);
+    for (int64_t i0 = begin4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end4; i0 += stride * UNROLL) {
+        float4 G[UNROLL], P[UNROLL], M[UNROLL], V[UNROLL], A[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < end4) {
+                G[u] = multimem_ld_reduce_add(g_mc + i);
+                P[u] = p_local[i];
+                M[u] = __ldcs(m + i);
+                V[u] = __ldcs(v + i);
+                if (ga) A[u] = __ldcs(ga + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < end4) {
+                adam1(P[u].x, G[u].x, M[u].x, V[u].x, s, bc);
+                adam1(P[u].y, G[u].y, M[u].y, V[u].y, s, bc);
+                adam1(P[u].z, G[u].z, M[u].z, V[u].z, s, bc);
+                adam1(P[u].w, G[u].w, M[u].w, V[u].w, s, bc);
+                multimem_st(p_mc + i, P[u]);
+                __stcs(m + i, M[u]);
+                __stcs(v + i, V[u]);
+                if (ga) {
+                    A[u].x += fabsf(G[u].x); A[u].y += fabsf(G[u].y); A[u].z += fabsf(G[u].z); A[u].w += fabsf(G[u].w);
+                    __stcs(ga + i, A[u]);
+                }
+            }
+        }
+    }
+}
+
+cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, cudaStream_t st) {
+    const int64_t begin4 = a.begin / 4, end4 = a.end / 4;
+    if (end4 <= begin4) return cudaSuccess;
+    static const int use_mc = adam_env("PLX_PEER_MULTICAST", 1);
+    if (a.grid_mc && a.grad_mc && use_mc) {
+        int dev = 0, sms = 148, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        static const int unroll = adam_env("PLX_MC_UNROLL", 2);
+        // few resident blocks on purpose: with the whole slab in flight at once the switch-reduced loads and the replicated
+        // stores would run as two serial phases; a deeper grid-stride loop keeps both NVLink directions busy together
+        static const int mc_cap = adam_env("PLX_MC_BLOCKS_PER_SM", 1);
+        const int64_t n4 = end4 - begin4;
+#define PLX_MC(U)                                                                                                      \
+        do {                                                                                                           \
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adam_mc<U>, 256, 0);              \
+            if (e != cudaSuccess) return e;                                                                            \
+            if (mc_cap > 0 && per_sm > mc_cap) per_sm = mc_cap;                                                        \
+            const int64_t want = (n4 + 256 * U - 1) / (256 * U);                                                       \
+            const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);                                         \
+            const unsigned blocks = (unsigned)(want < resident ? want : resident);                                     \
+            k_adam_mc<U><<<blocks, 256, 0, st>>>((const float4*)a.grids[a.rank], (float4*)a.grid_mc, (const float4*)a.grad_mc,   \
+                                                 (float4*)a.exp_avg, (float4*)a.exp_avg_sq, (float4*)a.grad_abs_sum, begin4, end4, s); \
+        } while (0)
+        if (unroll >= 4) PLX_MC(4); else if (unroll >= 2) PLX_MC(2); else PLX_MC(1);
+#undef PLX_MC
+        return cudaGetLastError();
+    }
+    PeerPtrs pp;
+    // put the local replica first so that the parameter read (grids[0]) is local
+    int order[PLX_MAX_PEERS];
+    for (int r = 0; r < a.world; ++r) order[r] = (a.rank + r) % a.world;
+    for (int r = 0; r < PLX_MAX_PEERS; ++r) {
+        pp.grids[r] = r < a.world ? (float4*)a.grids[order[r]] : nullptr;
+        pp.grads[r] = r < a.world ? (const float4*)a.grads[order[r]] : nullptr;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t n4 = end4 - begin4;
+    // remote loads have microseconds of latency: keep `world * UNROLL` 16-byte requests in flight per thread
+    static const int unroll_env = adam_env("PLX_PEER_UNROLL", 0);
+    static const int dbg_ld = adam_env("PLX_PEER_DBG_LD", 0), dbg_st = adam_env("PLX_PEER_DBG_ST", 0);   // timing experiments only
+    const int unroll = unroll_env ? unroll_env : 1;
+#define PLX_PEER(U)                                                                                                  \
+    do {                                                                                                             \
+        int per_sm = 0;                                                                                              \
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adam_peer<U>, 256, 0);              \
+        if (e != cudaSuccess) return e;                                                                              \
+        const int64_t want = (n4 + 256 * U - 1) / (256 * U);                                                         \
+        const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);                                           \
+        const unsigned blocks = (unsigned)(want < resident ? want : resident);                                       \
+        k_adam_peer<U><<<blocks, 256, 0, st>>>(pp, dbg_ld ? dbg_ld : a.world, dbg_st ? dbg_st : a.world, (float4*)a.exp_avg, (float4*)a.exp_avg_sq,               \
+                                               (float4*)a.grad_abs_sum, begin4, end4, s);                            \
+    } while (0)
+    if (unroll >= 4) PLX_PEER(4); else if (unroll >= 2) PLX_PEER(2); else PLX_PEER(1);
+#undef PLX_PEER
+    return cudaGetLastError();
+}
+
 // scalar tail / unaligned fallback
 template <bool HAS_ABS, bool ZERO>
 __global__ void k_adam_scalar(float* p, float* g, float* m, float* v, float* ga, int64_t begin, int64_t n,
@@ -97,11 +267,6 @@ static cudaError_t launch_adam_vec(float4* p, float4* g, float4* m, float4* v, f
     const unsigned blocks = (unsigned)(want < resident ? want : resident);
     k_adam<HAS_ABS, ZERO, UNROLL><<<blocks, 256, 0, st>>>(p, g, m, v, ga, n4, s);
     return cudaGetLastError();
-}
-
-static int adam_env(const char* name, int dflt) {
-    const char* e = std::getenv(name);
-    return e ? std::atoi(e) : dflt;
 }
 
 cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int64_t n, const AdamScalars& s,

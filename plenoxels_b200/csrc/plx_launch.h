@@ -26,6 +26,8 @@ struct AdamScalars {
 cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int64_t n, const AdamScalars& s,
                         bool zero_grad, cudaStream_t st);
 
+cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, cudaStream_t st);
+
 cudaError_t launch_generate_rays(const float* imgs, int n_cams, int img_h, int img_w, const float* poses, float fov,
                                  const float* uv, int rays_per_cam, int n_side, float* dirs, float* targets,
                                  cudaStream_t st);

@@ -95,22 +95,36 @@ class VoxelTrainer:
     def _distributed(self) -> bool:
         return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
 
+    def render_phase(self, uv: torch.Tensor | None = None) -> None:
+        """Ray generation + forward + loss + backward of this rank's batch into the local gradient buffer."""
+        self._args.uv = uv.data_ptr() if uv is not None else self.uv.data_ptr()
+        self.step_count += 1
+        self._args.step = self.step_count
+        with torch.cuda.device(self.device):
+            L.check(self.lib.plx_train_step(C.byref(self._args), L.PLX_STEP_RENDER, L.stream_ptr(self.device)),
+                    "plx_train_step(render)")
+        self._args.uv = self.uv.data_ptr()
+
+    def update_phase(self) -> None:
+        """[gradient exchange] + Adam (+ |grad| accumulation, gradient clear)."""
+        with torch.cuda.device(self.device):
+            if self._distributed():
+                all_reduce_sum_(self.grad, self.group)
+            L.check(self.lib.plx_train_step(C.byref(self._args), L.PLX_STEP_OPTIM, L.stream_ptr(self.device)),
+                    "plx_train_step(optim)")
+
     def step(self, uv: torch.Tensor | None = None) -> torch.Tensor:
         """One step with the uv draw already on the device (`uv` (C,R,2) cuda, or the trainer's own `self.uv`).
         Returns the device loss tensor (1,) without synchronising.  With a process group: this rank's partial loss."""
-        if uv is not None:
-            if uv.data_ptr() != self.uv.data_ptr():
-                self._args.uv = uv.data_ptr()
+        if self._distributed():
+            self.render_phase(uv)
+            self.update_phase()
+            return self.loss
+        self._args.uv = uv.data_ptr() if uv is not None else self.uv.data_ptr()
         self.step_count += 1
         self._args.step = self.step_count
-        st = L.stream_ptr(self.device)
         with torch.cuda.device(self.device):
-            if self._distributed():
-                L.check(self.lib.plx_train_step(C.byref(self._args), L.PLX_STEP_RENDER, st), "plx_train_step(render)")
-                all_reduce_sum_(self.grad, self.group)
-                L.check(self.lib.plx_train_step(C.byref(self._args), L.PLX_STEP_OPTIM, st), "plx_train_step(optim)")
-            else:
-                L.check(self.lib.plx_train_step(C.byref(self._args), L.PLX_STEP_ALL, st), "plx_train_step")
+            L.check(self.lib.plx_train_step(C.byref(self._args), L.PLX_STEP_ALL, L.stream_ptr(self.device)), "plx_train_step")
         self._args.uv = self.uv.data_ptr()
         return self.loss
 
@@ -143,3 +157,103 @@ class VoxelTrainer:
         if extra_param:
             param.update(extra_param)
         return {"grid": self.grid.detach().cpu(), "grid_grad": self.grad_abs_sum.detach().cpu(), "param": param}
+
+
+def slab_range(n_cells: int, rank: int, world: int):
+    """[begin, end) in floats of the contiguous block of cells whose optimiser state `rank` owns."""
+    base, extra = divmod(n_cells, world)
+    start = rank * base + min(rank, extra)
+    return 4 * start, 4 * (start + base + (1 if rank < extra else 0))
+
+
+class PeerVoxelTrainer(VoxelTrainer):
+    """Multi-GPU step whose gradient exchange is fused into the optimiser kernel over NVLink peer memory.
+
+    Every rank keeps a full grid replica and a full local gradient buffer, both in symmetric memory
+    (torch.distributed._symmetric_memory), so each process holds a mapped pointer to every peer's copy.  Per step:
+      K12   render this rank's rays, scatter-add into the LOCAL gradient buffer            (no communication)
+      --    barrier: all partial gradients are complete
+      K3p   for the cells this rank owns: sum the partial gradients straight out of the peers' buffers, Adam,
+            store the new parameters into every replica (plx_adam_step_peer)              (NVLink loads + stores)
+      --    barrier: all replicas updated; then clear the local gradient buffer
+    No NCCL collective on the data path, no staging copy; optimiser state and its traffic are sharded world-ways.
+    """
+
+    def __init__(self, grid, *args, group=None, **kwargs):
+        import torch.distributed._symmetric_memory as symm_mem
+        if not (dist.is_available() and dist.is_initialized()):
+            raise L.PlxError("PeerVoxelTrainer needs an initialised NCCL process group")
+        group = group or dist.group.WORLD
+        super().__init__(grid, *args, group=group, **kwargs)
+        dev = self.device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > L.PLX_MAX_PEERS:
+            raise L.PlxError(f"at most {L.PLX_MAX_PEERS} peers")
+        shape = tuple(self.grid.shape)
+        sym_grid = symm_mem.empty(shape, dtype=torch.float32, device=dev)
+        sym_grad = symm_mem.empty(shape, dtype=torch.float32, device=dev)
+        sym_grid.copy_(self.grid)
+        sym_grad.zero_()
+        self._h_grid = symm_mem.rendezvous(sym_grid, group)
+        self._h_grad = symm_mem.rendezvous(sym_grad, group)
+        self.grid, self.grad = sym_grid, sym_grad
+        dist.broadcast(self.grid, src=dist.get_global_rank(group, 0), group=group)      # identical replicas to start from
+        self._args = self._make_args()
+        p = L.PlxAdamPeer()
+        p.world, p.rank = self.world, self.rank
+        for r in range(self.world):
+            p.grids[r] = int(self._h_grid.buffer_ptrs[r])
+            p.grads[r] = int(self._h_grad.buffer_ptrs[r])
+        p.exp_avg, p.exp_avg_sq, p.grad_abs_sum = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.grad_abs_sum.data_ptr()
+        p.begin, p.end = slab_range(self.grid.numel() // 4, self.rank, self.world)
+        p.lr, p.beta1, p.beta2, p.eps = self.lr, self.betas[0], self.betas[1], self.eps
+        # NVLS multicast mappings of the same buffers, when the fabric offers them (in-switch reduce / replicate)
+        self.multicast = False
+        try:
+            mc_grid, mc_grad = int(self._h_grid.multicast_ptr or 0), int(self._h_grad.multicast_ptr or 0)
+            if mc_grid and mc_grad:
+                p.grid_mc, p.grad_mc = mc_grid, mc_grad
+                self.multicast = True
+        except Exception:           # no multicast support: per-peer pointers are used
+            pass
+        self._peer = p
+        self.launches_per_step = 2
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)
+
+    def _exchange_and_update(self, st):
+        self._peer.step = self.step_count
+        self._h_grad.barrier(channel=0)                       # every rank's partial gradient is complete
+        L.check(self.lib.plx_adam_step_peer(C.byref(self._peer), st), "plx_adam_step_peer")
+        self._h_grad.barrier(channel=1)                       # every replica holds the new parameters; peers done reading
+        self.grad.zero_()
+
+    def update_phase(self) -> None:
+        with torch.cuda.device(self.device):
+            self._exchange_and_update(L.stream_ptr(self.device))
+
+    def step(self, uv=None):
+        self.render_phase(uv)
+        self.update_phase()
+        return self.loss
+
+    def step_host(self, uv_host):
+        self.step_count += 1
+        self._args.step = self.step_count
+        st = L.stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.plx_train_step_host(C.byref(self._args), uv_host.data_ptr(), self.loss_host.data_ptr(),
+                                                 L.PLX_STEP_RENDER, st), "plx_train_step_host(render)")
+            self._exchange_and_update(st)
+        return self.loss_host
+
+    def gathered_grad_abs_sum(self):
+        """Full `grid_grad` (scripts/train.py:184): each rank accumulated |grad| for the cells it owns only."""
+        full = self.grad_abs_sum.clone()
+        b, e = self._peer.begin, self._peer.end
+        flat = full.view(-1)
+        mask = torch.zeros_like(flat)
+        mask[b:e] = 1
+        flat *= mask
+        all_reduce_sum_(full, self.group)
+        return full

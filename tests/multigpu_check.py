@@ -44,6 +44,27 @@ def main():
         print(f"world={world}: grad vs 1-GPU rel err {err:.2e}, vs oracle {oerr:.2e}; loss {float(loss):.7f} / {float(loss1):.7f} / {oloss:.7f}")
         assert err <= 1e-5 and oerr <= 1e-5 and abs(float(loss) - oloss) <= 1e-5 * oloss
         print("MULTIGPU_OK")
+    # ---- whole steps: NCCL all-reduce trainer vs the peer-memory trainer (fused reduce + Adam + broadcast)
+    from plenoxels_b200.trainer import PeerVoxelTrainer, VoxelTrainer
+    mk = dict(lr=0.0075, n_rays_global=C * R)
+    common = (pd, poses[cams].to(dev), synth.CAMERA_ANGLE_X, imgs[cams].to(dev), R, S, delta)
+    ta = VoxelTrainer(grid.to(dev), *common, **mk)
+    tb = PeerVoxelTrainer(grid.to(dev), *common, **mk)
+    for step in range(4):
+        u = synth.random_uv(C, R, seed=50 + step)[cams].to(dev)
+        la, lb = ta.step(u).clone(), tb.step(u).clone()
+    torch.cuda.synchronize()
+    dgrid = float((ta.grid - tb.grid).abs().max())
+    q = float(torch.quantile((ta.grid - tb.grid).abs().flatten()[::7], 0.999))
+    dabs = float((ta.grad_abs_sum - tb.gathered_grad_abs_sum()).abs().max() / ta.grad_abs_sum.abs().max())
+    allsame = [torch.zeros_like(tb.grid) for _ in range(world)]
+    dist.all_gather(allsame, tb.grid.contiguous())
+    replicas_equal = all(torch.equal(allsame[0], t) for t in allsame)
+    if rank == 0:
+        print(f"peer vs nccl trainer after 4 steps: max|dgrid| {dgrid:.2e} (q99.9 {q:.2e}), |grad| sum rel {dabs:.2e}, "
+              f"loss {float(la):.7f}/{float(lb):.7f}, replicas equal: {replicas_equal}")
+        assert q <= 1e-5 and dabs <= 1e-5 and replicas_equal
+        print("PEER_OK")
     dist.barrier()
     dist.destroy_process_group()
 

@@ -1,0 +1,155 @@
+"""The reference-named Python surface (src/*.py -> plenoxels_b200/*.py): host-side logic on CPU, and on the GPU the loop
+body of the reference's fit() (scripts/train.py:104-191) written with the drop-in functions + torch.optim.Adam, checked
+against the torch-CPU port of the reference."""
+import numpy as np
+import pytest
+import torch
+
+import src.grid_functions as gf
+import src.ray_sampling as rs
+import src.rays_logic as rl
+from oracle import torch_port as tp
+from plenoxels_b200 import synth
+
+
+def test_src_shim_exposes_the_reference_names():
+    for name in ("generate_grid", "get_nearest_voxels", "average_pool3d_grid", "convolve_grid_to_remove_noise",
+                 "trilinear_interpolation", "get_grid_points_indices", "find_out_of_bound", "fix_out_of_bounds"):
+        assert callable(getattr(gf, name))
+    for name in ("sample_camera_rays_batched", "normalize_samples_for_indecies", "compute_alpha_weighted_pixels",
+                 "generate_rays_batched"):
+        assert callable(getattr(rs, name))
+    assert rl.compute_alpha_weighted_pixels is rs.compute_alpha_weighted_pixels
+    import src.data_processing as dp
+    import src.visualization as vz
+    assert callable(dp.load_data) and callable(dp.load_image_data_from_path)
+    assert callable(vz.visulize_3d_in_2d) and callable(vz.visulize_3d_in_2d_fast)
+
+
+@pytest.mark.parametrize("G,pd", [(8, 0.1), (93, 0.0125), (20, 0.05)])
+def test_generate_grid_layout_and_free_origin(G, pd):
+    """4-tuple of src/grid_functions.py:184-217; the coordinate tensors know their minimum without a reduction,
+    also after the slicing + reshape fit() applies while growing the grid (scripts/train.py:112-116)."""
+    coords, cells, mesh, grid_grid = gf.generate_grid(G, G, G + 1, points_distance=pd, info_size=4, device="cpu")
+    assert coords.shape == (G * G * (G + 1), 3) and coords.dtype == torch.float32
+    assert cells.shape == (G, G, G + 1, 4) and cells.requires_grad and float(cells.abs().sum()) == 0.0
+    assert mesh.shape == (G, G, G + 1, 3) and mesh.dtype == torch.int64
+    assert grid_grid.shape == (G, G, G + 1, 3)
+    ref = tp.cell_centres((G, G, G + 1), pd)
+    assert torch.equal(grid_grid.as_subclass(torch.Tensor), ref)
+    assert gf.coords_origin(coords) == tuple(ref.reshape(-1, 3).min(0)[0].tolist())
+    for start, stride in ((1, 2), (3, 5), (0, 1)):
+        if start >= G:
+            continue
+        sl = grid_grid[start::stride, start::stride, start::stride].reshape(-1, 3)
+        assert isinstance(sl, gf.GridCoords)
+        assert gf.coords_origin(sl) == tuple(sl.as_subclass(torch.Tensor).min(0)[0].tolist())
+    # anything else falls back to the real reduction
+    assert not isinstance(coords * 2, gf.GridCoords)
+    assert gf.coords_origin(coords * 2) == tuple((ref.reshape(-1, 3) * 2).min(0)[0].tolist())
+
+
+def test_index_helpers_match_reference_semantics():
+    ns = torch.tensor([[0.2, 1.5, -0.5], [3.7, -1.2, 2.0], [7.9, 7.0, 8.1]])
+    grid = torch.zeros(8, 8, 8, 4)
+    pts = gf.get_grid_points_indices(ns)
+    assert pts.shape == (3, 8, 3) and pts.dtype == torch.int64
+    assert pts[0, 0].tolist() == [1, 2, 0] and pts[0, 7].tolist() == [0, 1, -1]          # [ccc] ... [fff]
+    assert gf.find_out_of_bound(ns, grid).tolist() == [False, False, False]
+    assert gf.find_out_of_bound(torch.tensor([[0.0, 7.9, 3.0]]), grid).tolist() == [True]
+    idx = torch.tensor([[-1, 8, 3], [9, -9, 0]])
+    i0, i1, i2 = gf.fix_out_of_bounds(idx, grid)
+    assert idx.tolist() == [[7, 0, 3], [1, 7, 0]], "wrap is in place, python-style modulo"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pooled", [False, True])
+def test_fit_loop_body_on_dropin_functions_matches_reference_port(plx_lib, monkeypatch, pooled):
+    """scripts/train.py:130-184 with the drop-in functions, autograd and torch.optim.Adam on the GPU vs the torch-CPU port
+    of the reference; `pooled` routes the grid through average_pool3d_grid (channel-planar, strided) like :110-118."""
+    dev = "cuda:0"
+    G, C, H, R, S = 24, 3, 16, 64, 48
+    pd, delta, lr = synth.GRID_EXTENT / G, 6.0 / S, 0.0075
+    grid0, poses, imgs = synth.soft_grid(G), synth.lookat_poses(C), synth.random_images(C, H, H)
+    grid_indices, grid_cells_full, _, grid_grid = gf.generate_grid(G, G, G, points_distance=pd, info_size=4, device=dev)
+    with torch.no_grad():
+        grid_cells_full.copy_(grid0.to(dev))
+    opt = torch.optim.Adam([grid_cells_full], lr=lr)
+    port = tp.ReferenceStep(grid0, pd, poses, synth.CAMERA_ANGLE_X, imgs, R, S, delta, lr)
+    T, im = poses.to(dev), imgs.to(dev)
+    rf, stride = 3, 1
+    for step in range(3):
+        uv = synth.random_uv(C, R, seed=70 + step)
+        monkeypatch.setattr(torch, "rand", lambda *a, **k: uv.clone().to(k.get("device", "cpu")))
+        if pooled:
+            start = int(rf / 2)
+            gi = grid_grid[start::stride, start::stride, start::stride].reshape(-1, 3)
+            cells = gf.average_pool3d_grid(grid_cells_full, receptive_field_size=rf, stride=stride)
+            cur_pd = pd * stride
+        else:
+            gi, cells, cur_pd = grid_indices, grid_cells_full, pd
+        samples, targets, cam_pos, dirs = rs.sample_camera_rays_batched(
+            transform_matrices=T, camera_angle_x=synth.CAMERA_ANGLE_X, imgs=im, number_of_rays=R, num_samples=S,
+            delta_step=delta, even_spread=False, camera_ray=False, device=dev)
+        ns = rs.normalize_samples_for_indecies(gi, samples, cur_pd)
+        nearest, mask = gf.get_nearest_voxels(ns, cells.clip(0, 1))
+        nearest = nearest * mask.unsqueeze(-1)
+        pix = rs.compute_alpha_weighted_pixels(nearest.reshape(C, R, S, 4)).reshape(-1, 4)
+        loss = torch.nn.functional.mse_loss(pix, targets)
+        opt.zero_grad()
+        loss.backward()
+        monkeypatch.undo()
+        if pooled:
+            # reference side of the same pooled step
+            pg = port.grid
+            pc = torch.nn.functional.avg_pool3d(pg.permute(3, 0, 1, 2).unsqueeze(0), (rf,) * 3, stride=stride).squeeze().permute(1, 2, 3, 0)
+            centres = tp.cell_centres((G, G, G), pd)[start::stride, start::stride, start::stride].reshape(-1, 3)
+            d_ref, t_ref = tp.rays_from_uv(imgs, poses, synth.CAMERA_ANGLE_X, uv.clone())
+            pos = tp.place_samples(poses[:, :3, 3], d_ref, R, S, delta)
+            v_ref, m_ref = tp.nearest_lookup((pos - centres.min(0)[0]) / (pd * stride), pc.clip(0, 1))
+            pix_ref = tp.composite((v_ref * m_ref.unsqueeze(-1)).reshape(C, R, S, 4)).reshape(-1, 4)
+            loss_ref = torch.nn.functional.mse_loss(pix_ref, t_ref)
+            port.opt.zero_grad()
+            loss_ref.backward()
+            port.opt.step()
+        else:
+            loss_ref = port.step(uv)
+        assert abs(float(loss) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+        g, gr = grid_cells_full.grad.cpu(), port.grid.grad
+        assert float((g - gr).abs().max()) <= 1e-5 * float(gr.abs().max())
+        opt.step()
+    diff = (grid_cells_full.detach().cpu() - port.grid.detach()).abs()
+    assert float(torch.quantile(diff.flatten(), 0.999)) <= 1e-5
+
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REFERENCE), reason="reference tree only exists in the build container")
+def test_reference_scripts_import_unmodified_against_this_repo(tmp_path):
+    """`scripts/train.py` / `compare_inference_to_image.py` / `main.py` of the UNMODIFIED reference resolve every `src.*` import
+    to this repo (PYTHONPATH order), including `src.rays_logic`, which the reference itself lacks.
+    matplotlib / plotly are GUI-only and absent from the image, so empty stand-ins are put on the path."""
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    stubs = tmp_path / "stubs"
+    for mod in ("matplotlib", "plotly"):
+        (stubs / mod).mkdir(parents=True)
+    (stubs / "matplotlib" / "__init__.py").write_text("")
+    (stubs / "matplotlib" / "pyplot.py").write_text("")
+    (stubs / "plotly" / "__init__.py").write_text("")
+    (stubs / "plotly" / "graph_objects.py").write_text("")
+    (stubs / "plotly" / "io.py").write_text("")
+    (stubs / "plotly" / "express.py").write_text("")
+    code = ("import scripts.train as t, scripts.compare_inference_to_image as c, src.grid_functions as g;"
+            "import inspect, sys;"
+            "assert g.__file__.startswith(%r), g.__file__;"
+            "assert t.__file__.startswith(%r), t.__file__;"
+            "assert t.get_nearest_voxels is g.get_nearest_voxels;"
+            "print(list(inspect.signature(t.fit).parameters)[:4])") % (repo, REFERENCE)
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([repo, str(stubs), REFERENCE]))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "gridsize" in out.stdout

@@ -178,7 +178,10 @@ __global__ void __launch_bounds__(256) k_adam_mc(const float4* __restrict__ p_lo
 cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, cudaStream_t st) {
     const int64_t begin4 = a.begin / 4, end4 = a.end / 4;
     if (end4 <= begin4) return cudaSuccess;
-    static const int use_mc = adam_env("PLX_PEER_MULTICAST", 1);
+    // in-switch reduction pays off once several peers would otherwise be read one by one; with 2 ranks it only adds a
+    // round trip through the switch (measured: 93 vs 60 us at N=2, 69 vs 96 us at N=8).  PLX_PEER_MULTICAST=0/1 overrides.
+    static const int mc_env = adam_env("PLX_PEER_MULTICAST", -1);
+    const bool use_mc = mc_env >= 0 ? mc_env != 0 : a.world >= 4;
     if (a.grid_mc && a.grad_mc && use_mc) {
         int dev = 0, sms = 148, per_sm = 0;
         cudaGetDevice(&dev);

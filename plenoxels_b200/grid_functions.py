@@ -108,7 +108,13 @@ def get_nearest_voxels(normalized_samples_for_indices, grid, receptive_field=1):
     """Nearest-voxel values (M,4) at periodically wrapped indices + in-bounds mask (M,) — src/grid_functions.py:103-114.
     One gather kernel (round-half-even, mask, wrap, 16-byte cell read); differentiable w.r.t. `grid`."""
     L.require_cuda(normalized_samples_for_indices, grid)
-    return ops.gather_nearest(normalized_samples_for_indices, grid)
+    from . import lazy
+    ns = normalized_samples_for_indices
+    if isinstance(ns, lazy.LazyTensor):
+        if ns._kind == "normalized" and ns._real is None and grid.dim() == 4 and grid.shape[3] == 4 and grid.dtype == torch.float32:
+            return lazy.lazy_lookup(ns, grid)           # stays lazy: see plenoxels_b200/lazy.py
+        ns = ns.materialize()
+    return ops.gather_nearest(ns, grid)
 
 
 def get_grid_points_indices(normalized_samples_for_indecies):
@@ -123,6 +129,9 @@ def trilinear_interpolation(normalized_samples_for_indecies, selected_points, gr
     """(N,info) trilinear values — src/grid_functions.py:7-44.  `selected_points` must be the (wrapped) corners of
     `get_grid_points_indices` for the same samples; the kernel recomputes them from the coordinates."""
     L.require_cuda(normalized_samples_for_indecies, grid_cells)
+    from . import lazy
+    if isinstance(normalized_samples_for_indecies, lazy.LazyTensor):
+        normalized_samples_for_indecies = normalized_samples_for_indecies.materialize()
     vals, _ = ops.trilinear_lookup(normalized_samples_for_indecies, grid_cells, masked=False)
     return vals
 

@@ -8,15 +8,26 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+import os
+
 from . import _lib as L
-from . import ops
+from . import lazy, ops
 from .grid_functions import coords_origin
+
+
+def _lazy_enabled() -> bool:
+    """PLX_LAZY=0 turns the lazy-fusion bridge off (every function then materialises its result)."""
+    return os.environ.get("PLX_LAZY", "1") != "0"
 
 
 def normalize_samples_for_indecies(grid_indices, samples_interval, points_distance):
     """(samples - grid_indices.min(0)[0]) / points_distance — src/ray_sampling.py:12-13.
     The minimum is taken from the grid's metadata when `grid_indices` came from `generate_grid` (no G^3 reduction)."""
     L.require_cuda(samples_interval)
+    if isinstance(samples_interval, lazy.LazyTensor) and samples_interval._kind == "samples" and samples_interval._real is None:
+        return lazy.lazy_normalized(samples_interval, coords_origin(grid_indices), points_distance)
+    if isinstance(samples_interval, lazy.LazyTensor):
+        samples_interval = samples_interval.materialize()
     return ops.normalize_points(samples_interval, coords_origin(grid_indices), points_distance)
 
 
@@ -45,14 +56,23 @@ def sample_camera_rays_batched(transform_matrices, camera_angle_x, imgs, number_
     dirs, pixels_to_rays = generate_rays_batched(imgs, number_of_rays, transform_matrices, camera_angle_x,
                                                  even_spread=even_spread, device=device)
     camera_positions = transform_matrices[:, :3, 3]
-    samples_interval = ops.sample_points(camera_positions.float(), dirs, num_samples, delta_step,
-                                         rays_per_origin=number_of_rays)
+    if _lazy_enabled():
+        # a handle, not (C*R*S,3) floats: the positions only exist if someone other than the fused march asks for them
+        samples_interval = lazy.lazy_samples(camera_positions.float(), dirs, number_of_rays, num_samples, delta_step)
+    else:
+        samples_interval = ops.sample_points(camera_positions.float(), dirs, num_samples, delta_step,
+                                             rays_per_origin=number_of_rays)
     return samples_interval, pixels_to_rays, camera_positions, dirs
 
 
 def compute_alpha_weighted_pixels(samples):
     """(C,R,S,4) -> (C,R,4) front-to-back compositing — src/ray_sampling.py:172-192 (warp-scan kernel, differentiable)."""
     L.require_cuda(samples)
+    if isinstance(samples, lazy.LazyTensor):
+        fused = lazy.fused_composite(samples)          # masked (C,R,S,4) lookup of lazy samples -> one fused march (K1/K2)
+        if fused is not None:
+            return fused
+        samples = samples.materialize()
     return ops.composite(samples)
 
 

@@ -191,42 +191,74 @@ class PeerVoxelTrainer(VoxelTrainer):
             raise L.PlxError(f"at most {L.PLX_MAX_PEERS} peers")
         shape = tuple(self.grid.shape)
         sym_grid = symm_mem.empty(shape, dtype=torch.float32, device=dev)
-        sym_grad = symm_mem.empty(shape, dtype=torch.float32, device=dev)
         sym_grid.copy_(self.grid)
-        sym_grad.zero_()
         self._h_grid = symm_mem.rendezvous(sym_grid, group)
-        self._h_grad = symm_mem.rendezvous(sym_grad, group)
-        self.grid, self.grad = sym_grid, sym_grad
+        self.grid = sym_grid
         dist.broadcast(self.grid, src=dist.get_global_rank(group, 0), group=group)      # identical replicas to start from
+        # two gradient buffers, used on alternate steps: the one consumed by step i is cleared on a side stream while
+        # step i+1 renders into the other, so the 16 B/cell clear never sits on the critical path
+        self._grads, self._h_grads = [], []
+        for _ in range(2):
+            gbuf = symm_mem.empty(shape, dtype=torch.float32, device=dev)
+            gbuf.zero_()
+            self._grads.append(gbuf)
+            self._h_grads.append(symm_mem.rendezvous(gbuf, group))
+        self.grad = self._grads[0]
+        self._clear_stream = torch.cuda.Stream(device=dev)
+        self._cleared = [None, None]          # event: buffer b is zero again
         self._args = self._make_args()
-        p = L.PlxAdamPeer()
-        p.world, p.rank = self.world, self.rank
-        for r in range(self.world):
-            p.grids[r] = int(self._h_grid.buffer_ptrs[r])
-            p.grads[r] = int(self._h_grad.buffer_ptrs[r])
-        p.exp_avg, p.exp_avg_sq, p.grad_abs_sum = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.grad_abs_sum.data_ptr()
-        p.begin, p.end = slab_range(self.grid.numel() // 4, self.rank, self.world)
-        p.lr, p.beta1, p.beta2, p.eps = self.lr, self.betas[0], self.betas[1], self.eps
-        # NVLS multicast mappings of the same buffers, when the fabric offers them (in-switch reduce / replicate)
+        slab = slab_range(self.grid.numel() // 4, self.rank, self.world)
         self.multicast = False
-        try:
-            mc_grid, mc_grad = int(self._h_grid.multicast_ptr or 0), int(self._h_grad.multicast_ptr or 0)
-            if mc_grid and mc_grad:
-                p.grid_mc, p.grad_mc = mc_grid, mc_grad
-                self.multicast = True
-        except Exception:           # no multicast support: per-peer pointers are used
-            pass
-        self._peer = p
+        self._peers = []
+        for b in range(2):
+            p = L.PlxAdamPeer()
+            p.world, p.rank = self.world, self.rank
+            for r in range(self.world):
+                p.grids[r] = int(self._h_grid.buffer_ptrs[r])
+                p.grads[r] = int(self._h_grads[b].buffer_ptrs[r])
+            p.exp_avg, p.exp_avg_sq, p.grad_abs_sum = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.grad_abs_sum.data_ptr()
+            p.begin, p.end = slab
+            p.lr, p.beta1, p.beta2, p.eps = self.lr, self.betas[0], self.betas[1], self.eps
+            # NVLS multicast mappings of the same buffers, when the fabric offers them (in-switch reduce / replicate)
+            try:
+                mc_grid, mc_grad = int(self._h_grid.multicast_ptr or 0), int(self._h_grads[b].multicast_ptr or 0)
+                if mc_grid and mc_grad:
+                    p.grid_mc, p.grad_mc = mc_grid, mc_grad
+                    self.multicast = True
+            except Exception:       # no multicast support: per-peer pointers are used
+                pass
+            self._peers.append(p)
+        self._peer = self._peers[0]
+        self._cur = 0
         self.launches_per_step = 2
         torch.cuda.synchronize(dev)
         dist.barrier(group)
 
+    def render_phase(self, uv=None) -> None:
+        b = self.step_count % 2                 # buffer of the step about to run
+        self._cur = b
+        self.grad = self._grads[b]
+        self._args.grad = self.grad.data_ptr()
+        if self._cleared[b] is not None:        # its clear (issued two steps ago on the side stream) must have finished
+            torch.cuda.current_stream(self.device).wait_event(self._cleared[b])
+        super().render_phase(uv)
+
     def _exchange_and_update(self, st):
-        self._peer.step = self.step_count
-        self._h_grad.barrier(channel=0)                       # every rank's partial gradient is complete
-        L.check(self.lib.plx_adam_step_peer(C.byref(self._peer), st), "plx_adam_step_peer")
-        self._h_grad.barrier(channel=1)                       # every replica holds the new parameters; peers done reading
-        self.grad.zero_()
+        b = self._cur
+        peer = self._peers[b]
+        peer.step = self.step_count
+        h = self._h_grads[b]
+        h.barrier(channel=0)                                  # every rank's partial gradient is complete
+        L.check(self.lib.plx_adam_step_peer(C.byref(peer), st), "plx_adam_step_peer")
+        h.barrier(channel=1)                                  # every replica holds the new parameters; peers done reading
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._clear_stream):
+            self._clear_stream.wait_event(done)
+            self._grads[b].zero_()
+            ev = torch.cuda.Event()
+            ev.record(self._clear_stream)
+        self._cleared[b] = ev
 
     def update_phase(self) -> None:
         with torch.cuda.device(self.device):
@@ -238,6 +270,12 @@ class PeerVoxelTrainer(VoxelTrainer):
         return self.loss
 
     def step_host(self, uv_host):
+        b = self.step_count % 2
+        self._cur = b
+        self.grad = self._grads[b]
+        self._args.grad = self.grad.data_ptr()
+        if self._cleared[b] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._cleared[b])
         self.step_count += 1
         self._args.step = self.step_count
         st = L.stream_ptr(self.device)
@@ -250,7 +288,7 @@ class PeerVoxelTrainer(VoxelTrainer):
     def gathered_grad_abs_sum(self):
         """Full `grid_grad` (scripts/train.py:184): each rank accumulated |grad| for the cells it owns only."""
         full = self.grad_abs_sum.clone()
-        b, e = self._peer.begin, self._peer.end
+        b, e = self._peers[0].begin, self._peers[0].end
         flat = full.view(-1)
         mask = torch.zeros_like(flat)
         mask[b:e] = 1

@@ -153,3 +153,48 @@ def test_reference_scripts_import_unmodified_against_this_repo(tmp_path):
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=str(tmp_path))
     assert out.returncode == 0, out.stderr[-2000:]
     assert "gridsize" in out.stdout
+
+
+@pytest.mark.gpu
+def test_lazy_bridge_fuses_and_falls_back(plx_lib, monkeypatch):
+    """The unfused reference call sequence returns lazy handles and ends in ONE fused march; an unrecognised op (the
+    beta-loss slice of scripts/train.py:172) materialises through the eager kernels; both equal the fully eager path."""
+    from plenoxels_b200 import lazy
+    dev = "cuda:0"
+    G, C, H, R, S = 20, 3, 16, 48, 40
+    pd, delta, beta = synth.GRID_EXTENT / G, 6.0 / S, 5e-3
+    poses, imgs = synth.lookat_poses(C).to(dev), synth.random_images(C, H, H).to(dev)
+    uv = synth.random_uv(C, R, seed=5)
+    grid0 = synth.soft_grid(G).to(dev)
+    results = {}
+    for mode in ("lazy", "eager"):
+        monkeypatch.setenv("PLX_LAZY", "1" if mode == "lazy" else "0")
+        monkeypatch.setattr(torch, "rand", lambda *a, **k: uv.clone().to(k.get("device", "cpu")))
+        gi, cells, _, _ = gf.generate_grid(G, G, G, points_distance=pd, info_size=4, device=dev)
+        with torch.no_grad():
+            cells.copy_(grid0)
+        samples, targets, cam_pos, dirs = rs.sample_camera_rays_batched(
+            transform_matrices=poses, camera_angle_x=synth.CAMERA_ANGLE_X, imgs=imgs, number_of_rays=R, num_samples=S,
+            delta_step=delta, even_spread=False, camera_ray=False, device=dev)
+        ns = rs.normalize_samples_for_indecies(gi, samples, pd)
+        nearest, mask = gf.get_nearest_voxels(ns, cells.clip(0, 1))
+        nearest = nearest * mask.unsqueeze(-1)
+        nearest = nearest.reshape(C, R, S, 4)
+        if mode == "lazy":
+            assert all(isinstance(t, lazy.LazyTensor) for t in (samples, ns, nearest, mask))
+            assert nearest._spec["masked"] and nearest._real is None and tuple(nearest.shape) == (C, R, S, 4)
+        pix = rs.compute_alpha_weighted_pixels(nearest)
+        assert not isinstance(pix, lazy.LazyTensor) and tuple(pix.shape) == (C, R, 4)
+        loss = torch.nn.functional.mse_loss(pix.reshape(-1, 4), targets)
+        eps = 1e-4
+        a = nearest[:, :, :, -1]                                       # unrecognised op -> materialises
+        assert not isinstance(a, lazy.LazyTensor)
+        loss = loss + beta * (torch.log(a + eps) - torch.log(1 - a + eps)).mean()
+        loss.backward()
+        monkeypatch.undo()
+        results[mode] = (pix.detach().cpu(), float(loss), cells.grad.detach().cpu(),
+                         samples.materialize().cpu() if mode == "lazy" else samples.cpu())
+    assert torch.equal(results["lazy"][3], results["eager"][3]), "materialised sample positions are the eager ones"
+    assert float((results["lazy"][0] - results["eager"][0]).abs().max()) <= 2e-6
+    assert abs(results["lazy"][1] - results["eager"][1]) <= 1e-6 * abs(results["eager"][1])
+    assert float((results["lazy"][2] - results["eager"][2]).abs().max()) <= 2e-6 * float(results["eager"][2].abs().max())

@@ -17,9 +17,9 @@ def timeit(fn, n=50):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1)/n*1000
-tr.step_count += 1; tr._peer.step = tr.step_count
+tr.step_count += 1; tr._peers[0].step = tr.step_count; tr._peer = tr._peers[0]
 res = {}
-res['barrier'] = timeit(lambda: tr._h_grad.barrier(channel=0))
+res["barrier"] = timeit(lambda: tr._h_grads[0].barrier(channel=0))
 for U in (1,2,4):
     os.environ["X"]=str(U)
 res["adam_peer"] = timeit(lambda: L.check(tr.lib.plx_adam_step_peer(C.byref(tr._peer), st)))

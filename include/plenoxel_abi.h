@@ -43,6 +43,9 @@ extern "C" {
 #define PLX_CLAMP01 1u        /* look the grid up through clip(0,1) (scripts/train.py:146); backward applies the pass-mask */
 #define PLX_NO_CLIP 2u        /* visit every sample k = 1..S (disable the conservative ray/box pre-filter) */
 #define PLX_NO_EARLY_STOP 4u  /* keep marching after the transmittance reached exactly 0 */
+#define PLX_COHERENT_RAYS 8u  /* hint: consecutive rays are neighbouring pixels of one view (inference, even-spread lattice);
+                                 plx_render_fwd then marches one ray per THREAD, 32 neighbouring rays per warp, so that the
+                                 lanes of a load hit neighbouring cells (sector / L1 reuse) and no warp scan is needed */
 
 /* Ray-marching geometry shared by the fused kernels. */
 typedef struct PlxMarch {

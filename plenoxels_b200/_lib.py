@@ -16,7 +16,7 @@ c_f32p = C.POINTER(C.c_float)
 c_void = C.c_void_p
 
 PLX_NEAREST, PLX_TRILINEAR = 0, 1
-PLX_CLAMP01, PLX_NO_CLIP, PLX_NO_EARLY_STOP = 1, 2, 4
+PLX_CLAMP01, PLX_NO_CLIP, PLX_NO_EARLY_STOP, PLX_COHERENT_RAYS = 1, 2, 4, 8
 PLX_STEP_RENDER, PLX_STEP_OPTIM, PLX_STEP_ALL = 1, 2, 3
 MODES = {"nearest": PLX_NEAREST, "trilinear": PLX_TRILINEAR}
 
@@ -170,7 +170,7 @@ def stream_ptr(device) -> int:
 
 
 def make_march(grid: torch.Tensor, num_samples: int, delta_step: float, gmin, points_distance: float, mode: str,
-               clamp: bool, no_clip: bool = False, no_early_stop: bool = False) -> PlxMarch:
+               clamp: bool, no_clip: bool = False, no_early_stop: bool = False, coherent: bool = False) -> PlxMarch:
     if grid.dim() != 4 or grid.shape[3] != 4:
         raise PlxError(f"grid must be (X,Y,Z,4), got {tuple(grid.shape)}")
     if grid.dtype != torch.float32:
@@ -184,7 +184,8 @@ def make_march(grid: torch.Tensor, num_samples: int, delta_step: float, gmin, po
     m.points_distance = float(points_distance)
     m.delta_step = float(delta_step)
     m.mode = MODES[mode]
-    m.flags = (PLX_CLAMP01 if clamp else 0) | (PLX_NO_CLIP if no_clip else 0) | (PLX_NO_EARLY_STOP if no_early_stop else 0)
+    m.flags = ((PLX_CLAMP01 if clamp else 0) | (PLX_NO_CLIP if no_clip else 0) | (PLX_NO_EARLY_STOP if no_early_stop else 0)
+               | (PLX_COHERENT_RAYS if coherent else 0))
     return m
 
 

@@ -100,6 +100,44 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) k_render_fwd(const P
 }
 
 // =================================================================================================================
+// K1p — forward for coherent rays (inference): one ray per thread, 32 neighbouring rays per warp
+// =================================================================================================================
+// Image-order rays of one view pass through neighbouring cells at equal depth, so the 32 lanes of a load share sectors
+// and L1 lines; the transmittance recurrence runs sequentially in registers (no warp scan), UNR samples are looked up
+// (independent loads) before they are composited.  Same exact index arithmetic, same results as K1 up to summation order.
+template <int MODE, bool FAST, int UNR>
+__global__ void __launch_bounds__(128) k_render_fwd_packet(const PlxRenderFwd a) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= a.rays.n_rays) return;
+    const PlxMarch& m = a.march;
+    const Geo g = make_geo(m);
+    const Ray r = load_ray(a.rays, ray);
+    const bool fast_ray = FAST && ray_in_fast_range(m, r);
+    int k0, k1;
+    clip_range(m, r, k0, k1);
+    float T = 1.f, ar = 0.f, ag = 0.f, ab = 0.f, aa = 0.f, ad = 0.f;
+    for (int kb = k0; kb <= k1 && T != 0.f; kb += UNR) {
+        float4 c[UNR];
+        float t[UNR];
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            TriGeom tg;
+            c[j] = lookup<MODE, FAST>(m, g, a.grid, r, fast_ray, kb + j, kb + j <= k1, true, t[j], tg).c;
+        }
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const float w = c[j].w * T;                   // alpha_k * T_k, src/ray_sampling.py:184
+            ar = fmaf(w, c[j].x, ar); ag = fmaf(w, c[j].y, ag); ab = fmaf(w, c[j].z, ab);
+            aa += w;
+            ad = fmaf(w, t[j], ad);
+            T *= 1.f - c[j].w;
+        }
+    }
+    reinterpret_cast<float4*>(a.rgba)[ray] = make_float4(ar, ag, ab, aa);
+    if (a.depth) a.depth[ray] = ad;
+}
+
+// =================================================================================================================
 // K2 — backward
 // =================================================================================================================
 template <int MODE, bool FAST>
@@ -207,6 +245,17 @@ cudaError_t launch_render_fwd(const PlxRenderFwd& a, cudaStream_t st) {
     const unsigned blocks = (unsigned)((a.rays.n_rays + wpb - 1) / wpb);
     const bool fast = fast_ok(a.march, a.grid);
     const bool dbg = a.count || a.sample_index || (a.march.flags & PLX_NO_EARLY_STOP);
+    if ((a.march.flags & PLX_COHERENT_RAYS) && !dbg && !a.tcarry && !a.targets) {
+        const unsigned pblocks = (unsigned)((a.rays.n_rays + 127) / 128);
+        if (a.march.mode == PLX_NEAREST) {
+            if (fast) k_render_fwd_packet<PLX_NEAREST, true, 4><<<pblocks, 128, 0, st>>>(a);
+            else      k_render_fwd_packet<PLX_NEAREST, false, 4><<<pblocks, 128, 0, st>>>(a);
+        } else {
+            if (fast) k_render_fwd_packet<PLX_TRILINEAR, true, 1><<<pblocks, 128, 0, st>>>(a);
+            else      k_render_fwd_packet<PLX_TRILINEAR, false, 1><<<pblocks, 128, 0, st>>>(a);
+        }
+        return cudaGetLastError();
+    }
 #define PLX_FWD(MODE)                                                                                     \
     do {                                                                                                  \
         if (fast) { if (dbg) k_render_fwd<MODE, true, true><<<blocks, wpb * 32, 0, st>>>(a);              \

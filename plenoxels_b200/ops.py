@@ -28,16 +28,17 @@ def grid_origin(dims, points_distance: float, start_index=0):
 class _RenderRays(torch.autograd.Function):
     @staticmethod
     def forward(ctx, grid, origins, dirs, rays_per_origin, num_samples, delta_step, gmin, points_distance, mode, clamp,
-                want_depth, want_count, beta_over_m):
+                want_depth, want_count, beta_over_m, coherent):
         dev = L.require_cuda(grid, origins, dirs)
         lib = L.load()
         n = dirs.shape[0]
-        march = L.make_march(grid, num_samples, delta_step, gmin, points_distance, mode, clamp)
+        need_grad = grid.requires_grad
+        march = L.make_march(grid, num_samples, delta_step, gmin, points_distance, mode, clamp,
+                             coherent=coherent and not need_grad and not want_count)
         rays = L.make_rays(origins, dirs, rays_per_origin)
         rgba = torch.empty((n, 4), dtype=torch.float32, device=dev)
         depth = torch.empty((n,), dtype=torch.float32, device=dev) if want_depth else None
         count = torch.empty((n,), dtype=torch.int32, device=dev) if want_count else None
-        need_grad = grid.requires_grad
         tcarry = torch.empty((n, lib.plx_num_chunks(num_samples)), dtype=torch.float32, device=dev) if need_grad else None
         a = L.PlxRenderFwd()
         a.march, a.rays = march, rays
@@ -71,11 +72,11 @@ class _RenderRays(torch.autograd.Function):
         b.beta_over_m = float(beta_over_m)
         with torch.cuda.device(dev):
             L.check(lib.plx_render_bwd(C.byref(b), L.stream_ptr(dev)), "plx_render_bwd")
-        return (grad_grid,) + (None,) * 12
+        return (grad_grid,) + (None,) * 13
 
 
 def render_rays(grid, origins, dirs, num_samples, delta_step, gmin, points_distance, mode="nearest", clamp=True,
-                rays_per_origin=1, return_depth=False, return_count=False, beta_over_m=0.0):
+                rays_per_origin=1, return_depth=False, return_count=False, beta_over_m=0.0, coherent=False):
     """Fused march: rgba (N,4) [, depth (N,), count (N,) int32] of rays through `grid` (X,Y,Z,4).
 
     One kernel for the sequence scripts/train.py:130-151: sample_camera_rays_batched (src/ray_sampling.py:161-167),
@@ -83,10 +84,12 @@ def render_rays(grid, origins, dirs, num_samples, delta_step, gmin, points_dista
     trilinear lookup (:7-44,:220-246), mask multiply, compute_alpha_weighted_pixels (src/ray_sampling.py:172-192).
     Differentiable w.r.t. `grid` (K2).  `beta_over_m` = beta / M adds the gradient of the sparsity loss of
     scripts/train.py:170-177 in the backward pass (its value is not part of the returned pixels).
+    `coherent=True` (inference only: ignored when a gradient or the count is requested) tells the library that consecutive
+    rays are neighbouring pixels of a view; it then marches one ray per thread in packets of 32 (PLX_COHERENT_RAYS).
     """
     return _RenderRays.apply(grid, origins, dirs, int(rays_per_origin), int(num_samples), float(delta_step),
                              tuple(float(x) for x in gmin), float(points_distance), mode, bool(clamp),
-                             bool(return_depth), bool(return_count), float(beta_over_m))
+                             bool(return_depth), bool(return_count), float(beta_over_m), bool(coherent))
 
 
 def sample_indices(grid, origins, dirs, num_samples, delta_step, gmin, points_distance, mode="nearest",

@@ -26,7 +26,7 @@ def visulize_3d_in_2d(grid_cells_data, transform_matrices, camera_angle_x, imgs,
     poses = transform_matrices.to(device).float()
     dirs, _ = ops.generate_rays(None, poses, camera_angle_x, uv=None, rays_per_cam=n_side * n_side, want_targets=False)
     pix = ops.render_rays(grid, poses[:, :3, 3], dirs, num_samples, delta, coords_origin(grid_indices), pd, clamp=False,
-                          rays_per_origin=n_side * n_side)
+                          rays_per_origin=n_side * n_side, coherent=True)
     res = int(np.sqrt(number_of_rays))
     img = (pix.cpu().numpy() * 255).round().clip(0, 255).astype(np.uint8).reshape(res, res, 4)
     return np.transpose(img, (1, 0, 2))

@@ -55,6 +55,17 @@ def test_forward_rgba_depth_count(case, mode):
 
 
 @pytest.mark.parametrize("mode", ["nearest", "trilinear"])
+def test_forward_coherent_ray_packets(case, mode):
+    """PLX_COHERENT_RAYS (one ray per thread, packets of 32) renders the same pixels and depth as the oracle."""
+    d = case.cuda()
+    rgba, depth = ops.render_rays(d["grid"], d["origins"], d["dirs"], case.S, case.delta, case.gmin, case.pd, mode=mode,
+                                  rays_per_origin=case.R, return_depth=True, coherent=True)
+    orgba, odepth, _, _ = case.oracle_forward(mode)
+    assert rel_err(rgba.cpu().numpy(), orgba) <= TOL
+    assert rel_err(depth.cpu().numpy(), odepth) <= TOL
+
+
+@pytest.mark.parametrize("mode", ["nearest", "trilinear"])
 @pytest.mark.parametrize("beta", [0.0, 5e-3])
 def test_backward_grid_gradient(case, mode, beta):
     d = case.cuda()

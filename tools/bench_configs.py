@@ -44,11 +44,14 @@ def c4(mode="nearest"):
     n = side * side
     _, cnt = ops.render_rays(grid, o, dirs, S, delta, gmin, pd, mode=mode, clamp=False, rays_per_origin=n, return_count=True)
     m_in = int(cnt.sum())
-    ms = timed(lambda: ops.render_rays(grid, o, dirs, S, delta, gmin, pd, mode=mode, clamp=False, rays_per_origin=n), n=10)
     per = 16 * (8 if mode == "trilinear" else 1)
-    gbs = (per * m_in + 40 * n) / (ms * 1e-3) / 1e9
-    print(json.dumps({"config": "c4", "mode": mode, "rays": n, "S": S, "m_in": m_in, "ms_per_frame": ms,
-                      "Mrays_per_s": n / ms / 1e3, "algorithmic_GBs": gbs, "frac_of_measured_peak": gbs / PEAK}))
+    for coherent in (False, True):
+        ms = timed(lambda: ops.render_rays(grid, o, dirs, S, delta, gmin, pd, mode=mode, clamp=False, rays_per_origin=n,
+                                           coherent=coherent), n=10)
+        gbs = (per * m_in + 40 * n) / (ms * 1e-3) / 1e9
+        print(json.dumps({"config": "c4", "mode": mode, "kernel": "ray packets (thread/ray)" if coherent else "warp/ray",
+                          "rays": n, "S": S, "m_in": m_in, "ms_per_frame": ms, "Mrays_per_s": n / ms / 1e3,
+                          "algorithmic_GBs": gbs, "frac_of_measured_peak": gbs / PEAK}))
 
 
 def c5():

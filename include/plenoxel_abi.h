@@ -190,6 +190,11 @@ typedef struct PlxAdamPeer {
      * (`multimem.st.v4.f32`), which halves the bytes every GPU moves over its NVLink ports. */
     float* grid_mc;
     const float* grad_mc;
+    /* optional step tail (same contract as plx_train_step / plx_train_step_host): publish *loss_src to result_host
+     * { float loss; int32_t step; } and clear *loss_clear.  Any of the three may be NULL. */
+    const float* loss_src;
+    float* loss_clear;
+    void* result_host;
 } PlxAdamPeer;
 int plx_adam_step_peer(const PlxAdamPeer* args, void* stream);
 
@@ -245,7 +250,10 @@ int plx_selftest_arith(float y, uint64_t n, uint64_t seed, uint64_t* mismatches,
  *   plx_generate_rays -> plx_render_fwd (+MSE epilogue) -> plx_render_bwd -> [caller's collective] -> plx_adam_step.
  * `phase` selects which part runs so a multi-GPU caller can put the gradient all-reduce between the two halves:
  *   PLX_STEP_RENDER = rays + forward + loss + backward;  PLX_STEP_OPTIM = Adam;  PLX_STEP_ALL = both.
- * Scratch (dirs, targets, rgba, grad_rgba, tcarry) is caller-provided.  loss[0] is zeroed by the call.
+ * Scratch (dirs, targets, rgba, grad_rgba, tcarry) is caller-provided.
+ * `loss` points to TWO floats that the caller zeroes once: step s accumulates its loss into loss[s & 1] and the optimiser
+ * phase clears loss[(s + 1) & 1] for the next step, so no per-step memset is needed and loss[s & 1] stays readable
+ * until step s + 2 runs.
  */
 #define PLX_STEP_RENDER 1
 #define PLX_STEP_OPTIM 2
@@ -270,11 +278,16 @@ typedef struct PlxTrainStep {
 int plx_train_step(const PlxTrainStep* args, int32_t phase, void* stream);
 
 /*
- * The same step driven from HOST buffers (the end-to-end path): copies this step's `uv_host` (pinned, C*R*2 floats)
- * to args->uv on `stream`, runs the phases, and copies loss[0] back to `loss_host` (pinned).  Asynchronous; the caller
- * synchronises the stream before reading `loss_host`.
+ * The same step driven from HOST buffers (the end-to-end path), still exactly two kernel launches:
+ *   - `uv_host` (C*R*2 floats) must be PINNED host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory): the march
+ *     kernel reads this step's uv straight out of it over PCIe (zero-copy, 8 bytes per ray), no staging copy;
+ *   - `result_host` (pinned, 8 bytes) receives { float loss; int32_t step; }: the optimiser kernel stores the step's loss
+ *     and then, after a system-scope fence, the step number.  The host may poll result_host[1] == step (or synchronise
+ *     the stream) and then read the loss.
+ * Asynchronous on `stream`.  With phase = PLX_STEP_RENDER only, nothing is published (the caller's own optimiser
+ * phase does that: plx_train_step_host(..., PLX_STEP_OPTIM) or plx_adam_step_peer).
  */
-int plx_train_step_host(const PlxTrainStep* args, const float* uv_host, float* loss_host, int32_t phase, void* stream);
+int plx_train_step_host(const PlxTrainStep* args, const float* uv_host, void* result_host, int32_t phase, void* stream);
 
 #ifdef __cplusplus
 }

@@ -66,7 +66,8 @@ class PlxAdamPeer(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("grids", c_void * PLX_MAX_PEERS),
                 ("grads", c_void * PLX_MAX_PEERS), ("exp_avg", c_void), ("exp_avg_sq", c_void), ("grad_abs_sum", c_void),
                 ("begin", C.c_int64), ("end", C.c_int64), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
-                ("eps", C.c_double), ("step", C.c_int64), ("grid_mc", c_void), ("grad_mc", c_void)]
+                ("eps", C.c_double), ("step", C.c_int64), ("grid_mc", c_void), ("grad_mc", c_void),
+                ("loss_src", c_void), ("loss_clear", c_void), ("result_host", c_void)]
 
 
 class PlxTrainStep(C.Structure):

@@ -125,7 +125,7 @@ int plx_adam_step(float* p, float* g, float* m, float* v, float* gabs, int64_t n
     if (n > 0 && (!p || !g || !m || !v)) return fail(PLX_E_NULL, "p/g/m/v is NULL");
     if (step < 1) return fail(PLX_E_SHAPE, "step counts from 1");
     return cuda_result(plx::launch_adam(p, g, m, v, gabs, n, adam_scalars(lr, beta1, beta2, eps, step), zero_grad != 0,
-                                        (cudaStream_t)stream), "plx_adam_step");
+                                        plx::StepTail{nullptr, nullptr, nullptr, 0}, (cudaStream_t)stream), "plx_adam_step");
 }
 
 int plx_adam_step_peer(const PlxAdamPeer* a, void* stream) {
@@ -141,7 +141,8 @@ int plx_adam_step_peer(const PlxAdamPeer* a, void* stream) {
     }
     if ((uintptr_t)a->exp_avg % 16 || (uintptr_t)a->exp_avg_sq % 16 || (uintptr_t)a->grad_abs_sum % 16)
         return fail(PLX_E_ALIGN, "optimizer state must be 16-byte aligned");
-    return cuda_result(plx::launch_adam_peer(*a, adam_scalars(a->lr, a->beta1, a->beta2, a->eps, a->step), (cudaStream_t)stream),
+    const plx::StepTail tail{a->loss_src, a->loss_clear, (float*)a->result_host, (int32_t)a->step};
+    return cuda_result(plx::launch_adam_peer(*a, adam_scalars(a->lr, a->beta1, a->beta2, a->eps, a->step), tail, (cudaStream_t)stream),
                        "plx_adam_step_peer");
 }
 
@@ -245,16 +246,19 @@ int plx_selftest_arith(float y, uint64_t n, uint64_t seed, uint64_t* mismatches,
     return cuda_result(plx::launch_selftest(y, n, seed, (unsigned long long*)mismatches, (cudaStream_t)stream), "plx_selftest_arith");
 }
 
-int plx_train_step(const PlxTrainStep* a, int32_t phase, void* stream) {
+// shared body of plx_train_step / plx_train_step_host: `uv` is where the march reads this step's uv from (device memory,
+// or pinned host memory for the zero-copy end-to-end path); `result_host` receives {loss, step} from the optimiser kernel
+static int train_step_impl(const PlxTrainStep* a, const float* uv, void* result_host, int32_t phase, void* stream) {
     if (!a) return fail(PLX_E_NULL, "args is NULL");
-    cudaStream_t st = (cudaStream_t)stream;
     int rc;
     const int64_t n_rays = (int64_t)a->n_cams * a->rays_per_cam;
+    if (!a->loss) return fail(PLX_E_NULL, "train step: loss (2 floats) is NULL");
+    float* loss_now = a->loss + (a->step & 1);
+    float* loss_next = a->loss + ((a->step + 1) & 1);
     if (phase & PLX_STEP_RENDER) {
-        if (!a->uv || !a->dirs || !a->targets || !a->rgba || !a->grad_rgba || !a->loss || !a->grad)
-            return fail(PLX_E_NULL, "train step: uv/scratch/loss/grad pointer is NULL");
+        if (!uv || !a->dirs || !a->targets || !a->rgba || !a->grad_rgba || !a->grad)
+            return fail(PLX_E_NULL, "train step: uv/scratch/grad pointer is NULL");
         if (a->n_rays_global < n_rays) return fail(PLX_E_SHAPE, "n_rays_global < local ray count");
-        if ((rc = cuda_result(cudaMemsetAsync(a->loss, 0, sizeof(float), st), "memset loss")) != PLX_OK) return rc;
         const float grad_scale = (float)(2.0 / (4.0 * (double)a->n_rays_global));
         const float loss_scale = (float)(1.0 / (4.0 * (double)a->n_rays_global));
         // preferred: one fused kernel (ray generation + forward + loss + backward); PLX_TRAIN_FUSED=0 forces the 3-kernel path
@@ -264,58 +268,57 @@ int plx_train_step(const PlxTrainStep* a, int32_t phase, void* stream) {
         t.march = a->march;
         t.rays.n_rays = n_rays;
         t.gen.imgs = a->imgs; t.gen.n_cams = a->n_cams; t.gen.img_h = a->img_h; t.gen.img_w = a->img_w;
-        t.gen.poses = a->poses; t.gen.fov = a->fov; t.gen.uv = a->uv; t.gen.rays_per_cam = a->rays_per_cam;
-        t.grid = a->grid; t.grad_grid = a->grad; t.rgba = a->rgba; t.loss = a->loss;
+        t.gen.poses = a->poses; t.gen.fov = a->fov; t.gen.uv = uv; t.gen.rays_per_cam = a->rays_per_cam;
+        t.grid = a->grid; t.grad_grid = a->grad; t.rgba = a->rgba; t.loss = loss_now;
         t.grad_scale = grad_scale; t.loss_scale = loss_scale; t.beta_over_m = a->beta_over_m;
         if (allow_fused && a->img_h == a->img_w && plx::render_train_supported(t)) {
             if ((rc = plx_render_train(&t, stream)) != PLX_OK) return rc;
-            goto optim;
+        } else {
+            if ((rc = plx_generate_rays(a->imgs, a->n_cams, a->img_h, a->img_w, a->poses, a->fov, uv, a->rays_per_cam, 0,
+                                        a->dirs, a->targets, stream)) != PLX_OK) return rc;
+            PlxRenderFwd f;
+            std::memset(&f, 0, sizeof(f));
+            f.march = a->march;
+            // camera positions = poses[:, :3, 3] (src/ray_sampling.py:159), read in place through the strided view
+            f.rays.origins = a->poses + 3;
+            f.rays.origin_stride = 16;
+            f.rays.origin_comp_stride = 4;
+            f.rays.dirs = a->dirs;
+            f.rays.n_rays = n_rays;
+            f.rays.rays_per_origin = a->rays_per_cam;
+            f.grid = a->grid;
+            f.rgba = a->rgba; f.tcarry = a->tcarry;
+            f.targets = a->targets; f.grad_rgba = a->grad_rgba; f.loss = loss_now;
+            f.grad_scale = grad_scale;
+            f.loss_scale = loss_scale;
+            if ((rc = plx_render_fwd(&f, stream)) != PLX_OK) return rc;
+            PlxRenderBwd b;
+            std::memset(&b, 0, sizeof(b));
+            b.march = a->march; b.rays = f.rays; b.grid = a->grid; b.grad_rgba = a->grad_rgba; b.tcarry = a->tcarry;
+            b.grad_grid = a->grad; b.beta_over_m = a->beta_over_m;
+            if ((rc = plx_render_bwd(&b, stream)) != PLX_OK) return rc;
         }
-        if ((rc = plx_generate_rays(a->imgs, a->n_cams, a->img_h, a->img_w, a->poses, a->fov, a->uv, a->rays_per_cam, 0,
-                                    a->dirs, a->targets, stream)) != PLX_OK) return rc;
-        PlxRenderFwd f;
-        f.march = a->march;
-        // camera positions = poses[:, :3, 3] (src/ray_sampling.py:159), read in place through the strided view
-        f.rays.origins = a->poses + 3;
-        f.rays.origin_stride = 16;
-        f.rays.origin_comp_stride = 4;
-        f.rays.dirs = a->dirs;
-        f.rays.n_rays = n_rays;
-        f.rays.rays_per_origin = a->rays_per_cam;
-        f.grid = a->grid;
-        f.rgba = a->rgba; f.depth = nullptr; f.count = nullptr; f.sample_index = nullptr; f.tcarry = a->tcarry;
-        f.targets = a->targets; f.grad_rgba = a->grad_rgba; f.loss = a->loss;
-        f.grad_scale = grad_scale;
-        f.loss_scale = loss_scale;
-        if ((rc = plx_render_fwd(&f, stream)) != PLX_OK) return rc;
-        PlxRenderBwd b;
-        b.march = a->march; b.rays = f.rays; b.grid = a->grid; b.grad_rgba = a->grad_rgba; b.tcarry = a->tcarry;
-        b.grad_grid = a->grad; b.beta_over_m = a->beta_over_m;
-        if ((rc = plx_render_bwd(&b, stream)) != PLX_OK) return rc;
     }
-optim:
     if (phase & PLX_STEP_OPTIM) {
         const int64_t n = (int64_t)a->march.nx * a->march.ny * a->march.nz * 4;
-        if ((rc = plx_adam_step(a->grid, a->grad, a->exp_avg, a->exp_avg_sq, a->grad_abs_sum, n, a->lr, a->beta1, a->beta2,
-                                a->eps, a->step, 1, stream)) != PLX_OK) return rc;
+        if (n > 0 && (!a->grid || !a->grad || !a->exp_avg || !a->exp_avg_sq)) return fail(PLX_E_NULL, "train step: optimiser state is NULL");
+        if (a->step < 1) return fail(PLX_E_SHAPE, "step counts from 1");
+        const plx::StepTail tail{loss_now, loss_next, (float*)result_host, (int32_t)a->step};
+        return cuda_result(plx::launch_adam(a->grid, a->grad, a->exp_avg, a->exp_avg_sq, a->grad_abs_sum, n,
+                                            adam_scalars(a->lr, a->beta1, a->beta2, a->eps, a->step), true, tail,
+                                            (cudaStream_t)stream), "plx_train_step(optim)");
     }
     return PLX_OK;
 }
 
-int plx_train_step_host(const PlxTrainStep* a, const float* uv_host, float* loss_host, int32_t phase, void* stream) {
-    if (!a) return fail(PLX_E_NULL, "args is NULL");
-    cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-    if (phase & PLX_STEP_RENDER) {
-        if (!uv_host || !a->uv) return fail(PLX_E_NULL, "uv_host / uv is NULL");
-        const size_t bytes = (size_t)a->n_cams * a->rays_per_cam * 2 * sizeof(float);
-        if ((rc = cuda_result(cudaMemcpyAsync((void*)a->uv, uv_host, bytes, cudaMemcpyHostToDevice, st), "uv H2D")) != PLX_OK) return rc;
-    }
-    if ((rc = plx_train_step(a, phase, stream)) != PLX_OK) return rc;
-    if ((phase & PLX_STEP_RENDER) && loss_host) {
-        if ((rc = cuda_result(cudaMemcpyAsync(loss_host, a->loss, sizeof(float), cudaMemcpyDeviceToHost, st), "loss D2H")) != PLX_OK) return rc;
-    }
-    return PLX_OK;
+int plx_train_step(const PlxTrainStep* a, int32_t phase, void* stream) {
+    return train_step_impl(a, a ? a->uv : nullptr, nullptr, phase, stream);
+}
+
+int plx_train_step_host(const PlxTrainStep* a, const float* uv_host, void* result_host, int32_t phase, void* stream) {
+    if ((phase & PLX_STEP_RENDER) && !uv_host) return fail(PLX_E_NULL, "uv_host is NULL");
+    if ((uintptr_t)result_host % 8) return fail(PLX_E_ALIGN, "result_host must be 8-byte aligned");
+    return train_step_impl(a, (phase & PLX_STEP_RENDER) ? uv_host : (a ? a->uv : nullptr), result_host, phase, stream);
 }
 
 }  // extern "C"

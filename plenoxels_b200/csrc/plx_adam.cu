@@ -24,10 +24,22 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, con
     p = __fadd_rn(p, fdiv_var(__fmul_rn(s.neg_step_size, m), denom));
 }
 
+__device__ __forceinline__ void step_tail(const StepTail& t) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (t.src && t.dst_host) {
+            *reinterpret_cast<volatile float*>(t.dst_host) = *t.src;
+            __threadfence_system();                                  // the loss is visible to the host before the step number
+            *reinterpret_cast<volatile int32_t*>(t.dst_host + 1) = t.step;
+        }
+        if (t.clear) *t.clear = 0.f;
+    }
+}
+
 template <bool HAS_ABS, bool ZERO, int UNROLL>
 __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                               float4* __restrict__ v, float4* __restrict__ ga, int64_t n4,
-                                              const AdamScalars s) {
+                                              const AdamScalars s, const StepTail tail) {
+    step_tail(tail);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const FastDiv bc = make_fastdiv(s.bc2_sqrt);
     for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * UNROLL) {
@@ -78,7 +90,9 @@ struct PeerPtrs {
 
 template <int UNROLL>
 __global__ void __launch_bounds__(256) k_adam_peer(PeerPtrs pp, int world, int world_st, float4* __restrict__ m, float4* __restrict__ v,
-                                                   float4* __restrict__ ga, int64_t begin4, int64_t end4, const AdamScalars s) {
+                                                   float4* __restrict__ ga, int64_t begin4, int64_t end4, const AdamScalars s,
+                                                   const StepTail tail) {
+    step_tail(tail);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const FastDiv bc = make_fastdiv(s.bc2_sqrt);
     for (int64_t i0 = begin4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end4; i0 += stride * UNROLL) {
@@ -139,7 +153,8 @@ __device__ __forceinline__ void multimem_st(float4* mc, float4 v) {
 template <int UNROLL>
 __global__ void __launch_bounds__(256) k_adam_mc(const float4* __restrict__ p_local, float4* p_mc, const float4* g_mc,
                                                  float4* __restrict__ m, float4* __restrict__ v, float4* __restrict__ ga,
-                                                 int64_t begin4, int64_t end4, const AdamScalars s) {
+                                                 int64_t begin4, int64_t end4, const AdamScalars s, const StepTail tail) {
+    step_tail(tail);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const FastDiv bc = make_fastdiv(s.bc2_sqrt);
     for (int64_t i0 = begin4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end4; i0 += stride * UNROLL) {
@@ -175,7 +190,7 @@ __global__ void __launch_bounds__(256) k_adam_mc(const float4* __restrict__ p_lo
     }
 }
 
-cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, cudaStream_t st) {
+cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, const StepTail& tail, cudaStream_t st) {
     const int64_t begin4 = a.begin / 4, end4 = a.end / 4;
     if (end4 <= begin4) return cudaSuccess;
     // in-switch reduction pays off once several peers would otherwise be read one by one; with 2 ranks it only adds a
@@ -200,7 +215,7 @@ cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, cudaStr
             const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);                                         \
             const unsigned blocks = (unsigned)(want < resident ? want : resident);                                     \
             k_adam_mc<U><<<blocks, 256, 0, st>>>((const float4*)a.grids[a.rank], (float4*)a.grid_mc, (const float4*)a.grad_mc,   \
-                                                 (float4*)a.exp_avg, (float4*)a.exp_avg_sq, (float4*)a.grad_abs_sum, begin4, end4, s); \
+                                                 (float4*)a.exp_avg, (float4*)a.exp_avg_sq, (float4*)a.grad_abs_sum, begin4, end4, s, tail); \
         } while (0)
         if (unroll >= 4) PLX_MC(4); else if (unroll >= 2) PLX_MC(2); else PLX_MC(1);
 #undef PLX_MC
@@ -231,7 +246,7 @@ cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, cudaStr
         const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);                                           \
         const unsigned blocks = (unsigned)(want < resident ? want : resident);                                       \
         k_adam_peer<U><<<blocks, 256, 0, st>>>(pp, dbg_ld ? dbg_ld : a.world, dbg_st ? dbg_st : a.world, (float4*)a.exp_avg, (float4*)a.exp_avg_sq,               \
-                                               (float4*)a.grad_abs_sum, begin4, end4, s);                            \
+                                               (float4*)a.grad_abs_sum, begin4, end4, s, tail);                      \
     } while (0)
     if (unroll >= 4) PLX_PEER(4); else if (unroll >= 2) PLX_PEER(2); else PLX_PEER(1);
 #undef PLX_PEER
@@ -256,7 +271,7 @@ __global__ void k_adam_scalar(float* p, float* g, float* m, float* v, float* ga,
 
 template <bool HAS_ABS, bool ZERO, int UNROLL>
 static cudaError_t launch_adam_vec(float4* p, float4* g, float4* m, float4* v, float4* ga, int64_t n4, const AdamScalars& s,
-                                   int blocks_per_sm_cap, cudaStream_t st) {
+                                   int blocks_per_sm_cap, const StepTail& tail, cudaStream_t st) {
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adam<HAS_ABS, ZERO, UNROLL>, 256, 0);
     if (e != cudaSuccess) return e;
@@ -268,12 +283,14 @@ static cudaError_t launch_adam_vec(float4* p, float4* g, float4* m, float4* v, f
     int64_t want = (n4 + 256 * UNROLL - 1) / (256 * UNROLL);
     const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
     const unsigned blocks = (unsigned)(want < resident ? want : resident);
-    k_adam<HAS_ABS, ZERO, UNROLL><<<blocks, 256, 0, st>>>(p, g, m, v, ga, n4, s);
+    k_adam<HAS_ABS, ZERO, UNROLL><<<blocks, 256, 0, st>>>(p, g, m, v, ga, n4, s, tail);
     return cudaGetLastError();
 }
 
+__global__ void k_step_tail_only(const StepTail tail) { step_tail(tail); }
+
 cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int64_t n, const AdamScalars& s,
-                        bool zero_grad, cudaStream_t st) {
+                        bool zero_grad, const StepTail& tail, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const bool aligned = ((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                          ((uintptr_t)v % 16 == 0) && (!gabs || (uintptr_t)gabs % 16 == 0);
@@ -285,15 +302,16 @@ cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int
         cudaError_t e;
 #define PLX_ADAM_V(U)                                                                                                         \
         do {                                                                                                                  \
-            if (gabs) { e = zero_grad ? launch_adam_vec<true, true, U>((float4*)p, (float4*)g, (float4*)m, (float4*)v, (float4*)gabs, n4, s, cap, st)   \
-                                      : launch_adam_vec<true, false, U>((float4*)p, (float4*)g, (float4*)m, (float4*)v, (float4*)gabs, n4, s, cap, st); } \
-            else      { e = zero_grad ? launch_adam_vec<false, true, U>((float4*)p, (float4*)g, (float4*)m, (float4*)v, nullptr, n4, s, cap, st)        \
-                                      : launch_adam_vec<false, false, U>((float4*)p, (float4*)g, (float4*)m, (float4*)v, nullptr, n4, s, cap, st); }    \
+            if (gabs) { e = zero_grad ? launch_adam_vec<true, true, U>((float4*)p, (float4*)g, (float4*)m, (float4*)v, (float4*)gabs, n4, s, cap, tail, st)   \
+                                      : launch_adam_vec<true, false, U>((float4*)p, (float4*)g, (float4*)m, (float4*)v, (float4*)gabs, n4, s, cap, tail, st); } \
+            else      { e = zero_grad ? launch_adam_vec<false, true, U>((float4*)p, (float4*)g, (float4*)m, (float4*)v, nullptr, n4, s, cap, tail, st)        \
+                                      : launch_adam_vec<false, false, U>((float4*)p, (float4*)g, (float4*)m, (float4*)v, nullptr, n4, s, cap, tail, st); }    \
         } while (0)
         if (unroll == 1) PLX_ADAM_V(1); else if (unroll == 4) PLX_ADAM_V(4); else PLX_ADAM_V(2);
 #undef PLX_ADAM_V
         if (e != cudaSuccess) return e;
     }
+    if (n4 == 0 && (tail.src || tail.clear)) k_step_tail_only<<<1, 32, 0, st>>>(tail);
     if (n4 * 4 < n) {
         const int64_t rem = n - n4 * 4;
         int64_t want = (rem + threads - 1) / threads;

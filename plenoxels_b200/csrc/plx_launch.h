@@ -23,10 +23,18 @@ struct AdamScalars {
     float eps;
     float neg_step_size;     // -lr / (1 - beta1^step)
 };
+// what one thread of the optimiser kernel does besides Adam: publish this step's loss to pinned host memory
+// { float loss; int32 step } and clear the other loss slot for the next step
+struct StepTail {
+    const float* src;
+    float* clear;
+    float* dst_host;
+    int32_t step;
+};
 cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int64_t n, const AdamScalars& s,
-                        bool zero_grad, cudaStream_t st);
+                        bool zero_grad, const StepTail& tail, cudaStream_t st);
 
-cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, cudaStream_t st);
+cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, const StepTail& tail, cudaStream_t st);
 
 cudaError_t launch_generate_rays(const float* imgs, int n_cams, int img_h, int img_w, const float* poses, float fov,
                                  const float* uv, int rays_per_cam, int n_side, float* dirs, float* targets,

@@ -69,8 +69,14 @@ class VoxelTrainer:
         self.rgba = torch.empty((n, 4), dtype=torch.float32, device=dev)
         self.grad_rgba = torch.empty((n, 4), dtype=torch.float32, device=dev)
         self.tcarry = torch.empty((n, self.lib.plx_num_chunks(self.num_samples)), dtype=torch.float32, device=dev)
-        self.loss = torch.zeros((1,), dtype=torch.float32, device=dev)
-        self.loss_host = torch.zeros((1,), dtype=torch.float32).pin_memory()
+        # two loss slots: step s accumulates into slot s & 1, the optimiser kernel clears the other one (plenoxel_abi.h)
+        self._loss2 = torch.zeros((2,), dtype=torch.float32, device=dev)
+        self.loss = self._loss2[1:2]                                   # view of the slot of the latest step
+        # pinned { float loss; int32 step } the optimiser kernel publishes to on the host path
+        self.result_host = torch.zeros((2,), dtype=torch.float32).pin_memory()
+        self.loss_host = self.result_host[:1]
+        self._result_f32 = self.result_host.numpy()
+        self._result_i32 = self._result_f32.view("int32")
         self._args = self._make_args()
         self.launches_per_step = 4        # generate_rays, render_fwd, render_bwd, adam (memset/memcpy are not kernels)
 
@@ -88,7 +94,7 @@ class VoxelTrainer:
         m_global = self.n_rays_global * self.num_samples
         a.beta_over_m = self.beta / m_global if (self.beta and m_global) else 0.0
         a.dirs, a.targets, a.rgba = self.dirs.data_ptr(), self.targets.data_ptr(), self.rgba.data_ptr()
-        a.grad_rgba, a.tcarry, a.loss = self.grad_rgba.data_ptr(), self.tcarry.data_ptr(), self.loss.data_ptr()
+        a.grad_rgba, a.tcarry, a.loss = self.grad_rgba.data_ptr(), self.tcarry.data_ptr(), self._loss2.data_ptr()
         return a
 
     # ---------------------------------------------------------------------------------------------------------
@@ -98,8 +104,7 @@ class VoxelTrainer:
     def render_phase(self, uv: torch.Tensor | None = None) -> None:
         """Ray generation + forward + loss + backward of this rank's batch into the local gradient buffer."""
         self._args.uv = uv.data_ptr() if uv is not None else self.uv.data_ptr()
-        self.step_count += 1
-        self._args.step = self.step_count
+        self._begin_step()
         with torch.cuda.device(self.device):
             L.check(self.lib.plx_train_step(C.byref(self._args), L.PLX_STEP_RENDER, L.stream_ptr(self.device)),
                     "plx_train_step(render)")
@@ -121,32 +126,47 @@ class VoxelTrainer:
             self.update_phase()
             return self.loss
         self._args.uv = uv.data_ptr() if uv is not None else self.uv.data_ptr()
-        self.step_count += 1
-        self._args.step = self.step_count
+        self._begin_step()
         with torch.cuda.device(self.device):
             L.check(self.lib.plx_train_step(C.byref(self._args), L.PLX_STEP_ALL, L.stream_ptr(self.device)), "plx_train_step")
         self._args.uv = self.uv.data_ptr()
         return self.loss
 
-    def step_host(self, uv_host: torch.Tensor) -> torch.Tensor:
-        """End-to-end step from HOST memory: `uv_host` (C,R,2) pinned fp32 is copied to the device, the step runs, and
-        the loss scalar is copied back into pinned `self.loss_host` — all asynchronous on the current stream."""
-        if uv_host.is_cuda or uv_host.dtype != torch.float32 or not uv_host.is_contiguous() or \
-                uv_host.numel() != self.uv.numel():
-            raise L.PlxError("uv_host must be a contiguous float32 host tensor of shape (C,R,2)")
+    def _begin_step(self) -> None:
         self.step_count += 1
         self._args.step = self.step_count
+        s = self.step_count & 1
+        self.loss = self._loss2[s:s + 1]
+
+    def wait_result(self, step: int | None = None) -> float:
+        """Host path: spin on the pinned {loss, step} record until the optimiser kernel of `step` (default: the latest
+        step) has published it, then return the loss.  No driver synchronisation call is involved."""
+        step = self.step_count if step is None else step
+        seq = self._result_i32
+        while seq[1] != step:
+            pass
+        return float(self._result_f32[0])
+
+    def step_host(self, uv_host: torch.Tensor) -> torch.Tensor:
+        """End-to-end step from HOST memory: the march reads this step's uv straight out of pinned `uv_host` (C,R,2)
+        (zero-copy) and the optimiser kernel publishes {loss, step} into pinned `self.result_host`; two kernel launches,
+        asynchronous.  Read the loss with `wait_result()` (or synchronise the stream and read `self.loss_host`)."""
+        if uv_host.is_cuda or uv_host.dtype != torch.float32 or not uv_host.is_contiguous() or \
+                uv_host.numel() != self.uv.numel() or not uv_host.is_pinned():
+            raise L.PlxError("uv_host must be a pinned, contiguous float32 host tensor of shape (C,R,2)")
+        self._begin_step()
         st = L.stream_ptr(self.device)
+        res = self.result_host.data_ptr()
         with torch.cuda.device(self.device):
             if self._distributed():
-                L.check(self.lib.plx_train_step_host(C.byref(self._args), uv_host.data_ptr(), self.loss_host.data_ptr(),
-                                                     L.PLX_STEP_RENDER, st), "plx_train_step_host(render)")
+                L.check(self.lib.plx_train_step_host(C.byref(self._args), uv_host.data_ptr(), res, L.PLX_STEP_RENDER, st),
+                        "plx_train_step_host(render)")
                 all_reduce_sum_(self.grad, self.group)
-                L.check(self.lib.plx_train_step_host(C.byref(self._args), None, None, L.PLX_STEP_OPTIM, st),
+                L.check(self.lib.plx_train_step_host(C.byref(self._args), None, res, L.PLX_STEP_OPTIM, st),
                         "plx_train_step_host(optim)")
             else:
-                L.check(self.lib.plx_train_step_host(C.byref(self._args), uv_host.data_ptr(), self.loss_host.data_ptr(),
-                                                     L.PLX_STEP_ALL, st), "plx_train_step_host")
+                L.check(self.lib.plx_train_step_host(C.byref(self._args), uv_host.data_ptr(), res, L.PLX_STEP_ALL, st),
+                        "plx_train_step_host")
         return self.loss_host
 
     def checkpoint(self, extra_param: dict | None = None) -> dict:
@@ -243,10 +263,14 @@ class PeerVoxelTrainer(VoxelTrainer):
             torch.cuda.current_stream(self.device).wait_event(self._cleared[b])
         super().render_phase(uv)
 
-    def _exchange_and_update(self, st):
+    def _exchange_and_update(self, st, result_host=None):
         b = self._cur
         peer = self._peers[b]
         peer.step = self.step_count
+        s = self.step_count & 1
+        peer.loss_src = self._loss2.data_ptr() + 4 * s
+        peer.loss_clear = self._loss2.data_ptr() + 4 * (1 - s)
+        peer.result_host = result_host
         h = self._h_grads[b]
         h.barrier(channel=0)                                  # every rank's partial gradient is complete
         L.check(self.lib.plx_adam_step_peer(C.byref(peer), st), "plx_adam_step_peer")
@@ -270,19 +294,20 @@ class PeerVoxelTrainer(VoxelTrainer):
         return self.loss
 
     def step_host(self, uv_host):
+        if uv_host.is_cuda or not uv_host.is_pinned() or uv_host.numel() != self.uv.numel():
+            raise L.PlxError("uv_host must be a pinned float32 host tensor of shape (C,R,2)")
         b = self.step_count % 2
         self._cur = b
         self.grad = self._grads[b]
         self._args.grad = self.grad.data_ptr()
         if self._cleared[b] is not None:
             torch.cuda.current_stream(self.device).wait_event(self._cleared[b])
-        self.step_count += 1
-        self._args.step = self.step_count
+        self._begin_step()
         st = L.stream_ptr(self.device)
         with torch.cuda.device(self.device):
-            L.check(self.lib.plx_train_step_host(C.byref(self._args), uv_host.data_ptr(), self.loss_host.data_ptr(),
-                                                 L.PLX_STEP_RENDER, st), "plx_train_step_host(render)")
-            self._exchange_and_update(st)
+            L.check(self.lib.plx_train_step_host(C.byref(self._args), uv_host.data_ptr(), None, L.PLX_STEP_RENDER, st),
+                    "plx_train_step_host(render)")
+            self._exchange_and_update(st, self.result_host.data_ptr())
         return self.loss_host
 
     def gathered_grad_abs_sum(self):

@@ -279,8 +279,9 @@ def test_train_steps_match_oracle(mode):
             loss = float(tr.step(uv.cuda()))
         else:
             loss_host = tr.step_host(uv.pin_memory())
+            loss = tr.wait_result()                       # spins on the pinned {loss, step} record, no driver sync
             torch.cuda.synchronize()
-            loss = float(loss_host)
+            assert loss == float(loss_host) and int(tr._result_i32[1]) == step
         assert abs(loss - loss_o) <= TOL * abs(loss_o)
         assert rel_err(tr.grad_abs_sum.cpu().numpy(), ga) <= TOL
         # Adam's first steps are +-lr*sign(g): cells whose gradient is O(rounding noise) may flip; compare the bulk

@@ -116,6 +116,7 @@ static plx::AdamScalars adam_scalars(double lr, double beta1, double beta2, doub
     s.bc2_sqrt = (float)std::sqrt(bc2);
     s.eps = (float)eps;
     s.neg_step_size = (float)(-(lr / bc1));
+    s.keep_p = s.keep_g = false;
     return s;
 }
 

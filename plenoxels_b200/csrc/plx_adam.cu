@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
     step_tail(tail);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const FastDiv bc = make_fastdiv(s.bc2_sqrt);
+    // parameters and gradient are re-used by the march of the next step: keep them in L2 when they fit (plx_device.cuh)
+    const uint64_t pol = l2_policy(s.keep_p), pol_g = l2_policy(s.keep_g);
     for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * UNROLL) {
         float4 P[UNROLL], G[UNROLL], M[UNROLL], V[UNROLL], A[UNROLL];
         // all loads of the iteration are issued before the first use: 5 * UNROLL independent 16-byte requests per thread
@@ -49,8 +51,8 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
         for (int u = 0; u < UNROLL; ++u) {
             const int64_t i = i0 + u * stride;
             if (i < n4) {
-                P[u] = p[i];
-                G[u] = __ldcs(g + i);
+                P[u] = ld_hint(p + i, pol);
+                G[u] = ld_hint(g + i, pol_g);
                 M[u] = __ldcs(m + i);
                 V[u] = __ldcs(v + i);
                 if (HAS_ABS) A[u] = __ldcs(ga + i);
@@ -64,14 +66,14 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
                 adam1(P[u].y, G[u].y, M[u].y, V[u].y, s, bc);
                 adam1(P[u].z, G[u].z, M[u].z, V[u].z, s, bc);
                 adam1(P[u].w, G[u].w, M[u].w, V[u].w, s, bc);
-                p[i] = P[u];                // the grid is re-read by the next step's march: default (L2-resident) policy
+                st_hint(p + i, P[u], pol);
                 __stcs(m + i, M[u]);
                 __stcs(v + i, V[u]);
                 if (HAS_ABS) {
                     A[u].x += fabsf(G[u].x); A[u].y += fabsf(G[u].y); A[u].z += fabsf(G[u].z); A[u].w += fabsf(G[u].w);
                     __stcs(ga + i, A[u]);
                 }
-                if (ZERO) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ZERO) st_hint(g + i, make_float4(0.f, 0.f, 0.f, 0.f), pol_g);
             }
         }
     }
@@ -289,9 +291,16 @@ static cudaError_t launch_adam_vec(float4* p, float4* g, float4* m, float4* v, f
 
 __global__ void k_step_tail_only(const StepTail tail) { step_tail(tail); }
 
-cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int64_t n, const AdamScalars& s,
+cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int64_t n, const AdamScalars& s_in,
                         bool zero_grad, const StepTail& tail, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
+    AdamScalars s = s_in;
+    {
+        static const int mode = adam_env("PLX_L2_KEEP", 0);
+        const bool fits = l2_keep_ok(n / 4);
+        s.keep_p = fits && mode != 0;
+        s.keep_g = fits && mode == 1;
+    }
     const bool aligned = ((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                          ((uintptr_t)v % 16 == 0) && (!gabs || (uintptr_t)gabs % 16 == 0);
     const int64_t n4 = aligned ? n / 4 : 0;

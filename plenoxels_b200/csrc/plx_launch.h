@@ -22,6 +22,7 @@ struct AdamScalars {
     float bc2_sqrt;          // sqrt(1 - beta2^step)
     float eps;
     float neg_step_size;     // -lr / (1 - beta1^step)
+    bool keep_p, keep_g;     // L2 evict_last tags for parameters / gradient (set by launch_adam)
 };
 // what one thread of the optimiser kernel does besides Adam: publish this step's loss to pinned host memory
 // { float loss; int32 step } and clear the other loss slot for the next step

@@ -5,6 +5,8 @@
 // by their linear index with one 128-bit load and the quotient costs 3 FMAs (plx_device.cuh);
 // !FAST = arbitrary strides (channel-planar pooled grids), scalar loads, __fdiv_rn.
 #pragma once
+#include <cstdlib>
+
 #include "plx_device.cuh"
 #include "plx_launch.h"
 
@@ -18,6 +20,7 @@ struct Geo {
     float gx, gy, gz, delta;
     FastDiv div;
     bool clamp;
+    uint64_t pol, pol_grad;  // L2 cache policies for grid reads / gradient reductions
 };
 
 __device__ __forceinline__ Geo make_geo(const PlxMarch& m) {
@@ -28,6 +31,8 @@ __device__ __forceinline__ Geo make_geo(const PlxMarch& m) {
     g.delta = m.delta_step;
     g.div = make_fastdiv(m.points_distance);
     g.clamp = (m.flags & PLX_CLAMP01) != 0;
+    g.pol = l2_policy((m.flags & PLX_FLAG_KEEP_GRID) != 0);
+    g.pol_grad = l2_policy((m.flags & PLX_FLAG_KEEP_GRAD) != 0);
     return g;
 }
 
@@ -54,8 +59,8 @@ __device__ __forceinline__ void norm3(const PlxMarch& m, const Geo& g, const Ray
 }
 
 template <bool FAST>
-__device__ __forceinline__ float4 cell_at(const PlxMarch& m, const float* __restrict__ grid, int ix, int iy, int iz, int lin) {
-    if (FAST) return __ldg(reinterpret_cast<const float4*>(grid) + lin);
+__device__ __forceinline__ float4 cell_at(const PlxMarch& m, const Geo& g, const float* __restrict__ grid, int ix, int iy, int iz, int lin) {
+    if (FAST) return ldg_hint(reinterpret_cast<const float4*>(grid) + lin, g.pol);
     const int64_t off = ix * m.sx + iy * m.sy + iz * m.sz;
     return make_float4(__ldg(grid + off), __ldg(grid + off + m.sc), __ldg(grid + off + 2 * m.sc), __ldg(grid + off + 3 * m.sc));
 }
@@ -86,7 +91,7 @@ __device__ __forceinline__ Sample lookup_nearest(const PlxMarch& m, const Geo& g
         const int ix = (int)rx, iy = (int)ry, iz = (int)rz;
         s.lin = (ix * g.ny + iy) * g.nz + iz;
         if (need_value) {
-            s.raw = cell_at<FAST>(m, grid, ix, iy, iz, s.lin);
+            s.raw = cell_at<FAST>(m, g, grid, ix, iy, iz, s.lin);
             s.c = g.clamp ? clamp4(s.raw) : s.raw;
         }
     }
@@ -127,7 +132,7 @@ __device__ __forceinline__ float4 lerp4(float4 hi, float4 lo, float f) {
 
 template <bool FAST>
 __device__ __forceinline__ float4 tri_cell(const PlxMarch& m, const Geo& g, const float* __restrict__ grid, int ix, int iy, int iz) {
-    const float4 c = cell_at<FAST>(m, grid, ix, iy, iz, (ix * g.ny + iy) * g.nz + iz);
+    const float4 c = cell_at<FAST>(m, g, grid, ix, iy, iz, (ix * g.ny + iy) * g.nz + iz);
     return g.clamp ? clamp4(c) : c;
 }
 
@@ -162,6 +167,13 @@ __device__ __forceinline__ Sample lookup(const PlxMarch& m, const Geo& g, const 
     return s;
 }
 
+
+// host side: which of grid / gradient get the evict_last tag for this launch (PLX_L2_KEEP: 0 none, 1 both, 2 grid only)
+static inline uint32_t l2_keep_flags(const PlxMarch& m) {
+    static const int mode = [] { const char* e = std::getenv("PLX_L2_KEEP"); return e ? std::atoi(e) : 0; }();
+    if (mode == 0 || !l2_keep_ok((int64_t)m.nx * m.ny * m.nz)) return 0;
+    return mode == 2 ? PLX_FLAG_KEEP_GRID : (PLX_FLAG_KEEP_GRID | PLX_FLAG_KEEP_GRAD);
+}
 
 // host-side predicate for the FAST instantiations
 static inline bool fast_ok(const PlxMarch& m, const float* grid) {

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) k_render_bwd(const P
         if (bom != 0.f) da += bom * (1.f / (alpha + 1e-4f) + 1.f / (1.f - alpha + 1e-4f));   // scripts/train.py:170-177
         if (MODE == PLX_NEAREST) {
             if (g.clamp) { dr *= pass01(s.raw.x); dg *= pass01(s.raw.y); db *= pass01(s.raw.z); da *= pass01(s.raw.w); }
-            warp_scatter_add(a.grad_grid, s.inb, (int64_t)s.lin * 4, dr, dg, db, da, lane);
+            warp_scatter_add(a.grad_grid, s.inb, (int64_t)s.lin * 4, dr, dg, db, da, lane, g.pol_grad);
         } else {
             if (s.inb && (dr != 0.f || dg != 0.f || db != 0.f || da != 0.f)) {
 #pragma unroll
@@ -217,10 +217,10 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) k_render_bwd(const P
                     const int lin = (ix * g.ny + iy) * g.nz + iz;
                     float px = 1.f, py = 1.f, pz = 1.f, pw = 1.f;
                     if (g.clamp) {
-                        const float4 raw = cell_at<FAST>(m, a.grid, ix, iy, iz, lin);
+                        const float4 raw = cell_at<FAST>(m, g, a.grid, ix, iy, iz, lin);
                         px = pass01(raw.x); py = pass01(raw.y); pz = pass01(raw.z); pw = pass01(raw.w);
                     }
-                    red_add_v4(a.grad_grid + (int64_t)lin * 4, dr * w * px, dg * w * py, db * w * pz, da * w * pw);
+                    red_add_v4_hint(a.grad_grid + (int64_t)lin * 4, dr * w * px, dg * w * py, db * w * pz, da * w * pw, g.pol_grad);
                 }
             }
         }
@@ -239,8 +239,10 @@ static int warps_per_block(const char* env, int dflt) {
     return dflt;
 }
 
-cudaError_t launch_render_fwd(const PlxRenderFwd& a, cudaStream_t st) {
-    if (a.rays.n_rays == 0) return cudaSuccess;
+cudaError_t launch_render_fwd(const PlxRenderFwd& a_in, cudaStream_t st) {
+    if (a_in.rays.n_rays == 0) return cudaSuccess;
+    PlxRenderFwd a = a_in;
+    a.march.flags = (a.march.flags & 0xffffu) | l2_keep_flags(a.march);
     static const int wpb = warps_per_block("PLX_FWD_WPB", 4);
     const unsigned blocks = (unsigned)((a.rays.n_rays + wpb - 1) / wpb);
     const bool fast = fast_ok(a.march, a.grid);
@@ -268,8 +270,10 @@ cudaError_t launch_render_fwd(const PlxRenderFwd& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_render_bwd(const PlxRenderBwd& a, cudaStream_t st) {
-    if (a.rays.n_rays == 0) return cudaSuccess;
+cudaError_t launch_render_bwd(const PlxRenderBwd& a_in, cudaStream_t st) {
+    if (a_in.rays.n_rays == 0) return cudaSuccess;
+    PlxRenderBwd a = a_in;
+    a.march.flags = (a.march.flags & 0xffffu) | l2_keep_flags(a.march);
     static const int wpb = warps_per_block("PLX_BWD_WPB", 4);
     const unsigned blocks = (unsigned)((a.rays.n_rays + wpb - 1) / wpb);
     const size_t smem = a.tcarry ? 0 : (size_t)wpb * num_chunks(a.march.num_samples) * sizeof(float);

@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
 #pragma unroll
             for (int j = 0; j < SPL; ++j) {
                 raw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lin[j] >= 0) raw[j] = FAST ? __ldg(reinterpret_cast<const float4*>(a.grid) + lin[j])
-                                               : cell_at<false>(m, a.grid, lin[j] / (g.ny * g.nz), (lin[j] / g.nz) % g.ny, lin[j] % g.nz, lin[j]);
+                if (lin[j] >= 0) raw[j] = FAST ? ldg_hint(reinterpret_cast<const float4*>(a.grid) + lin[j], g.pol)
+                                               : cell_at<false>(m, g, a.grid, lin[j] / (g.ny * g.nz), (lin[j] / g.nz) % g.ny, lin[j] % g.nz, lin[j]);
                 c[j] = g.clamp ? clamp4(raw[j]) : raw[j];
                 v[j] = fmaf(c[j].x, gr.x, fmaf(c[j].y, gr.y, fmaf(c[j].z, gr.z, gr.w)));      // c_k . g_rgb + g_A
             }
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
                 if (g.clamp) { d[j].x *= pass01(raw[j].x); d[j].y *= pass01(raw[j].y); d[j].z *= pass01(raw[j].z); d[j].w *= pass01(raw[j].w); }
             }
             if (SPL == 1) {
-                warp_scatter_add(a.grad_grid, lin[0] >= 0, (int64_t)lin[0] * 4, d[0].x, d[0].y, d[0].z, d[0].w, lane);
+                warp_scatter_add(a.grad_grid, lin[0] >= 0, (int64_t)lin[0] * 4, d[0].x, d[0].y, d[0].z, d[0].w, lane, g.pol_grad);
             } else {
                 // merge runs inside the lane, then one 16-byte reduction per surviving entry
 #pragma unroll
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
 #pragma unroll
                 for (int j = 0; j < SPL; ++j)
                     if (lin[j] >= 0 && (d[j].x != 0.f || d[j].y != 0.f || d[j].z != 0.f || d[j].w != 0.f))
-                        red_add_v4(a.grad_grid + (int64_t)lin[j] * 4, d[j].x, d[j].y, d[j].z, d[j].w);
+                        red_add_v4_hint(a.grad_grid + (int64_t)lin[j] * 4, d[j].x, d[j].y, d[j].z, d[j].w, g.pol_grad);
             }
         }
     }
@@ -248,8 +248,10 @@ bool render_train_supported(const PlxRenderTrain& a) {
     return render_train_smem(a.march.num_samples, 2, 1) <= 200 * 1024;
 }
 
-cudaError_t launch_render_train(const PlxRenderTrain& a, cudaStream_t st) {
-    if (a.rays.n_rays == 0) return cudaSuccess;
+cudaError_t launch_render_train(const PlxRenderTrain& a_in, cudaStream_t st) {
+    if (a_in.rays.n_rays == 0) return cudaSuccess;
+    PlxRenderTrain a = a_in;
+    a.march.flags = (a.march.flags & 0xffffu) | l2_keep_flags(a.march);
     static const int spl_env = env_int("PLX_TRAIN_SPL", 0, 1, 2);
     static const int wpb_env = env_int("PLX_TRAIN_WPB", 4, 1, 4);
     static const int minb = env_int("PLX_TRAIN_MINB", 8, 8, 12);

@@ -199,6 +199,16 @@ typedef struct PlxAdamPeer {
 int plx_adam_step_peer(const PlxAdamPeer* args, void* stream);
 
 /*
+ * Cross-GPU barrier on the launching stream (one tiny kernel): rank `rank` stores `epoch` into slot [channel][rank] of
+ * every peer's flag array (release, system scope) and then waits until all `world` slots of its OWN array hold a value
+ * >= epoch (acquire).  flags[r] = peer-mapped pointer to rank r's int32[PLX_BARRIER_CHANNELS * PLX_MAX_PEERS] array in
+ * symmetric memory, zero-initialised; `epoch` must increase by one per call and channel.  Orders everything enqueued
+ * before it on every rank's stream before everything enqueued after it on this rank's stream.
+ */
+#define PLX_BARRIER_CHANNELS 4
+int plx_peer_barrier(int32_t* const* flags, int32_t rank, int32_t world, int32_t channel, int32_t epoch, void* stream);
+
+/*
  * Ray generation — generate_rays_batched, src/ray_sampling.py:195-264.
  * imgs (C,H,W,4); poses (C,4,4) row-major camera-to-world; uv (C,R,2) in [0,1] (the `torch.rand` draw of :227) or NULL
  * for the even-spread lattice of :220-223 with R = n_side^2 rays (u-major, linspace(0,1,n_side)).

@@ -96,6 +96,7 @@ PROTOTYPES = {
     "plx_adam_step": (C.c_int, [c_void, c_void, c_void, c_void, c_void, C.c_int64, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_int64, C.c_int32, c_void]),
     "plx_adam_step_peer": (C.c_int, [C.POINTER(PlxAdamPeer), c_void]),
+    "plx_peer_barrier": (C.c_int, [C.POINTER(c_void), C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_void]),
     "plx_generate_rays": (C.c_int, [c_void, C.c_int32, C.c_int32, C.c_int32, c_void, C.c_float, c_void, C.c_int32,
                                     C.c_int32, c_void, c_void, c_void]),
     "plx_sample_points": (C.c_int, [C.POINTER(PlxRays), C.c_int32, C.c_float, c_void, c_void]),

@@ -147,6 +147,14 @@ int plx_adam_step_peer(const PlxAdamPeer* a, void* stream) {
                        "plx_adam_step_peer");
 }
 
+int plx_peer_barrier(int32_t* const* flags, int32_t rank, int32_t world, int32_t channel, int32_t epoch, void* stream) {
+    if (!flags) return fail(PLX_E_NULL, "flags is NULL");
+    if (world < 1 || world > PLX_MAX_PEERS || rank < 0 || rank >= world) return fail(PLX_E_SHAPE, "bad world / rank");
+    if (channel < 0 || channel >= PLX_BARRIER_CHANNELS) return fail(PLX_E_SHAPE, "channel out of range");
+    for (int r = 0; r < world; ++r) if (!flags[r]) return fail(PLX_E_NULL, "flag array of rank %d is NULL", r);
+    return cuda_result(plx::launch_peer_barrier(flags, rank, world, channel, epoch, (cudaStream_t)stream), "plx_peer_barrier");
+}
+
 int plx_generate_rays(const float* imgs, int32_t n_cams, int32_t img_h, int32_t img_w, const float* poses, float fov,
                       const float* uv, int32_t rays_per_cam, int32_t n_side, float* dirs, float* targets, void* stream) {
     if (n_cams < 0 || rays_per_cam < 0) return fail(PLX_E_SHAPE, "negative camera / ray count");

@@ -207,6 +207,7 @@ cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, const S
         // few resident blocks on purpose: with the whole slab in flight at once the switch-reduced loads and the replicated
         // stores would run as two serial phases; a deeper grid-stride loop keeps both NVLink directions busy together
         static const int mc_cap = adam_env("PLX_MC_BLOCKS_PER_SM", 1);
+        static const int mc_blocks = adam_env("PLX_MC_BLOCKS", 0);          // total CTA count override (tuning)
         const int64_t n4 = end4 - begin4;
 #define PLX_MC(U)                                                                                                      \
         do {                                                                                                           \
@@ -215,7 +216,8 @@ cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, const S
             if (mc_cap > 0 && per_sm > mc_cap) per_sm = mc_cap;                                                        \
             const int64_t want = (n4 + 256 * U - 1) / (256 * U);                                                       \
             const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);                                         \
-            const unsigned blocks = (unsigned)(want < resident ? want : resident);                                     \
+            unsigned blocks = (unsigned)(want < resident ? want : resident);                                           \
+            if (mc_blocks > 0 && (unsigned)mc_blocks < blocks) blocks = (unsigned)mc_blocks;                           \
             k_adam_mc<U><<<blocks, 256, 0, st>>>((const float4*)a.grids[a.rank], (float4*)a.grid_mc, (const float4*)a.grad_mc,   \
                                                  (float4*)a.exp_avg, (float4*)a.exp_avg_sq, (float4*)a.grad_abs_sum, begin4, end4, s, tail); \
         } while (0)
@@ -252,6 +254,29 @@ cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, const S
     } while (0)
     if (unroll >= 4) PLX_PEER(4); else if (unroll >= 2) PLX_PEER(2); else PLX_PEER(1);
 #undef PLX_PEER
+    return cudaGetLastError();
+}
+
+// cross-GPU barrier over peer-mapped flag arrays (see plenoxel_abi.h)
+struct FlagPtrs { int32_t* p[PLX_MAX_PEERS]; };
+
+__global__ void k_peer_barrier(FlagPtrs f, int rank, int world, int channel, int epoch) {
+    const int r = threadIdx.x;
+    if (r < world) {
+        int32_t* theirs = f.p[r] + channel * PLX_MAX_PEERS + rank;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+        const int32_t* mine = f.p[rank] + channel * PLX_MAX_PEERS + r;
+        int32_t seen;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+        } while (seen - epoch < 0);
+    }
+}
+
+cudaError_t launch_peer_barrier(int32_t* const* flags, int rank, int world, int channel, int epoch, cudaStream_t st) {
+    FlagPtrs f;
+    for (int r = 0; r < PLX_MAX_PEERS; ++r) f.p[r] = r < world ? flags[r] : nullptr;
+    k_peer_barrier<<<1, 32, 0, st>>>(f, rank, world, channel, epoch);
     return cudaGetLastError();
 }
 

@@ -8,6 +8,7 @@ GLOBAL ray count so a plain SUM reproduces the single-GPU mean-MSE gradient exac
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -226,6 +227,17 @@ class PeerVoxelTrainer(VoxelTrainer):
         self.grad = self._grads[0]
         self._clear_stream = torch.cuda.Stream(device=dev)
         self._cleared = [None, None]          # event: buffer b is zero again
+        self._done_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self._clear_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        # barrier flags: int32[channels * max_peers] per rank in symmetric memory, epochs only ever grow
+        flags = symm_mem.empty((4 * L.PLX_MAX_PEERS,), dtype=torch.int32, device=dev)
+        flags.zero_()
+        self._flags = flags
+        self._h_flags = symm_mem.rendezvous(flags, group)
+        self._flag_ptrs = (L.c_void * L.PLX_MAX_PEERS)(*[int(self._h_flags.buffer_ptrs[r]) if r < self.world else None
+                                                           for r in range(L.PLX_MAX_PEERS)])
+        self._epoch = 0
+        self._own_barrier = os.environ.get("PLX_PEER_BARRIER", "own") == "own"
         self._args = self._make_args()
         slab = slab_range(self.grid.numel() // 4, self.rank, self.world)
         self.multicast = False
@@ -272,17 +284,23 @@ class PeerVoxelTrainer(VoxelTrainer):
         peer.loss_clear = self._loss2.data_ptr() + 4 * (1 - s)
         peer.result_host = result_host
         h = self._h_grads[b]
-        h.barrier(channel=0)                                  # every rank's partial gradient is complete
+        self._epoch += 1
+        self._barrier(h, 0, st)                               # every rank's partial gradient is complete
         L.check(self.lib.plx_adam_step_peer(C.byref(peer), st), "plx_adam_step_peer")
-        h.barrier(channel=1)                                  # every replica holds the new parameters; peers done reading
-        done = torch.cuda.Event()
+        self._barrier(h, 1, st)                               # every replica holds the new parameters; peers done reading
+        done, ev = self._done_ev[b], self._clear_ev[b]
         done.record(torch.cuda.current_stream(self.device))
+        self._clear_stream.wait_event(done)
         with torch.cuda.stream(self._clear_stream):
-            self._clear_stream.wait_event(done)
             self._grads[b].zero_()
-            ev = torch.cuda.Event()
             ev.record(self._clear_stream)
         self._cleared[b] = ev
+
+    def _barrier(self, handle, channel, st):
+        if self._own_barrier:
+            L.check(self.lib.plx_peer_barrier(self._flag_ptrs, self.rank, self.world, channel, self._epoch, st), "plx_peer_barrier")
+        else:
+            handle.barrier(channel=channel)
 
     def update_phase(self) -> None:
         with torch.cuda.device(self.device):

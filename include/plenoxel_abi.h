@@ -248,6 +248,17 @@ int plx_composite_bwd(const float* samples, int64_t n_rays, int32_t num_samples,
                       float* grad_samples, void* stream);
 
 /*
+ * average_pool3d_grid — src/grid_functions.py:173-181 (F.avg_pool3d, cubic window `kernel`, stride `stride`, no padding)
+ * on a contiguous (X,Y,Z,4) grid, as three separable box passes; `out` is contiguous (Ox,Oy,Oz,4) with
+ * O = (dim - kernel) / stride + 1.  Scratch: tmp1 (X*Y*Oz*4 floats), tmp2 (X*Oy*Oz*4 floats).
+ * plx_avgpool3d_bwd is its autograd (grad_out (Ox,Oy,Oz,4) -> grad_in (X,Y,Z,4), overwritten), same scratch sizes.
+ */
+int plx_avgpool3d_fwd(const float* in, const int32_t dims[3], int32_t kernel, int32_t stride, float* tmp1, float* tmp2,
+                      float* out, void* stream);
+int plx_avgpool3d_bwd(const float* grad_out, const int32_t dims[3], int32_t kernel, int32_t stride, float* tmp2, float* tmp1,
+                      float* grad_in, void* stream);
+
+/*
  * Self-test of the library's exact fp32 helpers: evaluates the hoisted-reciprocal quotient x / y (the march's divisor
  * path), the inlined square root and the per-element quotient (Adam) on `n` pseudo-random inputs and counts results
  * that differ in any bit from CUDA's IEEE intrinsics (__fdiv_rn / __fsqrt_rn).  `mismatches` = 3 device uint64 counters

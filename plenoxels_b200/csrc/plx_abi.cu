@@ -249,6 +249,30 @@ int plx_composite_bwd(const float* samples, int64_t n_rays, int32_t num_samples,
                        "plx_composite_bwd");
 }
 
+static int check_pool(const void* a, const int32_t* dims, int32_t k, int32_t s, const void* t1, const void* t2, const void* b) {
+    if (!dims) return fail(PLX_E_NULL, "dims is NULL");
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return fail(PLX_E_SHAPE, "grid dims must be positive");
+    if (k < 1 || s < 1) return fail(PLX_E_SHAPE, "kernel and stride must be >= 1");
+    if (k > dims[0] || k > dims[1] || k > dims[2]) return fail(PLX_E_SHAPE, "pooling window %d larger than the grid (%d,%d,%d)", k, dims[0], dims[1], dims[2]);
+    if (!a || !b || !t1 || !t2) return fail(PLX_E_NULL, "pooling buffer is NULL");
+    if ((uintptr_t)a % 16 || (uintptr_t)b % 16 || (uintptr_t)t1 % 16 || (uintptr_t)t2 % 16) return fail(PLX_E_ALIGN, "pooling buffers must be 16-byte aligned");
+    return PLX_OK;
+}
+
+int plx_avgpool3d_fwd(const float* in, const int32_t dims[3], int32_t kernel, int32_t stride, float* tmp1, float* tmp2,
+                      float* out, void* stream) {
+    int rc;
+    if ((rc = check_pool(in, dims, kernel, stride, tmp1, tmp2, out)) != PLX_OK) return rc;
+    return cuda_result(plx::launch_avgpool3d_fwd(in, dims, kernel, stride, tmp1, tmp2, out, (cudaStream_t)stream), "plx_avgpool3d_fwd");
+}
+
+int plx_avgpool3d_bwd(const float* grad_out, const int32_t dims[3], int32_t kernel, int32_t stride, float* tmp2, float* tmp1,
+                      float* grad_in, void* stream) {
+    int rc;
+    if ((rc = check_pool(grad_out, dims, kernel, stride, tmp1, tmp2, grad_in)) != PLX_OK) return rc;
+    return cuda_result(plx::launch_avgpool3d_bwd(grad_out, dims, kernel, stride, tmp2, tmp1, grad_in, (cudaStream_t)stream), "plx_avgpool3d_bwd");
+}
+
 int plx_selftest_arith(float y, uint64_t n, uint64_t seed, uint64_t* mismatches, void* stream) {
     if (!mismatches) return fail(PLX_E_NULL, "mismatches is NULL");
     if (!(y == y) || y == 0.f) return fail(PLX_E_SHAPE, "divisor must be a non-zero number");

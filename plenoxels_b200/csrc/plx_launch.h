@@ -37,6 +37,10 @@ cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int
 
 cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, const StepTail& tail, cudaStream_t st);
 
+cudaError_t launch_avgpool3d_fwd(const float* in, const int32_t* dims, int k, int s, float* tmp1, float* tmp2, float* out,
+                                 cudaStream_t st);
+cudaError_t launch_avgpool3d_bwd(const float* gout, const int32_t* dims, int k, int s, float* tmp2, float* tmp1, float* gin,
+                                 cudaStream_t st);
 cudaError_t launch_peer_barrier(int32_t* const* flags, int rank, int world, int channel, int epoch, cudaStream_t st);
 
 cudaError_t launch_generate_rays(const float* imgs, int n_cams, int img_h, int img_w, const float* poses, float fov,

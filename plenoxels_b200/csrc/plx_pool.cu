@@ -1,0 +1,75 @@
+// plx_pool.cu — strided 3-D average pooling of an (X,Y,Z,4) grid and its backward, as three separable box passes.
+//
+// Stands under average_pool3d_grid (src/grid_functions.py:173-181 = F.avg_pool3d(kernel k, stride s, no padding)) that
+// fit() applies to the whole grid on each of its first 230 steps (scripts/train.py:110-118, windows 93^3 .. 3^3, stride
+// max(1, k // 4)).  A k^3 window is the product of three 1-D box sums, so the forward is  Z-pass -> Y-pass -> X-pass with
+// k additions per output each (instead of k^3), and the backward is the three transposed passes in gather form (every
+// input cell sums the <= ceil(k/s) windows that cover it): no atomics, every access a 16-byte cell.
+#include "plx_device.cuh"
+#include "plx_launch.h"
+
+namespace plx {
+
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// out[a][o][c] = scale * sum_{d<k} in[a][o*s + d][c]   over a tensor viewed as (A, L, C) -> (A, O, C), C in float4 units
+__global__ void __launch_bounds__(256) k_box_fwd(const float4* __restrict__ in, float4* __restrict__ out, int64_t A, int L,
+                                                 int O, int64_t C, int k, int s, float scale) {
+    const int64_t total = A * O * C;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = e % C, o = (e / C) % O, a = e / (C * O);
+        const float4* src = in + (a * L + o * s) * C + c;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int d = 0; d < k; ++d) acc = add4(acc, __ldg(src + d * C));
+        out[e] = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+    }
+}
+
+// transposed pass: gin[a][l][c] = scale * sum_{o : o*s <= l < o*s + k} gout[a][o][c]
+__global__ void __launch_bounds__(256) k_box_bwd(const float4* __restrict__ gout, float4* __restrict__ gin, int64_t A, int L,
+                                                 int O, int64_t C, int k, int s, float scale) {
+    const int64_t total = A * L * C;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = e % C, l = (e / C) % L, a = e / (C * L);
+        int o_lo = (int)l - k + 1;
+        o_lo = o_lo <= 0 ? 0 : (o_lo + s - 1) / s;
+        int o_hi = (int)(l / s);
+        if (o_hi > O - 1) o_hi = O - 1;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int o = o_lo; o <= o_hi; ++o) acc = add4(acc, __ldg(gout + (a * O + o) * C + c));
+        gin[e] = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+    }
+}
+
+static unsigned pool_blocks(int64_t n) {
+    int64_t b = (n + 255) / 256;
+    const int64_t cap = 148 * 16;
+    return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+cudaError_t launch_avgpool3d_fwd(const float* in, const int32_t* dims, int k, int s, float* tmp1, float* tmp2, float* out,
+                                 cudaStream_t st) {
+    const int X = dims[0], Y = dims[1], Z = dims[2];
+    const int Ox = (X - k) / s + 1, Oy = (Y - k) / s + 1, Oz = (Z - k) / s + 1;
+    const float inv = 1.f / (float)k;
+    // Z pass: (X*Y, Z, 1) -> (X*Y, Oz, 1)
+    k_box_fwd<<<pool_blocks((int64_t)X * Y * Oz), 256, 0, st>>>((const float4*)in, (float4*)tmp1, (int64_t)X * Y, Z, Oz, 1, k, s, inv);
+    // Y pass: (X, Y, Oz) -> (X, Oy, Oz)
+    k_box_fwd<<<pool_blocks((int64_t)X * Oy * Oz), 256, 0, st>>>((const float4*)tmp1, (float4*)tmp2, X, Y, Oy, Oz, k, s, inv);
+    // X pass: (1, X, Oy*Oz) -> (1, Ox, Oy*Oz)
+    k_box_fwd<<<pool_blocks((int64_t)Ox * Oy * Oz), 256, 0, st>>>((const float4*)tmp2, (float4*)out, 1, X, Ox, (int64_t)Oy * Oz, k, s, inv);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_avgpool3d_bwd(const float* gout, const int32_t* dims, int k, int s, float* tmp2, float* tmp1, float* gin,
+                                 cudaStream_t st) {
+    const int X = dims[0], Y = dims[1], Z = dims[2];
+    const int Ox = (X - k) / s + 1, Oy = (Y - k) / s + 1, Oz = (Z - k) / s + 1;
+    const float inv = 1.f / (float)k;
+    k_box_bwd<<<pool_blocks((int64_t)X * Oy * Oz), 256, 0, st>>>((const float4*)gout, (float4*)tmp2, 1, X, Ox, (int64_t)Oy * Oz, k, s, inv);
+    k_box_bwd<<<pool_blocks((int64_t)X * Y * Oz), 256, 0, st>>>((const float4*)tmp2, (float4*)tmp1, X, Y, Oy, Oz, k, s, inv);
+    k_box_bwd<<<pool_blocks((int64_t)X * Y * Z), 256, 0, st>>>((const float4*)tmp1, (float4*)gin, (int64_t)X * Y, Z, Oz, 1, k, s, inv);
+    return cudaGetLastError();
+}
+
+}  // namespace plx

@@ -146,7 +146,11 @@ def collect_cell_information_via_indices(normalized_samples_for_indices, B):
 
 
 def average_pool3d_grid(tensor, receptive_field_size=3, stride=None):
-    """Strided 3-D average pooling of an (X,Y,Z,4) grid — src/grid_functions.py:173-181 (library op; §8f "next")."""
+    """Strided 3-D average pooling of an (X,Y,Z,4) grid — src/grid_functions.py:173-181.  On CUDA (X,Y,Z,4) fp32 grids this
+    is three separable box passes (plx_avgpool3d_fwd/bwd) returning a contiguous (x,y,z,4) tensor; anything else takes
+    the library call."""
+    if tensor.is_cuda and tensor.dim() == 4 and tensor.shape[3] == 4 and tensor.dtype == torch.float32:
+        return ops.avgpool3d_grid(tensor, receptive_field_size, stride)
     inp = tensor.permute(3, 0, 1, 2).unsqueeze(0)
     out = F.avg_pool3d(inp, (receptive_field_size,) * 3, stride=stride)
     return out.squeeze().permute(1, 2, 3, 0)

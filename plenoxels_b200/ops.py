@@ -326,6 +326,47 @@ class _Composite(torch.autograd.Function):
         return gs
 
 
+class _AvgPool3dGrid(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, grid, kernel, stride):
+        dev = L.require_cuda(grid)
+        g = grid.contiguous().float()
+        X, Y, Z, ch = g.shape
+        if ch != 4:
+            raise L.PlxError("average pooling kernel handles (X,Y,Z,4) grids")
+        O = [(d - kernel) // stride + 1 for d in (X, Y, Z)]
+        if min(O) < 1:
+            raise RuntimeError(f"pooling window {kernel} larger than the grid {(X, Y, Z)}")      # F.avg_pool3d raises too
+        out = torch.empty((O[0], O[1], O[2], 4), dtype=torch.float32, device=dev)
+        t1 = torch.empty((X * Y * O[2] * 4,), dtype=torch.float32, device=dev)
+        t2 = torch.empty((X * O[1] * O[2] * 4,), dtype=torch.float32, device=dev)
+        dims = (C.c_int32 * 3)(X, Y, Z)
+        with torch.cuda.device(dev):
+            L.check(L.load().plx_avgpool3d_fwd(g.data_ptr(), dims, kernel, stride, t1.data_ptr(), t2.data_ptr(), out.data_ptr(),
+                                               L.stream_ptr(dev)), "plx_avgpool3d_fwd")
+        ctx.meta = (X, Y, Z, kernel, stride, O)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        X, Y, Z, kernel, stride, O = ctx.meta
+        dev = grad_out.device
+        go = grad_out.contiguous().float()
+        gin = torch.empty((X, Y, Z, 4), dtype=torch.float32, device=dev)
+        t1 = torch.empty((X * Y * O[2] * 4,), dtype=torch.float32, device=dev)
+        t2 = torch.empty((X * O[1] * O[2] * 4,), dtype=torch.float32, device=dev)
+        dims = (C.c_int32 * 3)(X, Y, Z)
+        with torch.cuda.device(dev):
+            L.check(L.load().plx_avgpool3d_bwd(go.data_ptr(), dims, kernel, stride, t2.data_ptr(), t1.data_ptr(), gin.data_ptr(),
+                                               L.stream_ptr(dev)), "plx_avgpool3d_bwd")
+        return gin, None, None
+
+
+def avgpool3d_grid(grid, kernel, stride=None):
+    """`average_pool3d_grid` (src/grid_functions.py:173-181): cubic window, stride (default = window), no padding."""
+    return _AvgPool3dGrid.apply(grid, int(kernel), int(stride if stride is not None else kernel))
+
+
 def composite(samples):
     """`compute_alpha_weighted_pixels` (src/ray_sampling.py:172-192): (..., S, 4) -> (..., 4)."""
     if samples.shape[-1] != 4:

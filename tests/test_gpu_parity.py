@@ -287,3 +287,29 @@ def test_train_steps_match_oracle(mode):
         # Adam's first steps are +-lr*sign(g): cells whose gradient is O(rounding noise) may flip; compare the bulk
         diff = np.abs(tr.grid.cpu().numpy() - grid)
         assert np.quantile(diff, 0.999) <= 1e-5, f"step {step}: {np.quantile(diff, 0.999)}"
+
+
+@pytest.mark.parametrize("G,k,s", [(24, 3, 1), (24, 5, 1), (40, 9, 2), (40, 21, 5), (64, 33, 8), (31, 7, 3)])
+def test_average_pool3d_grid_matches_library(plx_lib, G, k, s):
+    """Separable box-filter pooling (plx_avgpool3d_fwd/bwd) vs F.avg_pool3d as average_pool3d_grid calls it
+    (src/grid_functions.py:173-181), forward and backward; tolerance = summation order only."""
+    torch.manual_seed(G + k)
+    grid = (torch.rand(G, G + 1, G + 2, 4, device="cuda") * 1.4 - 0.2).requires_grad_(True)
+    out = ops.avgpool3d_grid(grid, k, s)
+    ref_in = grid.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.avg_pool3d(ref_in.permute(3, 0, 1, 2).unsqueeze(0), (k, k, k), stride=s).squeeze(0).permute(1, 2, 3, 0)
+    assert out.shape == ref.shape
+    # judge both against an fp64 evaluation: the library's own fp32 summation noise grows with the window (k^3 terms)
+    in64 = grid.detach().double().requires_grad_(True)
+    ref64 = torch.nn.functional.avg_pool3d(in64.permute(3, 0, 1, 2).unsqueeze(0), (k, k, k), stride=s).squeeze(0).permute(1, 2, 3, 0)
+    err_ours = float((out.double() - ref64).abs().max())
+    err_lib = float((ref.double() - ref64).abs().max())
+    assert err_ours <= 2 * err_lib + 1e-6, (err_ours, err_lib)
+    g = torch.randn_like(out)
+    out.backward(g)
+    ref.backward(g)
+    ref64.backward(g.double())
+    scale = float(in64.grad.abs().max())
+    gerr_ours = float((grid.grad.double() - in64.grad).abs().max()) / scale
+    gerr_lib = float((ref_in.grad.double() - in64.grad).abs().max()) / scale
+    assert gerr_ours <= 2 * gerr_lib + 1e-6, (gerr_ours, gerr_lib)

@@ -82,8 +82,85 @@ def c5():
                               "train_Mrays_s": round(n / ms_t / 1e3, 1), "train_GBs": round(gt, 1), "train_frac": round(gt / PEAK, 3)}))
 
 
+def pool():
+    """average_pool3d_grid fwd+bwd (scripts/train.py:110-118) on a 256^3 grid: separable kernels vs the library call."""
+    G = 256
+    grid = torch.rand(G, G, G, 4, device=dev).requires_grad_(True)
+    for k in (93, 45, 9, 3):
+        s = max(1, k // 4)
+
+        def ours():
+            out = ops.avgpool3d_grid(grid, k, s)
+            out.backward(torch.ones_like(out))
+            grid.grad = None
+
+        def lib():
+            out = torch.nn.functional.avg_pool3d(grid.permute(3, 0, 1, 2).unsqueeze(0), (k, k, k), stride=s)
+            out.backward(torch.ones_like(out))
+            grid.grad = None
+
+        ms_o = timed(ours, n=5, warm=2)
+        ms_l = timed(lib, n=2, warm=1)
+        print(json.dumps({"config": "pool 256^3", "kernel": k, "stride": s, "ours_fwd_bwd_ms": round(ms_o, 3),
+                          "library_fwd_bwd_ms": round(ms_l, 3), "speedup": round(ms_l / ms_o, 1)}))
+
+
+def fit_body():
+    """The reference's loop body (scripts/train.py:130-184) written with the drop-in functions + torch.optim.Adam, as the
+    unmodified fit() runs it: lazy-fusion bridge on / off, at the C2 shape."""
+    import src.grid_functions as gf
+    import src.ray_sampling as rs
+    sc = synth.make_scene("c2", H=200)
+    C_, R, S = sc.poses.shape[0], sc.rays_per_cam, sc.num_samples
+    poses, imgs = sc.poses.to(dev), sc.imgs.to(dev)
+    for lazy_on in ("1", "0"):
+        os.environ["PLX_LAZY"] = lazy_on
+        gi, cells, _, _ = gf.generate_grid(sc.G, sc.G, sc.G, points_distance=sc.points_distance, info_size=4, device=dev)
+        with torch.no_grad():
+            cells.copy_(sc.grid.to(dev))
+        opt = torch.optim.Adam([cells], lr=sc.lr)
+        gabs = torch.zeros_like(cells)
+
+        def step():
+            samples, targets, cam, dirs = rs.sample_camera_rays_batched(
+                transform_matrices=poses, camera_angle_x=sc.fov, imgs=imgs, number_of_rays=R, num_samples=S,
+                delta_step=sc.delta_step, even_spread=False, camera_ray=False, device=dev)
+            ns = rs.normalize_samples_for_indecies(gi, samples, sc.points_distance)
+            nearest, mask = gf.get_nearest_voxels(ns, cells.clip(0, 1))
+            nearest = (nearest * mask.unsqueeze(-1)).reshape(C_, R, S, 4)
+            pix = rs.compute_alpha_weighted_pixels(nearest).reshape(-1, 4)
+            loss = torch.nn.functional.mse_loss(pix, targets)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            gabs.add_(cells.grad.abs())
+
+        ms = timed(step, n=20, warm=3)
+        print(json.dumps({"config": "fit() loop body via drop-in API, C2 shape", "lazy_bridge": lazy_on == "1",
+                          "ms_per_step": round(ms, 3), "Mrays_per_s": round(C_ * R / ms / 1e3, 2)}))
+
+
+def ref_cuda():
+    """The reference's own op sequence (oracle/torch_port.py = scripts/train.py:130-184 restated op for op) on device="cuda":
+    stock PyTorch eager on the same B200, the 'existing GPU path' of BASELINE.md §4."""
+    from oracle.torch_port import ReferenceStep
+    sc = synth.make_scene("c2", H=200)
+    ref = ReferenceStep(sc.grid, sc.points_distance, sc.poses, sc.fov, sc.imgs, sc.rays_per_cam, sc.num_samples, sc.delta_step,
+                        sc.lr, device="cuda:0")
+    uv = synth.random_uv(sc.poses.shape[0], sc.rays_per_cam).to(dev)
+    ms = timed(lambda: ref.step(uv), n=10, warm=2)
+    print(json.dumps({"config": "reference op sequence, stock PyTorch eager on cuda, C2 shape", "ms_per_step": round(ms, 3),
+                      "Mrays_per_s": round(sc.n_rays / ms / 1e3, 2)}))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c4"]
+    if "refcuda" in which:
+        ref_cuda()
+    if "pool" in which:
+        pool()
+    if "fit" in which:
+        fit_body()
     if "c4" in which:
         c4("nearest")
         if "trilinear" in which:

@@ -21,11 +21,6 @@
 
 namespace plx {
 
-template <int SPL>
-struct Seg {            // one iteration's SPL samples of a lane
-    float4 c[SPL];      // clamped cell values (0 when out of bounds / past the range)
-};
-
 // composite one iteration: acc += sum_j alpha_j T_j c_j, T <- T * prod(1 - alpha); returns the product of the iteration
 template <int SPL>
 __device__ __forceinline__ void composite_iter(const float4 (&c)[SPL], int lane, float& T, float4& acc) {
@@ -104,6 +99,12 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
             if (SPL == 1) lc[it * W + lane] = lin[0];
             else *reinterpret_cast<int2*>(lc + it * W + lane * 2) = make_int2(lin[0], lin[SPL - 1]);
             if (lane == 0) tcs[it] = T;
+            // empty space is the common case (a trained grid is mostly alpha == 0, fit() even starts from all zeros):
+            // an iteration whose 32*SPL samples are all transparent changes neither T nor the pixel — skip its scan
+            bool any_alpha = false;
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) any_alpha = any_alpha || c[j].w != 0.f;
+            if (!__any_sync(FULL, any_alpha)) continue;
             composite_iter<SPL>(c, lane, T, acc);
             if (T == 0.f && !full) {
                 // first sample whose factor is exactly 0 (alpha == 1); none => the product merely underflowed
@@ -172,25 +173,36 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
                 c[j] = g.clamp ? clamp4(raw[j]) : raw[j];
                 v[j] = fmaf(c[j].x, gr.x, fmaf(c[j].y, gr.y, fmaf(c[j].z, gr.z, gr.w)));      // c_k . g_rgb + g_A
             }
-            // lane aggregate of the affine maps s -> alpha v + (1 - alpha) s, last sample innermost
-            float A = 0.f, B = 1.f;
+            bool any_alpha = false;
 #pragma unroll
-            for (int j = SPL - 1; j >= 0; --j) { A = fmaf(1.f - c[j].w, A, c[j].w * v[j]); B *= 1.f - c[j].w; }
-            float behind[SPL];
-            behind[SPL - 1] = warp_behind(A, B, lane, carry);
+            for (int j = 0; j < SPL; ++j) any_alpha = any_alpha || c[j].w != 0.f;
+            float behind[SPL], pf[SPL];
+            float base;
+            if (__any_sync(FULL, any_alpha)) {
+                // lane aggregate of the affine maps s -> alpha v + (1 - alpha) s, last sample innermost
+                float A = 0.f, B = 1.f;
 #pragma unroll
-            for (int j = SPL - 1; j >= 1; --j) behind[j - 1] = fmaf(1.f - c[j].w, behind[j], c[j].w * v[j]);
-            if (opaque && ib == n_fwd - 1 && lane == zl) {
+                for (int j = SPL - 1; j >= 0; --j) { A = fmaf(1.f - c[j].w, A, c[j].w * v[j]); B *= 1.f - c[j].w; }
+                behind[SPL - 1] = warp_behind(A, B, lane, carry);
 #pragma unroll
-                for (int j = 0; j < SPL; ++j) if (j == zj) behind[j] = s_star;
+                for (int j = SPL - 1; j >= 1; --j) behind[j - 1] = fmaf(1.f - c[j].w, behind[j], c[j].w * v[j]);
+                if (opaque && ib == n_fwd - 1 && lane == zl) {
+#pragma unroll
+                    for (int j = 0; j < SPL; ++j) if (j == zj) behind[j] = s_star;
+                }
+                // T_k inside the iteration
+                pf[0] = 1.f;
+#pragma unroll
+                for (int j = 1; j < SPL; ++j) pf[j] = pf[j - 1] * (1.f - c[j - 1].w);
+                float total;
+                base = tcs[ib] * warp_excl_prod(pf[SPL - 1] * (1.f - c[SPL - 1].w), lane, total);
+            } else {
+                // all-transparent iteration: every map is the identity and every factor is 1 — T_k = T at the start of
+                // the iteration, the colour behind each sample is the carried one; no scan needed
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) { behind[j] = carry; pf[j] = 1.f; }
+                base = tcs[ib];
             }
-            // T_k inside the iteration
-            float pf[SPL];
-            pf[0] = 1.f;
-#pragma unroll
-            for (int j = 1; j < SPL; ++j) pf[j] = pf[j - 1] * (1.f - c[j - 1].w);
-            float total;
-            const float base = tcs[ib] * warp_excl_prod(pf[SPL - 1] * (1.f - c[SPL - 1].w), lane, total);
             float4 d[SPL];
 #pragma unroll
             for (int j = 0; j < SPL; ++j) {

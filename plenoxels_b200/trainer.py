@@ -179,6 +179,27 @@ class VoxelTrainer:
             param.update(extra_param)
         return {"grid": self.grid.detach().cpu(), "grid_grad": self.grad_abs_sum.detach().cpu(), "param": param}
 
+    def resume_state(self) -> dict:
+        """What the reference's checkpoint lacks for resuming (it saves no optimiser state): Adam moments and
+        the step counter.  `checkpoint()` merged with this dict is a superset of the reference format; scripts that read
+        only `grid` / `grid_grad` / `param` (scripts/compare_inference_to_image.py:41-49) are unaffected."""
+        return {"optimizer": {"exp_avg": self.exp_avg.detach().cpu(), "exp_avg_sq": self.exp_avg_sq.detach().cpu(),
+                              "step": self.step_count, "lr": self.lr, "betas": tuple(self.betas), "eps": self.eps}}
+
+    def load_state(self, ckpt: dict) -> None:
+        """Restore grid, |grad| sum and (if present) the optimiser state saved by `checkpoint()` / `resume_state()`."""
+        with torch.no_grad():
+            self.grid.copy_(ckpt["grid"].to(self.device))
+            if "grid_grad" in ckpt:
+                self.grad_abs_sum.copy_(ckpt["grid_grad"].to(self.device))
+            opt = ckpt.get("optimizer")
+            if opt:
+                self.exp_avg.copy_(opt["exp_avg"].to(self.device))
+                self.exp_avg_sq.copy_(opt["exp_avg_sq"].to(self.device))
+                self.step_count = int(opt["step"])
+            self.grad.zero_()
+            self._loss2.zero_()
+
 
 def slab_range(n_cells: int, rank: int, world: int):
     """[begin, end) in floats of the contiguous block of cells whose optimiser state `rank` owns."""

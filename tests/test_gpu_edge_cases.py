@@ -149,3 +149,22 @@ def test_checkpoint_has_the_reference_format(plx_lib, tmp_path):
         assert ck[k].shape == (64, 64, 64, 4) and ck[k].dtype == torch.float32 and not ck[k].is_cuda and not ck[k].requires_grad
     assert ck["param"]["gridsize"] == [64, 64, 64] and isinstance(ck["param"]["points_distance"], float)
     assert float(ck["grid_grad"].sum()) > 0
+
+
+def test_resume_continues_bit_exactly(plx_lib):
+    """checkpoint() + resume_state() -> load_state(): a resumed trainer takes the same next steps as the original
+    (deterministic here: 1 ray per cell at most would be needed for bit-exactness, so compare to atomics' noise level)."""
+    sc = synth.make_scene("c1", H=16)
+    mk = lambda: VoxelTrainer(sc.grid.to(DEV), sc.points_distance, sc.poses.to(DEV), sc.fov, sc.imgs.to(DEV), 256, 48, 6.0 / 48, lr=0.01)
+    a = mk()
+    uvs = [synth.random_uv(1, 256, seed=20 + i).to(DEV) for i in range(4)]
+    for u in uvs[:2]:
+        a.step(u)
+    ck = {**a.checkpoint(), **a.resume_state()}
+    b = mk()
+    b.load_state(ck)
+    assert b.step_count == 2 and torch.equal(b.grid, a.grid) and torch.equal(b.exp_avg_sq, a.exp_avg_sq)
+    for u in uvs[2:]:
+        la, lb = float(a.step(u)), float(b.step(u))
+        assert abs(la - lb) <= 1e-6 * abs(la)
+    assert float((a.grid - b.grid).abs().max()) <= 1e-5

@@ -259,6 +259,14 @@ int plx_avgpool3d_bwd(const float* grad_out, const int32_t dims[3], int32_t kern
                       float* grad_in, void* stream);
 
 /*
+ * tv_loss — scripts/train.py:44-65 with its weight (:163-168): loss_out[0] = tv * sqrt(sum of squared neighbour
+ * differences of the contiguous (X,Y,Z,4) grid along the three axes) and, when `grad` != NULL,
+ * grad += d(loss)/d(grid) (6-neighbour stencil).  `scratch` = 1 double of device memory.  Where the reference's gradient
+ * is 0/0 (a constant grid) nothing is added.
+ */
+int plx_tv_loss(const float* grid, const int32_t dims[3], float tv, float* grad, double* scratch, float* loss_out, void* stream);
+
+/*
  * Self-test of the library's exact fp32 helpers: evaluates the hoisted-reciprocal quotient x / y (the march's divisor
  * path), the inlined square root and the per-element quotient (Adam) on `n` pseudo-random inputs and counts results
  * that differ in any bit from CUDA's IEEE intrinsics (__fdiv_rn / __fsqrt_rn).  `mismatches` = 3 device uint64 counters

@@ -342,6 +342,29 @@ def render_backward(grid, origins, dirs, num_samples, delta_step, gmin, points_d
     return out * passmask
 
 
+# --------------------------------------------------------------------------- regulariser
+def tv_loss(grid, dtype=np.float64):
+    """`tv_loss` of scripts/train.py:44-65: sqrt of the summed squared neighbour differences along the three grid axes
+    (all four channels), and its gradient w.r.t. the grid (autograd of :63).  At an all-equal grid the reference's
+    gradient is 0/0 = NaN; this restatement (and the kernel) return 0 there."""
+    g = np.asarray(grid).astype(dtype)
+    d1 = g[:, :-1] - g[:, 1:]
+    d2 = g[:, :, :-1] - g[:, :, 1:]
+    d0 = g[:-1] - g[1:]
+    s = (d1 ** 2).sum() + (d2 ** 2).sum() + (d0 ** 2).sum()
+    loss = float(np.sqrt(s))
+    grad = np.zeros_like(g)
+    if loss > 0:
+        grad[:, :-1] += d1
+        grad[:, 1:] -= d1
+        grad[:, :, :-1] += d2
+        grad[:, :, 1:] -= d2
+        grad[:-1] += d0
+        grad[1:] -= d0
+        grad /= loss
+    return loss, grad
+
+
 # --------------------------------------------------------------------------- optimiser
 def adam_step(p, g, m, v, gabs, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
     """One torch.optim.Adam step (torch/optim/adam.py `_single_tensor_adam`, non-capturable branch,

@@ -16,7 +16,13 @@ import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("PLX_REFERENCE", "/root/reference")
 sys.path.insert(0, REPO)
-sys.path.insert(1, REF)          # `src.*` resolves to the reference here
+sys.path.insert(1, REF)
+# `src.*` must resolve to the REFERENCE here.  The reference's src/ has no __init__.py (a namespace package), so this
+# repo's src/ shim (a regular package) would always win the import; pin the name to the reference directory instead.
+import types  # noqa: E402
+_ref_src = types.ModuleType("src")
+_ref_src.__path__ = [os.path.join(REF, "src")]
+sys.modules["src"] = _ref_src
 
 from oracle import plenoxel_oracle as po      # noqa: E402
 from oracle import torch_port as tp           # noqa: E402
@@ -168,8 +174,25 @@ def run_even_spread(tag, G, H, R, S, delta):
     check(f"{tag}: even-spread samples bit-exact (S={S})", np.array_equal(pos.reshape(-1, 3), samples.numpy()))
 
 
+def run_tv():
+    """tv_loss (scripts/train.py:44-65) value and autograd vs the oracle's analytic gradient."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_train", os.path.join(REF, "scripts", "train.py"))
+    ref_train = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_train)
+    for G in (6, 17):
+        g = (synth.dense_grid(G)[:, : G - 1, : G - 2]).clone().requires_grad_(True)
+        loss = ref_train.tv_loss(g)
+        loss.backward()
+        oloss, ograd = po.tv_loss(g.detach().numpy())
+        check(f"tv G={G}: loss", abs(oloss - float(loss)) <= 1e-6 * float(loss), f"{oloss:.7f} vs {float(loss):.7f}")
+        err = np.abs(ograd - g.grad.numpy()).max() / np.abs(g.grad.numpy()).max()
+        check(f"tv G={G}: gradient <= 1e-6 rel", err <= 1e-6, f"rel err {err:.2e}")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    run_tv()
     run_scene("c1-dense-nn", 64, 1, 64, 4096, 64, 6.0 / 64, "dense")
     run_scene("c1-ball-nn", 64, 4, 32, 256, 64, 6.0 / 64, "ball")
     run_scene("c2small-ball-nn", 128, 6, 40, 64, 600, 0.0125, "ball")

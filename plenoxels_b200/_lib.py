@@ -111,6 +111,7 @@ PROTOTYPES = {
     "plx_composite_bwd": (C.c_int, [c_void, C.c_int64, C.c_int32, c_void, c_void, c_void]),
     "plx_avgpool3d_fwd": (C.c_int, [c_void, C.POINTER(C.c_int32), C.c_int32, C.c_int32, c_void, c_void, c_void, c_void]),
     "plx_avgpool3d_bwd": (C.c_int, [c_void, C.POINTER(C.c_int32), C.c_int32, C.c_int32, c_void, c_void, c_void, c_void]),
+    "plx_tv_loss": (C.c_int, [c_void, C.POINTER(C.c_int32), C.c_float, c_void, c_void, c_void, c_void]),
     "plx_selftest_arith": (C.c_int, [C.c_float, C.c_uint64, C.c_uint64, c_void, c_void]),
     "plx_train_step": (C.c_int, [C.POINTER(PlxTrainStep), C.c_int32, c_void]),
     "plx_train_step_host": (C.c_int, [C.POINTER(PlxTrainStep), c_void, c_void, C.c_int32, c_void]),

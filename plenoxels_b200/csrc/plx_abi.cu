@@ -273,6 +273,13 @@ int plx_avgpool3d_bwd(const float* grad_out, const int32_t dims[3], int32_t kern
     return cuda_result(plx::launch_avgpool3d_bwd(grad_out, dims, kernel, stride, tmp2, tmp1, grad_in, (cudaStream_t)stream), "plx_avgpool3d_bwd");
 }
 
+int plx_tv_loss(const float* grid, const int32_t dims[3], float tv, float* grad, double* scratch, float* loss_out, void* stream) {
+    if (!dims || !grid || !scratch) return fail(PLX_E_NULL, "grid/dims/scratch is NULL");
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return fail(PLX_E_SHAPE, "grid dims must be positive");
+    if ((uintptr_t)grid % 16 || (uintptr_t)grad % 16 || (uintptr_t)scratch % 8) return fail(PLX_E_ALIGN, "tv buffers are misaligned");
+    return cuda_result(plx::launch_tv_loss(grid, dims, tv, grad, scratch, loss_out, (cudaStream_t)stream), "plx_tv_loss");
+}
+
 int plx_selftest_arith(float y, uint64_t n, uint64_t seed, uint64_t* mismatches, void* stream) {
     if (!mismatches) return fail(PLX_E_NULL, "mismatches is NULL");
     if (!(y == y) || y == 0.f) return fail(PLX_E_SHAPE, "divisor must be a non-zero number");

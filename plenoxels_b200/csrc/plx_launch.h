@@ -41,6 +41,8 @@ cudaError_t launch_avgpool3d_fwd(const float* in, const int32_t* dims, int k, in
                                  cudaStream_t st);
 cudaError_t launch_avgpool3d_bwd(const float* gout, const int32_t* dims, int k, int s, float* tmp2, float* tmp1, float* gin,
                                  cudaStream_t st);
+cudaError_t launch_tv_loss(const float* grid, const int32_t* dims, float tv, float* grad, double* scratch, float* loss_out,
+                           cudaStream_t st);
 cudaError_t launch_peer_barrier(int32_t* const* flags, int rank, int world, int channel, int epoch, cudaStream_t st);
 
 cudaError_t launch_generate_rays(const float* imgs, int n_cams, int img_h, int img_w, const float* poses, float fov,

@@ -72,4 +72,70 @@ cudaError_t launch_avgpool3d_bwd(const float* gout, const int32_t* dims, int k, 
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// tv_loss — scripts/train.py:44-65: sqrt( sum over the three grid axes of squared neighbour differences, 4 channels )
+// and its gradient, as two dense passes: (1) the sum of squares into a double accumulator, (2) the 6-neighbour stencil
+// grad += tv / sqrt(S) * (sum_axis (g - g_next) [has next] - (g_prev - g) [has prev]).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sq4(float4 a, float4 b) {
+    const float x = a.x - b.x, y = a.y - b.y, z = a.z - b.z, w = a.w - b.w;
+    return x * x + y * y + z * z + w * w;
+}
+
+__global__ void __launch_bounds__(256) k_tv_sumsq(const float4* __restrict__ g, int X, int Y, int Z, double* __restrict__ sum) {
+    __shared__ float s_part[8];
+    const int64_t n = (int64_t)X * Y * Z;
+    float acc = 0.f;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int z = (int)(e % Z), y = (int)((e / Z) % Y), x = (int)(e / ((int64_t)Z * Y));
+        const float4 c = __ldg(g + e);
+        if (z + 1 < Z) acc += sq4(c, __ldg(g + e + 1));
+        if (y + 1 < Y) acc += sq4(c, __ldg(g + e + Z));
+        if (x + 1 < X) acc += sq4(c, __ldg(g + e + (int64_t)Z * Y));
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += (double)s_part[i];
+        atomicAdd(sum, t);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_tv_grad(const float4* __restrict__ g, int X, int Y, int Z, const double* __restrict__ sum,
+                                                 float tv, float4* __restrict__ grad, float* __restrict__ loss_out) {
+    const double S = *sum;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && loss_out) *loss_out = tv * (float)sqrt(S);
+    if (!(S > 0.0) || !grad) return;               // the reference's gradient is 0/0 here; we add nothing
+    const float scale = tv / (float)sqrt(S);
+    const int64_t n = (int64_t)X * Y * Z, sx = (int64_t)Z * Y;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int z = (int)(e % Z), y = (int)((e / Z) % Y), x = (int)(e / sx);
+        const float4 c = __ldg(g + e);
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto towards = [&](const float4 nb) { d.x += c.x - nb.x; d.y += c.y - nb.y; d.z += c.z - nb.z; d.w += c.w - nb.w; };
+        if (z + 1 < Z) towards(__ldg(g + e + 1));
+        if (z > 0)     towards(__ldg(g + e - 1));
+        if (y + 1 < Y) towards(__ldg(g + e + Z));
+        if (y > 0)     towards(__ldg(g + e - Z));
+        if (x + 1 < X) towards(__ldg(g + e + sx));
+        if (x > 0)     towards(__ldg(g + e - sx));
+        float4 o = grad[e];
+        o.x = fmaf(scale, d.x, o.x); o.y = fmaf(scale, d.y, o.y); o.z = fmaf(scale, d.z, o.z); o.w = fmaf(scale, d.w, o.w);
+        grad[e] = o;
+    }
+}
+
+cudaError_t launch_tv_loss(const float* grid, const int32_t* dims, float tv, float* grad, double* scratch, float* loss_out,
+                           cudaStream_t st) {
+    const int X = dims[0], Y = dims[1], Z = dims[2];
+    const int64_t n = (int64_t)X * Y * Z;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    k_tv_sumsq<<<pool_blocks(n), 256, 0, st>>>((const float4*)grid, X, Y, Z, scratch);
+    k_tv_grad<<<pool_blocks(n), 256, 0, st>>>((const float4*)grid, X, Y, Z, scratch, tv, (float4*)grad, loss_out);
+    return cudaGetLastError();
+}
+
 }  // namespace plx

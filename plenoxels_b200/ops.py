@@ -367,6 +367,23 @@ def avgpool3d_grid(grid, kernel, stride=None):
     return _AvgPool3dGrid.apply(grid, int(kernel), int(stride if stride is not None else kernel))
 
 
+def tv_loss_(grid, tv, grad=None):
+    """tv * tv_loss(grid) (scripts/train.py:44-65, :163-168) as a (1,) device tensor; with `grad` (contiguous, grid-shaped)
+    its gradient is ADDED to it in place — two dense stencil passes instead of ~15 ATen ops and their autograd."""
+    dev = L.require_cuda(grid, grad)
+    if not grid.is_contiguous() or grid.dtype != torch.float32 or grid.dim() != 4 or grid.shape[3] != 4:
+        raise L.PlxError("tv_loss_ needs a contiguous float32 (X,Y,Z,4) grid")
+    if grad is not None and (not grad.is_contiguous() or grad.shape != grid.shape or grad.dtype != torch.float32):
+        raise L.PlxError("grad must be a contiguous float32 tensor of the grid's shape")
+    out = torch.zeros((1,), dtype=torch.float32, device=dev)
+    scratch = torch.zeros((1,), dtype=torch.float64, device=dev)
+    dims = (C.c_int32 * 3)(*[int(s) for s in grid.shape[:3]])
+    with torch.cuda.device(dev):
+        L.check(L.load().plx_tv_loss(grid.data_ptr(), dims, float(tv), L.ptr(grad), scratch.data_ptr(), out.data_ptr(),
+                                     L.stream_ptr(dev)), "plx_tv_loss")
+    return out
+
+
 def composite(samples):
     """`compute_alpha_weighted_pixels` (src/ray_sampling.py:172-192): (..., S, 4) -> (..., 4)."""
     if samples.shape[-1] != 4:

@@ -41,7 +41,7 @@ class VoxelTrainer:
     """
 
     def __init__(self, grid, points_distance, poses, fov, imgs, rays_per_cam, num_samples, delta_step, lr,
-                 mode="nearest", beta=0.0, betas=(0.9, 0.999), eps=1e-8, n_rays_global=None, group=None):
+                 mode="nearest", beta=0.0, betas=(0.9, 0.999), eps=1e-8, n_rays_global=None, group=None, tv=0.0):
         dev = L.require_cuda(grid, poses, imgs)
         self.lib = L.load()
         self.device = dev
@@ -58,6 +58,9 @@ class VoxelTrainer:
         self.rays_per_cam, self.num_samples, self.delta_step = int(rays_per_cam), int(num_samples), float(delta_step)
         self.lr, self.betas, self.eps, self.mode, self.beta = float(lr), betas, float(eps), mode, float(beta)
         self.step_count = 0
+        self.tv = float(tv)                     # weight of tv_loss (scripts/train.py:163-168); its value lands in self.tv_loss
+        self.tv_loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self._tv_scratch = torch.zeros((1,), dtype=torch.float64, device=dev)
         C_ = self.poses.shape[0]
         n = C_ * self.rays_per_cam
         self.n_rays = n
@@ -111,18 +114,26 @@ class VoxelTrainer:
                     "plx_train_step(render)")
         self._args.uv = self.uv.data_ptr()
 
+    def _add_tv(self) -> None:
+        """tv * tv_loss gradient into the (already exchanged) gradient buffer; every replica computes the same term."""
+        dims = (C.c_int32 * 3)(*[int(s) for s in self.grid.shape[:3]])
+        L.check(self.lib.plx_tv_loss(self.grid.data_ptr(), dims, self.tv, self.grad.data_ptr(), self._tv_scratch.data_ptr(),
+                                     self.tv_loss.data_ptr(), L.stream_ptr(self.device)), "plx_tv_loss")
+
     def update_phase(self) -> None:
-        """[gradient exchange] + Adam (+ |grad| accumulation, gradient clear)."""
+        """[gradient exchange] + [TV gradient] + Adam (+ |grad| accumulation, gradient clear)."""
         with torch.cuda.device(self.device):
             if self._distributed():
                 all_reduce_sum_(self.grad, self.group)
+            if self.tv > 0:
+                self._add_tv()
             L.check(self.lib.plx_train_step(C.byref(self._args), L.PLX_STEP_OPTIM, L.stream_ptr(self.device)),
                     "plx_train_step(optim)")
 
     def step(self, uv: torch.Tensor | None = None) -> torch.Tensor:
         """One step with the uv draw already on the device (`uv` (C,R,2) cuda, or the trainer's own `self.uv`).
         Returns the device loss tensor (1,) without synchronising.  With a process group: this rank's partial loss."""
-        if self._distributed():
+        if self._distributed() or self.tv > 0:
             self.render_phase(uv)
             self.update_phase()
             return self.loss

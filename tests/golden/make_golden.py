@@ -17,6 +17,12 @@ REPO = os.path.dirname(os.path.dirname(HERE))
 REF = os.environ.get("PLX_REFERENCE", "/root/reference")
 sys.path.insert(0, REPO)
 sys.path.insert(1, REF)
+# `src.*` must resolve to the REFERENCE here.  The reference's src/ has no __init__.py (a namespace package), so this
+# repo's src/ shim (a regular package) would always win the import; pin the name to the reference directory instead.
+import types  # noqa: E402
+_ref_src = types.ModuleType("src")
+_ref_src.__path__ = [os.path.join(REF, "src")]
+sys.modules["src"] = _ref_src
 
 import src.grid_functions as rgf      # noqa: E402  reference
 import src.ray_sampling as rrs        # noqa: E402  reference
@@ -109,7 +115,21 @@ def make_adam(name):
     print(name)
 
 
+def make_tv(name):
+    """tv_loss value + autograd gradient (scripts/train.py:44-65) on a small non-cubic grid."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_train", os.path.join(REF, "scripts", "train.py"))
+    ref_train = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_train)
+    g = synth.dense_grid(12, seed=21)[:, :11, :9].clone().requires_grad_(True)
+    loss = ref_train.tv_loss(g)
+    loss.backward()
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), grid=g.detach().numpy(), loss=np.float64(loss.item()), grad=g.grad.numpy())
+    print(name, float(loss))
+
+
 if __name__ == "__main__":
+    make_tv("tv_g12")
     make_case("nn_dense_g24", 24, 2, 8, 64, 48, 6.0 / 48, "dense", "nearest", seed=11)
     make_case("nn_ball_g32", 32, 3, 12, 48, 96, 6.0 / 96, "ball", "nearest", seed=12)
     make_case("tri_ball_g24", 24, 2, 8, 48, 64, 6.0 / 64, "ball", "trilinear", seed=13)

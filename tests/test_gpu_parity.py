@@ -313,3 +313,40 @@ def test_average_pool3d_grid_matches_library(plx_lib, G, k, s):
     gerr_ours = float((grid.grad.double() - in64.grad).abs().max()) / scale
     gerr_lib = float((ref_in.grad.double() - in64.grad).abs().max()) / scale
     assert gerr_ours <= 2 * gerr_lib + 1e-6, (gerr_ours, gerr_lib)
+
+
+@pytest.mark.parametrize("shape", [(12, 11, 9), (32, 32, 32), (5, 40, 7)])
+def test_tv_loss_kernel_matches_oracle(plx_lib, shape):
+    """plx_tv_loss (value + gradient accumulated into an existing buffer) vs the oracle (scripts/train.py:44-65)."""
+    torch.manual_seed(sum(shape))
+    grid = (torch.rand(*shape, 4, device="cuda") * 1.4 - 0.2)
+    base = torch.randn(*shape, 4, device="cuda") * 1e-3
+    grad = base.clone()
+    oloss, ograd = po.tv_loss(grid.cpu().numpy())
+    ops.tv_loss_(grid, 0.5, grad)                                           # accumulates into an existing gradient
+    assert rel_err(grad.cpu().numpy(), base.cpu().numpy().astype(np.float64) + 0.5 * ograd) <= TOL
+    tv = 1e-5
+    out = ops.tv_loss_(grid, tv, None)                                      # value only
+    assert abs(float(out) - tv * oloss) <= 1e-5 * tv * oloss
+    g0 = torch.zeros_like(grid)
+    ops.tv_loss_(grid, tv, g0)
+    assert rel_err(g0.cpu().numpy(), tv * ograd) <= TOL
+    const = torch.full((4, 4, 4, 4), 0.5, device="cuda")
+    gz = torch.zeros_like(const)
+    assert float(ops.tv_loss_(const, tv, gz)) == 0.0 and float(gz.abs().max()) == 0.0
+
+
+def test_trainer_with_tv_and_beta_matches_oracle(plx_lib):
+    """train.py's default regularisers (tv=1e-5, beta=5e-3) through VoxelTrainer: gradient = MSE + beta + TV terms."""
+    case = Case(G=24, C=3, H=16, R=64, S=64, delta=6.0 / 64, kind="soft")
+    d = case.cuda()
+    tv, beta = 1e-5, 5e-3
+    tr = VoxelTrainer(d["grid"], case.pd, d["poses"], case.fov, d["imgs"], case.R, case.S, case.delta, lr=0.0075, beta=beta, tv=tv)
+    loss = float(tr.step(d["uv"]))
+    orgba, _, _, _ = case.oracle_forward()
+    oloss, gpix = po.mse_loss(orgba, case.targets)
+    ograd = case.oracle_backward(gpix, beta=beta)
+    tvl, tvg = po.tv_loss(case.grid.numpy())
+    assert abs(loss - oloss) <= TOL * oloss
+    assert abs(float(tr.tv_loss) - tv * tvl) <= 1e-5 * tv * tvl
+    assert rel_err(tr.grad_abs_sum.cpu().numpy(), np.abs(ograd + tv * tvg)) <= TOL

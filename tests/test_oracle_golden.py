@@ -109,3 +109,11 @@ def test_round_half_even_and_bounds_edges():
     grid = np.arange(64 * 64 * 64 * 4, dtype=np.float32).reshape(64, 64, 64, 4)
     vals, _ = po.gather_nearest(ns[4:], grid)
     assert np.array_equal(vals[0], grid[63, 0, 63])
+
+
+def test_oracle_tv_loss_matches_reference():
+    z = load("tv_g12")
+    loss, grad = po.tv_loss(z["grid"])
+    assert abs(loss - float(z["loss"])) <= 1e-6 * float(z["loss"])
+    assert np.abs(grad - z["grad"]).max() <= 1e-6 * np.abs(z["grad"]).max()
+    assert po.tv_loss(np.full((3, 3, 3, 4), 0.25))[1].max() == 0.0        # constant grid: the reference gives NaN, we give 0

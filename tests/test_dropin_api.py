@@ -143,7 +143,10 @@ def test_reference_scripts_import_unmodified_against_this_repo(tmp_path):
     (stubs / "plotly" / "graph_objects.py").write_text("")
     (stubs / "plotly" / "io.py").write_text("")
     (stubs / "plotly" / "express.py").write_text("")
+    (stubs / "plotly" / "graph_objs.py").write_text("")
     code = ("import scripts.train as t, scripts.compare_inference_to_image as c, src.grid_functions as g;"
+            "import scripts.main as m, scripts.visulize_grid as vg, scripts.visulize_camera_and_grid as vc;"
+            "assert m.fit is t.fit and vg.convolve_grid_to_remove_noise is g.convolve_grid_to_remove_noise;"
             "import inspect, sys;"
             "assert g.__file__.startswith(%r), g.__file__;"
             "assert t.__file__.startswith(%r), t.__file__;"

@@ -140,6 +140,26 @@ def fit_body():
                           "ms_per_step": round(ms, 3), "Mrays_per_s": round(C_ * R / ms / 1e3, 2)}))
 
 
+def c2_regularised():
+    """C2 with train.py's default regularisers (tv=1e-5, beta=5e-3; scripts/train.py:227-228) — the secondary C2 case of
+    SURVEY.md §8d: the beta term touches every in-bounds sample (no early termination), TV adds two dense passes."""
+    from plenoxels_b200.trainer import VoxelTrainer
+    sc = synth.make_scene("c2", H=200)
+    uvs = [synth.random_uv(sc.poses.shape[0], sc.rays_per_cam, seed=i).to(dev) for i in range(8)]
+    for tv, beta in ((0.0, 0.0), (0.0, 5e-3), (1e-5, 5e-3)):
+        tr = VoxelTrainer(sc.grid.to(dev), sc.points_distance, sc.poses.to(dev), sc.fov, sc.imgs.to(dev), sc.rays_per_cam,
+                          sc.num_samples, sc.delta_step, lr=sc.lr, beta=beta, tv=tv)
+        i = [0]
+
+        def step():
+            tr.step(uvs[i[0] % 8])
+            i[0] += 1
+
+        ms = timed(step, n=50, warm=5)
+        print(json.dumps({"config": "c2 regularised", "tv": tv, "beta": beta, "ms_per_step": round(ms, 4),
+                          "Mrays_per_s": round(sc.n_rays / ms / 1e3, 1)}))
+
+
 def ref_cuda():
     """The reference's own op sequence (oracle/torch_port.py = scripts/train.py:130-184 restated op for op) on device="cuda":
     stock PyTorch eager on the same B200, the 'existing GPU path' of BASELINE.md §4."""
@@ -155,6 +175,8 @@ def ref_cuda():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c4"]
+    if "c2reg" in which:
+        c2_regularised()
     if "refcuda" in which:
         ref_cuda()
     if "pool" in which:

@@ -210,11 +210,20 @@ def run_gpu_arm(args):
     uv_dev = [u.to(dev) for u in uv_host]
 
     multi = os.environ.get("PLX_MULTI", "peer") if world > 1 else "single"
+    state = {"multi": multi}
 
     def new_trainer():
-        cls = PeerVoxelTrainer if multi == "peer" else VoxelTrainer
-        return cls(sc.grid.to(dev), sc.points_distance, sc.poses.to(dev), sc.fov, imgs_dev, R, S, sc.delta_step,
-                   lr=sc.lr, n_rays_global=n_rays * world)
+        args_ = (sc.grid.to(dev), sc.points_distance, sc.poses.to(dev), sc.fov, imgs_dev, R, S, sc.delta_step)
+        kw = dict(lr=sc.lr, n_rays_global=n_rays * world)
+        if state["multi"] == "peer":
+            try:
+                return PeerVoxelTrainer(*args_, **kw)
+            except Exception as e:          # symmetric memory unavailable on this box: NCCL all-reduce path (all ranks agree:
+                log(f"[bench] peer-memory trainer unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce trainer")
+                ok = torch.zeros(1, device=dev)           # rendezvous failures are collective, so every rank lands here)
+                dist.all_reduce(ok)
+                state["multi"] = "nccl"
+        return VoxelTrainer(*args_, **kw)
 
     imgs_dev = sc.imgs.to(dev)
     tr = new_trainer()
@@ -384,7 +393,7 @@ def run_gpu_arm(args):
                        "parallelism": ("single GPU" if world == 1 else
                                        f"ray-sharded replicas x{world}, " +
                                        ("gradient reduce-scatter + Adam + parameter all-gather fused in one kernel over NVLink peer memory"
-                                        if multi == "peer" else "dense gradient all-reduce (NCCL) + replicated Adam")),
+                                        if state["multi"] == "peer" else "dense gradient all-reduce (NCCL) + replicated Adam")),
                        "distinct_batches": n_batches, "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_rays * 8, "d2h_bytes_per_step": 8,
                     "ms_per_step": 1e3 * e2e_s / K,

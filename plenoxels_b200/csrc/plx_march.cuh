@@ -98,6 +98,24 @@ __device__ __forceinline__ Sample lookup_nearest(const PlxMarch& m, const Geo& g
     return s;
 }
 
+// nearest lookup that only ISSUES the load: returns the linear index (-1 = out of bounds) and the raw, unclamped cell.
+// The caller clamps when it consumes the value, so the load can stay in flight across other work (software pipelining).
+template <bool FAST>
+__device__ __forceinline__ int fetch_nearest(const PlxMarch& m, const Geo& g, const float* __restrict__ grid, const Ray& r,
+                                             bool fast_ray, int k, bool valid, float4& raw) {
+    const float t = __fmul_rn(g.delta, (float)k);
+    float nx, ny, nz;
+    norm3<FAST>(m, g, r, fast_ray, t, nx, ny, nz);
+    const float rx = rintf(nx), ry = rintf(ny), rz = rintf(nz);
+    const bool inb = valid && rx >= 0.f && rx < g.fnx && ry >= 0.f && ry < g.fny && rz >= 0.f && rz < g.fnz;
+    raw = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!inb) return -1;
+    const int ix = (int)rx, iy = (int)ry, iz = (int)rz;
+    const int lin = (ix * g.ny + iy) * g.nz + iz;
+    raw = cell_at<FAST>(m, g, grid, ix, iy, iz, lin);
+    return lin;
+}
+
 // ---- trilinear: SURVEY.md §8a row T ---------------------------------------------------------------------------
 struct TriGeom {
     int lo[3], hi[3];     // floor / wrapped ceil index per axis

@@ -84,18 +84,22 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
         bool opaque = false;                 // segment 1 ended on an alpha == 1 sample at (zl, zj)
         int zl = 0, zj = 0;
         int it = 0;
+        // software pipeline: the cells of iteration it+1 are requested before iteration it is composited, so the gather
+        // latency (L2 / HBM) overlaps the scans instead of stalling the warp at the first use
+        float4 rawn[SPL];
+        int linn[SPL];
+        auto fetch = [&](int i) {
+            const int kb = k0 + i * W + lane * SPL;
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) linn[j] = fetch_nearest<FAST>(m, g, a.grid, r, fast_ray, kb + j, kb + j <= k1, rawn[j]);
+        };
+        if (n_it > 0) fetch(0);
         for (; it < n_it; ++it) {
-            const int kb = k0 + it * W + lane * SPL;
             float4 c[SPL];
             int lin[SPL];
 #pragma unroll
-            for (int j = 0; j < SPL; ++j) {
-                float t;
-                TriGeom tg;
-                const Sample s = lookup<PLX_NEAREST, FAST>(m, g, a.grid, r, fast_ray, kb + j, kb + j <= k1, true, t, tg);
-                c[j] = s.c;
-                lin[j] = s.lin;
-            }
+            for (int j = 0; j < SPL; ++j) { c[j] = g.clamp ? clamp4(rawn[j]) : rawn[j]; lin[j] = linn[j]; }
+            if (it + 1 < n_it) fetch(it + 1);
             if (SPL == 1) lc[it * W + lane] = lin[0];
             else *reinterpret_cast<int2*>(lc + it * W + lane * 2) = make_int2(lin[0], lin[SPL - 1]);
             if (lane == 0) tcs[it] = T;
@@ -130,15 +134,11 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
         }
         const int n_fwd = it;                // iterations of segment 1 (their indices are cached)
         if (opaque) {                        // keep compositing behind k* until that segment saturates or the range ends
-            for (int i2 = n_fwd; i2 < n_it && T2 != 0.f; ++i2) {
-                const int kb = k0 + i2 * W + lane * SPL;
+            for (int i2 = n_fwd; i2 < n_it && T2 != 0.f; ++i2) {          // iteration n_fwd is already in flight (rawn)
                 float4 c[SPL];
 #pragma unroll
-                for (int j = 0; j < SPL; ++j) {
-                    float t;
-                    TriGeom tg;
-                    c[j] = lookup<PLX_NEAREST, FAST>(m, g, a.grid, r, fast_ray, kb + j, kb + j <= k1, true, t, tg).c;
-                }
+                for (int j = 0; j < SPL; ++j) c[j] = g.clamp ? clamp4(rawn[j]) : rawn[j];
+                if (i2 + 1 < n_it) fetch(i2 + 1);
                 composite_iter<SPL>(c, lane, T2, acc2);
             }
         }
@@ -159,20 +159,29 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
         const bool any_grad = gr.x != 0.f || gr.y != 0.f || gr.z != 0.f || gr.w != 0.f || full;
         float carry = 0.f;                   // S behind the last visited sample (0: end of ray, or irrelevant behind k*)
         __syncwarp();
+        auto refetch = [&](int i) {          // indices back from shared memory, cells requested (L1 / L2 hits mostly)
+            if (SPL == 1) linn[0] = lc[i * W + lane];
+            else { const int2 p = *reinterpret_cast<const int2*>(lc + i * W + lane * 2); linn[0] = p.x; linn[SPL - 1] = p.y; }
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                rawn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (linn[j] >= 0) rawn[j] = FAST ? ldg_hint(reinterpret_cast<const float4*>(a.grid) + linn[j], g.pol)
+                                                 : cell_at<false>(m, g, a.grid, linn[j] / (g.ny * g.nz), (linn[j] / g.nz) % g.ny, linn[j] % g.nz, linn[j]);
+            }
+        };
+        if (n_fwd > 0 && any_grad) refetch(n_fwd - 1);
         for (int ib = n_fwd - 1; ib >= 0 && any_grad; --ib) {
             int lin[SPL];
-            if (SPL == 1) lin[0] = lc[ib * W + lane];
-            else { const int2 p = *reinterpret_cast<const int2*>(lc + ib * W + lane * 2); lin[0] = p.x; lin[SPL - 1] = p.y; }
             float4 raw[SPL], c[SPL];
             float v[SPL];
 #pragma unroll
             for (int j = 0; j < SPL; ++j) {
-                raw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lin[j] >= 0) raw[j] = FAST ? ldg_hint(reinterpret_cast<const float4*>(a.grid) + lin[j], g.pol)
-                                               : cell_at<false>(m, g, a.grid, lin[j] / (g.ny * g.nz), (lin[j] / g.nz) % g.ny, lin[j] % g.nz, lin[j]);
+                lin[j] = linn[j];
+                raw[j] = rawn[j];
                 c[j] = g.clamp ? clamp4(raw[j]) : raw[j];
                 v[j] = fmaf(c[j].x, gr.x, fmaf(c[j].y, gr.y, fmaf(c[j].z, gr.z, gr.w)));      // c_k . g_rgb + g_A
             }
+            if (ib > 0) refetch(ib - 1);     // next iteration's cells in flight during this iteration's scans
             bool any_alpha = false;
 #pragma unroll
             for (int j = 0; j < SPL; ++j) any_alpha = any_alpha || c[j].w != 0.f;
@@ -266,7 +275,7 @@ cudaError_t launch_render_train(const PlxRenderTrain& a_in, cudaStream_t st) {
     a.march.flags = (a.march.flags & 0xffffu) | l2_keep_flags(a.march);
     static const int spl_env = env_int("PLX_TRAIN_SPL", 0, 1, 2);
     static const int wpb_env = env_int("PLX_TRAIN_WPB", 4, 1, 4);
-    static const int minb = env_int("PLX_TRAIN_MINB", 8, 8, 12);
+    static const int minb = env_int("PLX_TRAIN_MINB", 8, 6, 8);
     const int spl = spl_env ? spl_env : (a.march.num_samples >= 128 ? 2 : 1);
     int wpb = wpb_env;
     while (wpb > 1 && render_train_smem(a.march.num_samples, spl, wpb) > 200 * 1024) wpb >>= 1;
@@ -286,8 +295,8 @@ cudaError_t launch_render_train(const PlxRenderTrain& a_in, cudaStream_t st) {
         k_render_train<FASTP, SPLV, MB><<<blocks, wpb * 32, smem, st>>>(a, lin_words, lin_words + ((n_it_max + 3) & ~3));   \
     } while (0)
     if (!fast) { if (spl == 2) PLX_TRAIN(false, 2, 8); else PLX_TRAIN(false, 1, 8); }
-    else if (spl == 2) { if (minb >= 12) PLX_TRAIN(true, 2, 12); else if (minb >= 10) PLX_TRAIN(true, 2, 10); else PLX_TRAIN(true, 2, 8); }
-    else               { if (minb >= 12) PLX_TRAIN(true, 1, 12); else if (minb >= 10) PLX_TRAIN(true, 1, 10); else PLX_TRAIN(true, 1, 8); }
+    else if (spl == 2) { if (minb <= 6) PLX_TRAIN(true, 2, 6); else if (minb == 7) PLX_TRAIN(true, 2, 7); else PLX_TRAIN(true, 2, 8); }
+    else               { if (minb <= 6) PLX_TRAIN(true, 1, 6); else if (minb == 7) PLX_TRAIN(true, 1, 7); else PLX_TRAIN(true, 1, 8); }
 #undef PLX_TRAIN
     return cudaGetLastError();
 }

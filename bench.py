@@ -329,6 +329,9 @@ def run_gpu_arm(args):
             u = uv_dev[(W + i) % n_batches]
             ev = evs[i]
             tr3.loss.zero_()
+            if tr3._dynamic:
+                tr3._work_counter.zero_()
+                trn.work_counter = tr3._work_counter.data_ptr()
             ev[0].record()
             if fused:
                 trn.gen.uv = u.data_ptr()

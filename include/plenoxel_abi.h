@@ -153,6 +153,8 @@ typedef struct PlxRenderTrain {
     float* rgba;
     float* loss;
     float grad_scale, loss_scale, beta_over_m;
+    int32_t* work_counter;   /* optional: one device int32 that is 0 at launch; rays are then claimed dynamically by the warps
+                                of a one-wave grid (better balance for rays of unequal length).  NULL = static assignment */
 } PlxRenderTrain;
 int plx_render_train(const PlxRenderTrain* args, void* stream);
 
@@ -195,6 +197,7 @@ typedef struct PlxAdamPeer {
     const float* loss_src;
     float* loss_clear;
     void* result_host;
+    int32_t* counter_clear;  /* optional: the march's work counter, reset to 0 for the next step */
 } PlxAdamPeer;
 int plx_adam_step_peer(const PlxAdamPeer* args, void* stream);
 
@@ -303,6 +306,9 @@ typedef struct PlxTrainStep {
     float* dirs; float* targets; float* rgba; float* grad_rgba; float* tcarry;
     /* result */
     float* loss;
+    /* optional dynamic work distribution for the fused march (see PlxRenderTrain.work_counter): one device int32, zero
+     * before the first step; the optimiser phase resets it for the next step */
+    int32_t* work_counter;
 } PlxTrainStep;
 int plx_train_step(const PlxTrainStep* args, int32_t phase, void* stream);
 

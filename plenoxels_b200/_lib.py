@@ -56,7 +56,7 @@ class PlxRayGen(C.Structure):
 class PlxRenderTrain(C.Structure):
     _fields_ = [("march", PlxMarch), ("rays", PlxRays), ("targets", c_void), ("gen", PlxRayGen), ("grid", c_void),
                 ("grad_grid", c_void), ("rgba", c_void), ("loss", c_void), ("grad_scale", C.c_float),
-                ("loss_scale", C.c_float), ("beta_over_m", C.c_float)]
+                ("loss_scale", C.c_float), ("beta_over_m", C.c_float), ("work_counter", c_void)]
 
 
 PLX_MAX_PEERS = 8
@@ -67,7 +67,7 @@ class PlxAdamPeer(C.Structure):
                 ("grads", c_void * PLX_MAX_PEERS), ("exp_avg", c_void), ("exp_avg_sq", c_void), ("grad_abs_sum", c_void),
                 ("begin", C.c_int64), ("end", C.c_int64), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
                 ("eps", C.c_double), ("step", C.c_int64), ("grid_mc", c_void), ("grad_mc", c_void),
-                ("loss_src", c_void), ("loss_clear", c_void), ("result_host", c_void)]
+                ("loss_src", c_void), ("loss_clear", c_void), ("result_host", c_void), ("counter_clear", c_void)]
 
 
 class PlxTrainStep(C.Structure):
@@ -82,7 +82,7 @@ class PlxTrainStep(C.Structure):
                 ("step", C.c_int64),
                 ("beta_over_m", C.c_float),
                 ("dirs", c_void), ("targets", c_void), ("rgba", c_void), ("grad_rgba", c_void), ("tcarry", c_void),
-                ("loss", c_void)]
+                ("loss", c_void), ("work_counter", c_void)]
 
 
 # name -> (restype, argtypes); every symbol include/plenoxel_abi.h declares

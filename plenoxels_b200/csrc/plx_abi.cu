@@ -126,7 +126,7 @@ int plx_adam_step(float* p, float* g, float* m, float* v, float* gabs, int64_t n
     if (n > 0 && (!p || !g || !m || !v)) return fail(PLX_E_NULL, "p/g/m/v is NULL");
     if (step < 1) return fail(PLX_E_SHAPE, "step counts from 1");
     return cuda_result(plx::launch_adam(p, g, m, v, gabs, n, adam_scalars(lr, beta1, beta2, eps, step), zero_grad != 0,
-                                        plx::StepTail{nullptr, nullptr, nullptr, 0}, (cudaStream_t)stream), "plx_adam_step");
+                                        plx::StepTail{nullptr, nullptr, nullptr, 0, nullptr}, (cudaStream_t)stream), "plx_adam_step");
 }
 
 int plx_adam_step_peer(const PlxAdamPeer* a, void* stream) {
@@ -142,7 +142,7 @@ int plx_adam_step_peer(const PlxAdamPeer* a, void* stream) {
     }
     if ((uintptr_t)a->exp_avg % 16 || (uintptr_t)a->exp_avg_sq % 16 || (uintptr_t)a->grad_abs_sum % 16)
         return fail(PLX_E_ALIGN, "optimizer state must be 16-byte aligned");
-    const plx::StepTail tail{a->loss_src, a->loss_clear, (float*)a->result_host, (int32_t)a->step};
+    const plx::StepTail tail{a->loss_src, a->loss_clear, (float*)a->result_host, (int32_t)a->step, a->counter_clear};
     return cuda_result(plx::launch_adam_peer(*a, adam_scalars(a->lr, a->beta1, a->beta2, a->eps, a->step), tail, (cudaStream_t)stream),
                        "plx_adam_step_peer");
 }
@@ -311,6 +311,7 @@ static int train_step_impl(const PlxTrainStep* a, const float* uv, void* result_
         t.gen.poses = a->poses; t.gen.fov = a->fov; t.gen.uv = uv; t.gen.rays_per_cam = a->rays_per_cam;
         t.grid = a->grid; t.grad_grid = a->grad; t.rgba = a->rgba; t.loss = loss_now;
         t.grad_scale = grad_scale; t.loss_scale = loss_scale; t.beta_over_m = a->beta_over_m;
+        t.work_counter = a->work_counter;
         if (allow_fused && a->img_h == a->img_w && plx::render_train_supported(t)) {
             if ((rc = plx_render_train(&t, stream)) != PLX_OK) return rc;
         } else {
@@ -343,7 +344,7 @@ static int train_step_impl(const PlxTrainStep* a, const float* uv, void* result_
         const int64_t n = (int64_t)a->march.nx * a->march.ny * a->march.nz * 4;
         if (n > 0 && (!a->grid || !a->grad || !a->exp_avg || !a->exp_avg_sq)) return fail(PLX_E_NULL, "train step: optimiser state is NULL");
         if (a->step < 1) return fail(PLX_E_SHAPE, "step counts from 1");
-        const plx::StepTail tail{loss_now, loss_next, (float*)result_host, (int32_t)a->step};
+        const plx::StepTail tail{loss_now, loss_next, (float*)result_host, (int32_t)a->step, a->work_counter};
         return cuda_result(plx::launch_adam(a->grid, a->grad, a->exp_avg, a->exp_avg_sq, a->grad_abs_sum, n,
                                             adam_scalars(a->lr, a->beta1, a->beta2, a->eps, a->step), true, tail,
                                             (cudaStream_t)stream), "plx_train_step(optim)");

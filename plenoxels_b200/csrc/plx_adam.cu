@@ -32,6 +32,7 @@ __device__ __forceinline__ void step_tail(const StepTail& t) {
             *reinterpret_cast<volatile int32_t*>(t.dst_host + 1) = t.step;
         }
         if (t.clear) *t.clear = 0.f;
+        if (t.counter_clear) *t.counter_clear = 0;
     }
 }
 
@@ -348,7 +349,7 @@ cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int
 #undef PLX_ADAM_V
         if (e != cudaSuccess) return e;
     }
-    if (n4 == 0 && (tail.src || tail.clear)) k_step_tail_only<<<1, 32, 0, st>>>(tail);
+    if (n4 == 0 && (tail.src || tail.clear || tail.counter_clear)) k_step_tail_only<<<1, 32, 0, st>>>(tail);
     if (n4 * 4 < n) {
         const int64_t rem = n - n4 * 4;
         int64_t want = (rem + threads - 1) / threads;

@@ -31,6 +31,7 @@ struct StepTail {
     float* clear;
     float* dst_host;
     int32_t step;
+    int32_t* counter_clear;  // the fused march's work counter, reset for the next step
 };
 cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int64_t n, const AdamScalars& s,
                         bool zero_grad, const StepTail& tail, cudaStream_t st);

@@ -47,15 +47,28 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
     __shared__ int s_done;
     constexpr int W = 32 * SPL;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int64_t ray = (int64_t)blockIdx.x * wpb + wib;
     const PlxMarch& m = a.march;
     if (threadIdx.x == 0) { s_loss = 0.f; s_done = 0; }
     __syncthreads();                         // every warp arrives here at once: free
     float ray_loss = 0.f;
-    if (ray < a.rays.n_rays) {
-        int* lc = s_dyn + wib * warp_words;
-        float* tcs = reinterpret_cast<float*>(lc + lin_words);
-        const Geo g = make_geo(m);
+    int* lc = s_dyn + wib * warp_words;
+    float* tcs = reinterpret_cast<float*>(lc + lin_words);
+    const Geo g = make_geo(m);
+    // work distribution: with a `work_counter` the grid is one resident wave and every warp claims its next ray from a
+    // global counter as soon as it is free (rays differ in length, so warps of a block do not wait for each other and
+    // there is no partial last wave); without one, ray = block * warps + warp.
+    int64_t ray = (int64_t)blockIdx.x * wpb + wib;
+    const int64_t static_stride = (int64_t)gridDim.x * wpb;
+    for (bool first = true;; first = false) {
+        if (a.work_counter) {
+            int claimed = 0;
+            if (lane == 0) claimed = atomicAdd(a.work_counter, 1);
+            ray = __shfl_sync(FULL, claimed, 0);
+        } else if (!first) {
+            ray += static_stride;
+        }
+        if (ray >= a.rays.n_rays) break;
+        float this_loss = 0.f;
         // ---- this ray: precomputed, or generated here from (pose, uv) — src/ray_sampling.py:212-264
         Ray r;
         float4 tgt;
@@ -147,7 +160,7 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
         // ---------------------------------------------------------------------------------------- loss, scripts/train.py:156
         const float er = acc.x - tgt.x, eg = acc.y - tgt.y, eb = acc.z - tgt.z, ea = acc.w - tgt.w;
         const float4 gr = make_float4(er * a.grad_scale, eg * a.grad_scale, eb * a.grad_scale, ea * a.grad_scale);
-        ray_loss = (er * er + eg * eg + eb * eb + ea * ea) * a.loss_scale;
+        this_loss = (er * er + eg * eg + eb * eb + ea * ea) * a.loss_scale;
         if (lane == 0 && a.rgba) reinterpret_cast<float4*>(a.rgba)[ray] = acc;
         float s_star = 0.f;                  // colour behind k*, dotted with the pixel gradient
         if (opaque) {
@@ -238,6 +251,8 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
                         red_add_v4_hint(a.grad_grid + (int64_t)lin[j] * 4, d[j].x, d[j].y, d[j].z, d[j].w, g.pol_grad);
             }
         }
+        ray_loss += this_loss;
+        __syncwarp();                        // the per-warp shared-memory cache is reused by the next ray
     }
     // ---- loss: shared-memory partial per block, the last warp to finish adds it to the global accumulator
     if (a.loss && lane == 0) {
@@ -283,7 +298,15 @@ cudaError_t launch_render_train(const PlxRenderTrain& a_in, cudaStream_t st) {
     const int W = 32 * spl;
     const int n_it_max = (a.march.num_samples + W - 1) / W + 1;
     const int lin_words = n_it_max * W;
-    const unsigned blocks = (unsigned)((a.rays.n_rays + wpb - 1) / wpb);
+    unsigned blocks = (unsigned)((a.rays.n_rays + wpb - 1) / wpb);
+    if (a.work_counter) {                    // one resident wave: SMs x blocks per SM of this instantiation (8 at 128 threads)
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        static const int per_sm = env_int("PLX_TRAIN_BLOCKS_PER_SM", 8, 1, 16);
+        const unsigned wave = (unsigned)(sms * per_sm);
+        if (blocks > wave) blocks = wave;
+    }
     const bool fast = fast_ok(a.march, a.grid);
 #define PLX_TRAIN(FASTP, SPLV, MB)                                                                                              \
     do {                                                                                                                    \

@@ -75,6 +75,10 @@ class VoxelTrainer:
         self.tcarry = torch.empty((n, self.lib.plx_num_chunks(self.num_samples)), dtype=torch.float32, device=dev)
         # two loss slots: step s accumulates into slot s & 1, the optimiser kernel clears the other one (plenoxel_abi.h)
         self._loss2 = torch.zeros((2,), dtype=torch.float32, device=dev)
+        # work counter of the fused march (rays are claimed dynamically by the warps of a one-wave grid); the optimiser
+        # kernel resets it every step.  Opt-in (PLX_TRAIN_DYNAMIC=1): the hardware block scheduler balanced C2 better.
+        self._work_counter = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self._dynamic = os.environ.get("PLX_TRAIN_DYNAMIC", "0") == "1"      # measured slower on C2 (53.7 vs 47.7 us): off
         self.loss = self._loss2[1:2]                                   # view of the slot of the latest step
         # pinned { float loss; int32 step } the optimiser kernel publishes to on the host path
         self.result_host = torch.zeros((2,), dtype=torch.float32).pin_memory()
@@ -99,6 +103,7 @@ class VoxelTrainer:
         a.beta_over_m = self.beta / m_global if (self.beta and m_global) else 0.0
         a.dirs, a.targets, a.rgba = self.dirs.data_ptr(), self.targets.data_ptr(), self.rgba.data_ptr()
         a.grad_rgba, a.tcarry, a.loss = self.grad_rgba.data_ptr(), self.tcarry.data_ptr(), self._loss2.data_ptr()
+        a.work_counter = self._work_counter.data_ptr() if self._dynamic else None
         return a
 
     # ---------------------------------------------------------------------------------------------------------
@@ -210,6 +215,7 @@ class VoxelTrainer:
                 self.step_count = int(opt["step"])
             self.grad.zero_()
             self._loss2.zero_()
+            self._work_counter.zero_()
 
 
 def slab_range(n_cells: int, rank: int, world: int):
@@ -315,6 +321,7 @@ class PeerVoxelTrainer(VoxelTrainer):
         peer.loss_src = self._loss2.data_ptr() + 4 * s
         peer.loss_clear = self._loss2.data_ptr() + 4 * (1 - s)
         peer.result_host = result_host
+        peer.counter_clear = self._work_counter.data_ptr() if self._dynamic else None
         h = self._h_grads[b]
         self._epoch += 1
         self._barrier(h, 0, st)                               # every rank's partial gradient is complete

@@ -249,9 +249,12 @@ cudaError_t launch_render_fwd(const PlxRenderFwd& a_in, cudaStream_t st) {
     const bool dbg = a.count || a.sample_index || (a.march.flags & PLX_NO_EARLY_STOP);
     if ((a.march.flags & PLX_COHERENT_RAYS) && !dbg && !a.tcarry && !a.targets) {
         const unsigned pblocks = (unsigned)((a.rays.n_rays + 127) / 128);
+        static const int unr = warps_per_block("PLX_PACKET_UNROLL", 4);     // samples looked up before compositing; measured on C4: 4 -> 0.85 ms, 6 -> 0.88, 8 -> 1.01
         if (a.march.mode == PLX_NEAREST) {
-            if (fast) k_render_fwd_packet<PLX_NEAREST, true, 4><<<pblocks, 128, 0, st>>>(a);
-            else      k_render_fwd_packet<PLX_NEAREST, false, 4><<<pblocks, 128, 0, st>>>(a);
+            if (!fast)         k_render_fwd_packet<PLX_NEAREST, false, 4><<<pblocks, 128, 0, st>>>(a);
+            else if (unr >= 8) k_render_fwd_packet<PLX_NEAREST, true, 8><<<pblocks, 128, 0, st>>>(a);
+            else if (unr >= 6) k_render_fwd_packet<PLX_NEAREST, true, 6><<<pblocks, 128, 0, st>>>(a);
+            else               k_render_fwd_packet<PLX_NEAREST, true, 4><<<pblocks, 128, 0, st>>>(a);
         } else {
             if (fast) k_render_fwd_packet<PLX_TRILINEAR, true, 1><<<pblocks, 128, 0, st>>>(a);
             else      k_render_fwd_packet<PLX_TRILINEAR, false, 1><<<pblocks, 128, 0, st>>>(a);

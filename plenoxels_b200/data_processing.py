@@ -1,48 +1,53 @@
-"""Drop-in for the reference's `src/data_processing.py` (NeRF-synthetic loader; host I/O, off the hot path)."""
+"""Drop-in for the reference's `src/data_processing.py`: the NeRF-synthetic loader (host I/O, runs once, off the hot path).
+
+A dataset is a `transforms_*.json` (one `camera_angle_x`, a list of frames with `file_path`, `rotation` and a 4x4
+camera-to-world `transform_matrix`) next to a folder of RGBA PNGs named after the last component of each `file_path`.
+"""
 from __future__ import annotations
 
 import json
+from pathlib import Path
 
 import numpy as np
 import torch
 
 
+def read_data(data_path):
+    """Parsed transforms json — src/data_processing.py:32-35."""
+    return json.loads(Path(data_path).read_text())
+
+
 def get_data_from_index(data, index):
-    """(transform_matrix (4,4), rotation, file_path, camera_angle_x) of frame `index` — src/data_processing.py:7-15."""
+    """(pose (4,4) fp32, rotation, file_path, camera_angle_x) of one frame — src/data_processing.py:7-15."""
     frame = data["frames"][index]
-    return torch.tensor(frame["transform_matrix"]), frame["rotation"], frame["file_path"], data["camera_angle_x"]
+    pose = torch.tensor(frame["transform_matrix"])
+    return pose, frame["rotation"], frame["file_path"], data["camera_angle_x"]
 
 
 def load_data(data):
-    """(poses (C,4,4), file_paths, camera_angle_x) — src/data_processing.py:18-29."""
-    poses, paths, fov = [], [], 0.0
-    for i in range(len(data["frames"])):
-        pose, _, path, fov = get_data_from_index(data, i)
-        poses.append(pose.unsqueeze(0))
-        paths.append(path)
-    return torch.cat(poses, 0), paths, fov
+    """(poses (C,4,4), file paths, camera_angle_x) — src/data_processing.py:18-29 (0.0 for an empty frame list)."""
+    frames = data["frames"]
+    if not frames:
+        return torch.cat([], 0), [], 0.0
+    poses = torch.stack([torch.tensor(f["transform_matrix"]) for f in frames], 0)
+    return poses, [f["file_path"] for f in frames], data["camera_angle_x"]
 
 
-def read_data(data_path):
-    """src/data_processing.py:32-35."""
-    with open(data_path, "r") as f:
-        return json.load(f)
-
-
-def _load_images(paths):
+def _png_stack(folder, frames) -> torch.Tensor:
+    """(C,H,W,4) fp32 in [0,1] from `<folder>/<basename of file_path>.png`."""
     from PIL import Image
-    imgs = np.array([np.array(Image.open(p)) for p in paths])
-    return torch.tensor(imgs, dtype=torch.float) / 255
-
-
-def load_image_data(data_folder, object_folder, split="train"):
-    """src/data_processing.py:38-48."""
-    data = read_data(f"{data_folder}/{object_folder}/transforms_{split}.json")
-    stem = f"{data_folder}/{object_folder}/{split}"
-    return data, _load_images([f'{stem}/{fr["file_path"].split("/")[-1]}.png' for fr in data["frames"]])
+    names = [Path(folder) / (f["file_path"].split("/")[-1] + ".png") for f in frames]
+    pixels = np.stack([np.asarray(Image.open(n)) for n in names], 0)
+    return torch.tensor(pixels, dtype=torch.float) / 255
 
 
 def load_image_data_from_path(path, transformpath):
-    """(transforms dict, imgs (C,H,W,4) fp32 in [0,1]) — src/data_processing.py:51-60."""
+    """(transforms dict, imgs (C,H,W,4)) — src/data_processing.py:51-60."""
     data = read_data(transformpath)
-    return data, _load_images([f'{path}/{fr["file_path"].split("/")[-1]}.png' for fr in data["frames"]])
+    return data, _png_stack(path, data["frames"])
+
+
+def load_image_data(data_folder, object_folder, split="train"):
+    """Same, addressed as <data_folder>/<object_folder>/{transforms_<split>.json, <split>/} — src/data_processing.py:38-48."""
+    root = Path(data_folder) / object_folder
+    return load_image_data_from_path(root / split, root / f"transforms_{split}.json")

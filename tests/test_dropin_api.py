@@ -201,3 +201,35 @@ def test_lazy_bridge_fuses_and_falls_back(plx_lib, monkeypatch):
     assert float((results["lazy"][0] - results["eager"][0]).abs().max()) <= 2e-6
     assert abs(results["lazy"][1] - results["eager"][1]) <= 1e-6 * abs(results["eager"][1])
     assert float((results["lazy"][2] - results["eager"][2]).abs().max()) <= 2e-6 * float(results["eager"][2].abs().max())
+
+
+def test_dataset_loader_roundtrip(tmp_path):
+    """load_image_data_from_path / load_data (src/data_processing.py:18-60) on a synthetic NeRF-format dataset; compared with
+    the reference's loader when the reference tree is present."""
+    import json
+    import os
+    from PIL import Image
+    import src.data_processing as dp
+    (tmp_path / "train").mkdir()
+    poses = synth.lookat_poses(3)
+    rng = np.random.default_rng(0)
+    frames, pix = [], []
+    for i in range(3):
+        a = (rng.random((8, 8, 4)) * 255).astype(np.uint8)
+        pix.append(a)
+        Image.fromarray(a, "RGBA").save(tmp_path / "train" / f"r_{i}.png")
+        frames.append({"file_path": f"./train/r_{i}", "rotation": 0.1, "transform_matrix": poses[i].tolist()})
+    (tmp_path / "transforms_train.json").write_text(json.dumps({"camera_angle_x": 0.69, "frames": frames}))
+    data, imgs = dp.load_image_data_from_path(str(tmp_path / "train"), str(tmp_path / "transforms_train.json"))
+    T, paths, fov = dp.load_data(data)
+    assert imgs.shape == (3, 8, 8, 4) and imgs.dtype == torch.float32
+    assert torch.equal(imgs, torch.tensor(np.stack(pix), dtype=torch.float) / 255)
+    assert torch.equal(T, poses) and fov == 0.69 and paths == [f["file_path"] for f in frames]
+    if os.path.isdir(REFERENCE):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_dp", os.path.join(REFERENCE, "src", "data_processing.py"))
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        rdata, rimgs = ref.load_image_data_from_path(str(tmp_path / "train"), str(tmp_path / "transforms_train.json"))
+        rT, rpaths, rfov = ref.load_data(rdata)
+        assert torch.equal(imgs, rimgs) and torch.equal(T, rT) and paths == rpaths and fov == rfov

@@ -362,6 +362,23 @@ class _AvgPool3dGrid(torch.autograd.Function):
         return gin, None, None
 
 
+def avgpool3d_grid_backward_into(grad_out, dims, kernel, stride, grad_in):
+    """Autograd of `avgpool3d_grid` written straight into an existing full-resolution gradient buffer (overwritten)."""
+    dev = L.require_cuda(grad_out, grad_in)
+    X, Y, Z = (int(d) for d in dims[:3])
+    O = [(d - kernel) // stride + 1 for d in (X, Y, Z)]
+    go = grad_out.contiguous().float()
+    if tuple(go.shape) != (O[0], O[1], O[2], 4) or tuple(grad_in.shape) != (X, Y, Z, 4) or not grad_in.is_contiguous():
+        raise L.PlxError("avgpool3d_grid_backward_into: shape mismatch")
+    t1 = torch.empty((X * Y * O[2] * 4,), dtype=torch.float32, device=dev)
+    t2 = torch.empty((X * O[1] * O[2] * 4,), dtype=torch.float32, device=dev)
+    cd = (C.c_int32 * 3)(X, Y, Z)
+    with torch.cuda.device(dev):
+        L.check(L.load().plx_avgpool3d_bwd(go.data_ptr(), cd, int(kernel), int(stride), t2.data_ptr(), t1.data_ptr(),
+                                           grad_in.data_ptr(), L.stream_ptr(dev)), "plx_avgpool3d_bwd")
+    return grad_in
+
+
 def avgpool3d_grid(grid, kernel, stride=None):
     """`average_pool3d_grid` (src/grid_functions.py:173-181): cubic window, stride (default = window), no padding."""
     return _AvgPool3dGrid.apply(grid, int(kernel), int(stride if stride is not None else kernel))

@@ -233,3 +233,87 @@ def test_dataset_loader_roundtrip(tmp_path):
         rdata, rimgs = ref.load_image_data_from_path(str(tmp_path / "train"), str(tmp_path / "transforms_train.json"))
         rT, rpaths, rfov = ref.load_data(rdata)
         assert torch.equal(imgs, rimgs) and torch.equal(T, rT) and paths == rpaths and fov == rfov
+
+
+@pytest.mark.gpu
+def test_fused_fit_with_progressive_growing_matches_reference_port(plx_lib, monkeypatch):
+    """plenoxels_b200.fit.GridFitter (pooling -> fused march with beta -> TV -> pooling backward -> Adam) against the
+    reference's loop body with the same schedule restated on torch-CPU (scripts/train.py:104-184): losses, gradients and the
+    grid after 12 steps that cross two pooling windows and the full-resolution regime."""
+    from plenoxels_b200.fit import GridFitter, receptive_field_at
+    G, C, H, R, S = 32, 3, 16, 48, 40
+    pd, delta, lr, tv, beta = synth.GRID_EXTENT / G, 6.0 / S, 0.0075, 1e-5, 5e-3
+    schedule = [9, 5]
+    poses, imgs = synth.lookat_poses(C), synth.random_images(C, H, H)
+    init = synth.soft_grid(G)                      # a zero grid would make tv_loss's gradient 0/0 in the reference
+    ft = GridFitter([G, G, G], pd, poses, synth.CAMERA_ANGLE_X, imgs, R, S, delta, lr, tv=tv, beta=beta, schedule=schedule,
+                    device="cuda:0")
+    ft.grid.copy_(init.cuda())
+    ref_grid = init.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref_grid], lr=lr)
+    centres_full = tp.cell_centres((G, G, G), pd)
+    eps = 1e-4
+    for i in range(12):
+        uv = synth.random_uv(C, R, seed=300 + i)
+        monkeypatch.setattr(torch, "rand", lambda *a, **k: uv.clone().to(k.get("device", "cpu")))
+        mse, tvl = ft.step(i)
+        monkeypatch.undo()
+        gpu_grad = ft.grad_abs_sum.clone()
+        # ---- reference loop body on the CPU
+        rf = receptive_field_at(i, schedule)
+        if rf > 1:
+            stride, start = max(1, rf // 4), int(rf / 2)
+            cells = torch.nn.functional.avg_pool3d(ref_grid.permute(3, 0, 1, 2).unsqueeze(0), (rf,) * 3, stride=stride).squeeze().permute(1, 2, 3, 0)
+            centres = centres_full[start::stride, start::stride, start::stride].reshape(-1, 3)
+            cur_pd = pd * stride
+        else:
+            cells, centres, cur_pd = ref_grid, centres_full.reshape(-1, 3), pd
+        d_ref, t_ref = tp.rays_from_uv(imgs, poses, synth.CAMERA_ANGLE_X, uv.clone())
+        pos = tp.place_samples(poses[:, :3, 3], d_ref, R, S, delta)
+        v_ref, m_ref = tp.nearest_lookup((pos - centres.min(0)[0]) / cur_pd, cells.clip(0, 1))
+        nearest = (v_ref * m_ref.unsqueeze(-1)).reshape(C, R, S, 4)
+        pix = tp.composite(nearest).reshape(-1, 4)
+        mse_ref = torch.nn.functional.mse_loss(pix, t_ref)
+        gx = cells[:, :-1] - cells[:, 1:]
+        gy = cells[:, :, :-1] - cells[:, :, 1:]
+        gz = cells[:-1] - cells[1:]
+        tv_ref = tv * torch.sqrt(gx.pow(2).sum() + gy.pow(2).sum() + gz.pow(2).sum())            # scripts/train.py:44-65
+        a = nearest[:, :, :, -1]
+        beta_ref = beta * (torch.log(a + eps) - torch.log(1 - a + eps)).mean()                    # :170-177
+        opt.zero_grad()
+        (mse_ref + tv_ref + beta_ref).backward()
+        assert abs(float(mse) - float(mse_ref)) <= 2e-5 * abs(float(mse_ref)), f"step {i}"
+        assert abs(float(tvl) - float(tv_ref)) <= 2e-5 * abs(float(tv_ref)), f"step {i}"
+        if i == 0:
+            g0 = ref_grid.grad.abs()
+            assert float((gpu_grad.cpu() - g0).abs().max()) <= 1e-5 * float(g0.max())
+        opt.step()
+    diff = (ft.grid.cpu() - ref_grid.detach()).abs()
+    assert float(torch.quantile(diff.flatten(), 0.999)) <= 2e-5, float(torch.quantile(diff.flatten(), 0.999))
+
+
+@pytest.mark.gpu
+def test_fit_function_end_to_end(plx_lib, tmp_path):
+    """fit() with the reference's argument list on a synthetic NeRF-format dataset: runs, logs, saves the reference's .pth."""
+    import json
+    from PIL import Image
+    from plenoxels_b200.fit import fit
+    (tmp_path / "train").mkdir()
+    poses = synth.lookat_poses(4)
+    rng = np.random.default_rng(1)
+    frames = []
+    for i in range(4):
+        Image.fromarray((rng.random((16, 16, 4)) * 255).astype(np.uint8), "RGBA").save(tmp_path / "train" / f"r_{i}.png")
+        frames.append({"file_path": f"./train/r_{i}", "rotation": 0.0, "transform_matrix": poses[i].tolist()})
+    (tmp_path / "transforms_train.json").write_text(json.dumps({"camera_angle_x": synth.CAMERA_ANGLE_X, "frames": frames}))
+    save = tmp_path / "grid_cells_trained.pth"
+    ft = fit([96, 96, 96], synth.GRID_EXTENT / 96, 32, 64, 6.0 / 64, 0.0075, 1e-5, 5e-3, 8, False, str(tmp_path / "train"),
+             str(tmp_path / "transforms_train.json"), str(save), "cuda:0", progressive_growing=False, log_every=4)
+    ck = torch.load(save)
+    assert set(ck) == {"grid", "grid_grad", "param"} and ck["grid"].shape == (96, 96, 96, 4)
+    assert ck["param"]["gridsize"] == [96, 96, 96] and ck["param"]["number_of_rays"] == 32
+    assert float(ck["grid_grad"].sum()) > 0 and ft.steps_done == 8
+    # the reference's own fit() raises when the grid is smaller than the first pooling window (93): so do we
+    with pytest.raises(RuntimeError):
+        fit([64, 64, 64], 0.05, 8, 16, 0.1, 0.01, 0, 0, 1, False, str(tmp_path / "train"), str(tmp_path / "transforms_train.json"),
+            str(save), "cuda:0")

@@ -160,6 +160,32 @@ def c2_regularised():
                           "Mrays_per_s": round(sc.n_rays / ms / 1e3, 1)}))
 
 
+def main_fit():
+    """The whole training run of scripts/main.py:24-44 (256^3 grid, pd 0.0125, 100 views x 75 rays x 600 samples, lr 0.0025,
+    1650 steps, progressive growing on, tv = beta = 0) through plenoxels_b200.fit.GridFitter on synthetic 800x800 views."""
+    import time
+    from plenoxels_b200.fit import GridFitter
+    poses, imgs = synth.lookat_poses(100), synth.random_images(100, 800, 800)
+    ft = GridFitter([256, 256, 256], 0.0125, poses, synth.CAMERA_ANGLE_X, imgs, 75, 600, 0.0125, 0.0025, tv=0, beta=0, device="cuda:0")
+    for i in range(3):
+        ft.step(i)
+    torch.cuda.synchronize()
+    ft2 = GridFitter([256, 256, 256], 0.0125, poses, synth.CAMERA_ANGLE_X, imgs, 75, 600, 0.0125, 0.0025, tv=0, beta=0, device="cuda:0")
+    t0 = time.perf_counter()
+    marks = {}
+    for i in range(1650):
+        ft2.step(i)
+        if i == 229:
+            torch.cuda.synchronize()
+            marks["progressive_230_steps_s"] = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    total = time.perf_counter() - t0
+    print(json.dumps({"config": "scripts/main.py training run (1650 steps, 256^3, 7500 rays x 600 samples/step)",
+                      "total_s": round(total, 3), **{k: round(v, 3) for k, v in marks.items()},
+                      "full_res_ms_per_step": round((total - marks["progressive_230_steps_s"]) / 1420 * 1e3, 4),
+                      "final_mse": float(ft2.last["mse"]), "reference_README": "2-10 minutes depending on hardware"}))
+
+
 def ref_cuda():
     """The reference's own op sequence (oracle/torch_port.py = scripts/train.py:130-184 restated op for op) on device="cuda":
     stock PyTorch eager on the same B200, the 'existing GPU path' of BASELINE.md §4."""
@@ -175,6 +201,8 @@ def ref_cuda():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c4"]
+    if "mainfit" in which:
+        main_fit()
     if "c2reg" in which:
         c2_regularised()
     if "refcuda" in which:

@@ -128,7 +128,28 @@ def make_tv(name):
     print(name, float(loss))
 
 
+def make_inference(name):
+    """visulize_3d_in_2d (src/visualization.py:111-154): ray-marched uint8 image of one camera, with the alpha threshold.
+    matplotlib / plotly are GUI-only imports of that module and absent here: empty stand-ins are injected."""
+    for mod in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.cm", "mpl_toolkits", "mpl_toolkits.mplot3d", "plotly", "plotly.graph_objects", "plotly.io", "plotly.express", "plotly.graph_objs"):
+        sys.modules.setdefault(mod, types.ModuleType(mod))
+    import src.visualization as rvz
+    G, res, S = 24, 12, 80
+    pd = synth.GRID_EXTENT / G
+    grid = synth.ball_grid(G, seed=31)
+    poses = synth.lookat_poses(5)[2:3]
+    imgs = synth.random_images(1, 16, 16, seed=32)
+    coords, _, _, _ = rgf.generate_grid(G, G, G, points_distance=pd, info_size=4, device="cpu")
+    ck = {"grid": grid, "param": {"points_distance": pd, "delta_step": 6.0 / S}}
+    img = rvz.visulize_3d_in_2d(ck, poses, synth.CAMERA_ANGLE_X, imgs, coords, True, 0.2, res * res, S, device="cpu")
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), grid=grid.numpy(), poses=poses.numpy(), imgs=imgs.numpy(),
+                        pd=np.float64(pd), delta=np.float64(6.0 / S), S=np.int64(S), res=np.int64(res), threshold=np.float64(0.2),
+                        fov=np.float64(synth.CAMERA_ANGLE_X), image=img)
+    print(name, img.shape, img.dtype, int(img[..., 3].max()))
+
+
 if __name__ == "__main__":
+    make_inference("inference_g24")
     make_tv("tv_g12")
     make_case("nn_dense_g24", 24, 2, 8, 64, 48, 6.0 / 48, "dense", "nearest", seed=11)
     make_case("nn_ball_g32", 32, 3, 12, 48, 96, 6.0 / 96, "ball", "nearest", seed=12)

@@ -350,3 +350,21 @@ def test_trainer_with_tv_and_beta_matches_oracle(plx_lib):
     assert abs(loss - oloss) <= TOL * oloss
     assert abs(float(tr.tv_loss) - tv * tvl) <= 1e-5 * tv * tvl
     assert rel_err(tr.grad_abs_sum.cpu().numpy(), np.abs(ograd + tv * tvg)) <= TOL
+
+
+def test_visulize_3d_in_2d_matches_reference_image(plx_lib):
+    """The drop-in ray-marched inference (src/visualization.py:111-154, coherent ray-packet kernel) against the uint8 image
+    the UNMODIFIED reference rendered for the same checkpoint and camera (tests/golden/inference_g24.npz)."""
+    import os
+    import src.grid_functions as gf
+    import src.visualization as vz
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "inference_g24.npz"))
+    G = z["grid"].shape[0]
+    ck = {"grid": torch.from_numpy(z["grid"]), "param": {"points_distance": float(z["pd"]), "delta_step": float(z["delta"])}}
+    coords, _, _, _ = gf.generate_grid(G, G, G, points_distance=float(z["pd"]), info_size=4, device="cuda:0")
+    res = int(z["res"])
+    img = vz.visulize_3d_in_2d(ck, torch.from_numpy(z["poses"]).cuda(), float(z["fov"]), torch.from_numpy(z["imgs"]).cuda(), coords,
+                               True, float(z["threshold"]), res * res, int(z["S"]), device="cuda:0")
+    assert img.shape == z["image"].shape and img.dtype == np.uint8
+    assert np.abs(img.astype(int) - z["image"].astype(int)).max() <= 1
+    assert (img == z["image"]).mean() > 0.99

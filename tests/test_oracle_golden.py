@@ -117,3 +117,26 @@ def test_oracle_tv_loss_matches_reference():
     assert abs(loss - float(z["loss"])) <= 1e-6 * float(z["loss"])
     assert np.abs(grad - z["grad"]).max() <= 1e-6 * np.abs(z["grad"]).max()
     assert po.tv_loss(np.full((3, 3, 3, 4), 0.25))[1].max() == 0.0        # constant grid: the reference gives NaN, we give 0
+
+
+def _oracle_inference_image(z):
+    """visulize_3d_in_2d (src/visualization.py:111-154) restated on the oracle: clip, alpha threshold, even-spread rays of
+    one camera, nearest lookup without further clamping, composite, x255 round clip uint8, transpose."""
+    grid = np.clip(z["grid"], 0.0, 1.0).astype(np.float32)
+    grid[..., 3][grid[..., 3] < float(z["threshold"])] = 0.0
+    res, S = int(z["res"]), int(z["S"])
+    uv = po.even_spread_uv(1, res * res)
+    dirs, _, _ = po.generate_rays(z["imgs"], z["poses"], float(z["fov"]), uv)
+    o = np.repeat(z["poses"][:, :3, 3], res * res, axis=0)
+    gmin = po.grid_origin(grid.shape[:3], float(z["pd"]))
+    rgba, _, _, _ = po.render_forward(grid, o, dirs, S, float(z["delta"]), gmin, float(z["pd"]), clamp=False)
+    img = (rgba * 255).round().clip(0, 255).astype(np.uint8).reshape(res, res, 4)
+    return np.transpose(img, (1, 0, 2))
+
+
+def test_oracle_inference_image_matches_reference():
+    z = load("inference_g24")
+    img = _oracle_inference_image(z)
+    assert img.shape == z["image"].shape and img.dtype == np.uint8
+    assert np.abs(img.astype(int) - z["image"].astype(int)).max() <= 1          # a value on a .5 boundary may round either way
+    assert (img == z["image"]).mean() > 0.99

@@ -16,7 +16,7 @@ namespace plx {
 // launch-invariant geometry, derived once per thread from the PlxMarch argument
 struct Geo {
     float fnx, fny, fnz;     // grid dims as floats (the in-bounds test runs on the rounded float)
-    int ny, nz;
+    int nx, ny, nz;
     float gx, gy, gz, delta;
     FastDiv div;
     bool clamp;
@@ -26,7 +26,7 @@ struct Geo {
 __device__ __forceinline__ Geo make_geo(const PlxMarch& m) {
     Geo g;
     g.fnx = (float)m.nx; g.fny = (float)m.ny; g.fnz = (float)m.nz;
-    g.ny = m.ny; g.nz = m.nz;
+    g.nx = m.nx; g.ny = m.ny; g.nz = m.nz;
     g.gx = m.gmin[0]; g.gy = m.gmin[1]; g.gz = m.gmin[2];
     g.delta = m.delta_step;
     g.div = make_fastdiv(m.points_distance);
@@ -69,6 +69,22 @@ __device__ __forceinline__ float4 clamp4(float4 c) {
     return make_float4(__saturatef(c.x), __saturatef(c.y), __saturatef(c.z), __saturatef(c.w));
 }
 
+// round-half-even + in-bounds test of the three normalised coordinates (src/grid_functions.py:111, :58-61).
+// Reference form: r = rint(n) as float, 0 <= r < dim per axis.  For a ray in the fast range every coordinate is finite,
+// so the same decision is one conversion and one unsigned compare per axis: __float2int_rn rounds half to even like
+// rintf, saturates beyond int32 (-> fails the unsigned test, as the float test would) and maps -0.0 to 0 (inside).
+// Anything that could be NaN / inf takes the float form.
+__device__ __forceinline__ bool nearest_cell(const Geo& g, bool exact_int, float nx, float ny, float nz, int& ix, int& iy, int& iz) {
+    if (exact_int) {
+        ix = __float2int_rn(nx); iy = __float2int_rn(ny); iz = __float2int_rn(nz);
+        return (unsigned)ix < (unsigned)g.nx && (unsigned)iy < (unsigned)g.ny && (unsigned)iz < (unsigned)g.nz;
+    }
+    const float rx = rintf(nx), ry = rintf(ny), rz = rintf(nz);
+    const bool inb = rx >= 0.f && rx < g.fnx && ry >= 0.f && ry < g.fny && rz >= 0.f && rz < g.fnz;
+    ix = inb ? (int)rx : 0; iy = inb ? (int)ry : 0; iz = inb ? (int)rz : 0;
+    return inb;
+}
+
 // One sample's lookup result.
 struct Sample {
     float4 c;        // (clamped) value, 0 when out of bounds
@@ -80,15 +96,14 @@ struct Sample {
 // ---- nearest neighbour: src/grid_functions.py:111 (round half even), :58-61 (mask) -------------------------
 template <bool FAST>
 __device__ __forceinline__ Sample lookup_nearest(const PlxMarch& m, const Geo& g, const float* __restrict__ grid, float nx,
-                                                 float ny, float nz, bool valid, bool need_value) {
+                                                 float ny, float nz, bool valid, bool need_value, bool exact_int) {
     Sample s;
     s.c = make_float4(0.f, 0.f, 0.f, 0.f);
     s.raw = s.c;
-    const float rx = rintf(nx), ry = rintf(ny), rz = rintf(nz);
-    s.inb = valid && rx >= 0.f && rx < g.fnx && ry >= 0.f && ry < g.fny && rz >= 0.f && rz < g.fnz;
+    int ix, iy, iz;
+    s.inb = nearest_cell(g, exact_int, nx, ny, nz, ix, iy, iz) && valid;
     s.lin = -1;
     if (s.inb) {
-        const int ix = (int)rx, iy = (int)ry, iz = (int)rz;
         s.lin = (ix * g.ny + iy) * g.nz + iz;
         if (need_value) {
             s.raw = cell_at<FAST>(m, g, grid, ix, iy, iz, s.lin);
@@ -106,11 +121,10 @@ __device__ __forceinline__ int fetch_nearest(const PlxMarch& m, const Geo& g, co
     const float t = __fmul_rn(g.delta, (float)k);
     float nx, ny, nz;
     norm3<FAST>(m, g, r, fast_ray, t, nx, ny, nz);
-    const float rx = rintf(nx), ry = rintf(ny), rz = rintf(nz);
-    const bool inb = valid && rx >= 0.f && rx < g.fnx && ry >= 0.f && ry < g.fny && rz >= 0.f && rz < g.fnz;
+    int ix, iy, iz;
+    const bool inb = nearest_cell(g, FAST && fast_ray, nx, ny, nz, ix, iy, iz) && valid;
     raw = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!inb) return -1;
-    const int ix = (int)rx, iy = (int)ry, iz = (int)rz;
     const int lin = (ix * g.ny + iy) * g.nz + iz;
     raw = cell_at<FAST>(m, g, grid, ix, iy, iz, lin);
     return lin;
@@ -172,7 +186,7 @@ __device__ __forceinline__ Sample lookup(const PlxMarch& m, const Geo& g, const 
     t = __fmul_rn(g.delta, (float)k);                                       // src/ray_sampling.py:161
     float nx, ny, nz;
     norm3<FAST>(m, g, r, fast_ray, t, nx, ny, nz);
-    if (MODE == PLX_NEAREST) return lookup_nearest<FAST>(m, g, grid, nx, ny, nz, valid, need_value);
+    if (MODE == PLX_NEAREST) return lookup_nearest<FAST>(m, g, grid, nx, ny, nz, valid, need_value, FAST && fast_ray);
     Sample s;
     s.c = make_float4(0.f, 0.f, 0.f, 0.f);
     s.raw = s.c;

@@ -44,6 +44,27 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) k_render_fwd(const P
         int cnt = 0;
         int c = 0;
         bool alive = true;                   // false once T == 0 exactly: later samples have weight 0
+        if (MODE == PLX_NEAREST && !DBG) {
+            // nearest mode, production path: software-pipelined — the cell of chunk c+1 is requested before chunk c is
+            // composited, so the gather latency overlaps the scan (same scheme as K12, plx_train.cu)
+            float4 rawn;
+            int linn = k0 <= k1 ? fetch_nearest<FAST>(m, g, a.grid, r, fast_ray, k0 + lane, k0 + lane <= k1, rawn) : -1;
+            for (int kb = k0; kb <= k1; kb += CHUNK, ++c) {
+                const float4 cell = g.clamp ? clamp4(rawn) : rawn;
+                const float t = __fmul_rn(g.delta, (float)(kb + lane));
+                (void)linn;
+                if (kb + CHUNK <= k1) linn = fetch_nearest<FAST>(m, g, a.grid, r, fast_ray, kb + CHUNK + lane, kb + CHUNK + lane <= k1, rawn);
+                if (tc && lane == 0) tc[c] = T;
+                float total;
+                const float ex = warp_excl_prod(1.f - cell.w, lane, total);
+                const float w = cell.w * (T * ex);          // alpha_k * T_k, src/ray_sampling.py:184
+                ar = fmaf(w, cell.x, ar); ag = fmaf(w, cell.y, ag); ab = fmaf(w, cell.z, ab);
+                aa += w;
+                ad = fmaf(w, t, ad);
+                T *= total;
+                if (T == 0.f) { alive = false; ++c; break; }
+            }
+        } else
         for (int kb = k0; kb <= k1; kb += CHUNK, ++c) {
             const int k = kb + lane;
             const bool valid = k <= k1;
@@ -185,13 +206,32 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) k_render_bwd(const P
 
     // ---- pass 2: reverse over the chunks
     float behind_carry = 0.f;                // S behind the last sample of the ray = 0
+    // nearest mode: the cell of chunk c-1 is requested before chunk c is processed (software pipeline, as in K1 / K12)
+    float4 rawn = make_float4(0.f, 0.f, 0.f, 0.f);
+    int linn = -1;
+    if (MODE == PLX_NEAREST) {
+        const int kl = k0 + (nch - 1) * CHUNK + lane;
+        linn = fetch_nearest<FAST>(m, g, a.grid, r, fast_ray, kl, kl <= k1, rawn);
+    }
     for (int c = nch - 1; c >= 0; --c) {
         const int k = k0 + c * CHUNK + lane;
         const bool valid = k <= k1;
         const float Tc = tc[c];
         float t;
         TriGeom tg;
-        const Sample s = lookup<MODE, FAST>(m, g, a.grid, r, fast_ray, k, valid, true, t, tg);
+        Sample s;
+        if (MODE == PLX_NEAREST) {
+            s.raw = rawn;
+            s.c = g.clamp ? clamp4(rawn) : rawn;
+            s.lin = linn;
+            s.inb = linn >= 0;
+            if (c > 0) {
+                const int kp = k - CHUNK;
+                linn = fetch_nearest<FAST>(m, g, a.grid, r, fast_ray, kp, kp <= k1, rawn);
+            }
+        } else {
+            s = lookup<MODE, FAST>(m, g, a.grid, r, fast_ray, k, valid, true, t, tg);
+        }
         const float alpha = s.c.w;
         const float v = fmaf(s.c.x, gr.x, fmaf(s.c.y, gr.y, fmaf(s.c.z, gr.z, gr.w)));     // c_k . g_rgb + g_A
         const float behind = warp_behind(alpha * v, 1.f - alpha, lane, behind_carry);

@@ -40,7 +40,7 @@ __device__ __forceinline__ void composite_iter(const float4 (&c)[SPL], int lane,
     T *= total;
 }
 
-template <bool FAST, int SPL, int MINB>
+template <bool FAST, int SPL, int MINB, bool PIPE>
 __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain a, int lin_words, int warp_words) {
     extern __shared__ __align__(16) int s_dyn[];   // per warp (warp_words ints, 16-byte multiple): lin cache [lin_words], then chunk transmittances
     __shared__ float s_loss;
@@ -106,13 +106,14 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
 #pragma unroll
             for (int j = 0; j < SPL; ++j) linn[j] = fetch_nearest<FAST>(m, g, a.grid, r, fast_ray, kb + j, kb + j <= k1, rawn[j]);
         };
-        if (n_it > 0) fetch(0);
+        if (PIPE && n_it > 0) fetch(0);
         for (; it < n_it; ++it) {
             float4 c[SPL];
             int lin[SPL];
+            if (!PIPE) fetch(it);
 #pragma unroll
             for (int j = 0; j < SPL; ++j) { c[j] = g.clamp ? clamp4(rawn[j]) : rawn[j]; lin[j] = linn[j]; }
-            if (it + 1 < n_it) fetch(it + 1);
+            if (PIPE && it + 1 < n_it) fetch(it + 1);
             if (SPL == 1) lc[it * W + lane] = lin[0];
             else *reinterpret_cast<int2*>(lc + it * W + lane * 2) = make_int2(lin[0], lin[SPL - 1]);
             if (lane == 0) tcs[it] = T;
@@ -147,11 +148,12 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
         }
         const int n_fwd = it;                // iterations of segment 1 (their indices are cached)
         if (opaque) {                        // keep compositing behind k* until that segment saturates or the range ends
-            for (int i2 = n_fwd; i2 < n_it && T2 != 0.f; ++i2) {          // iteration n_fwd is already in flight (rawn)
+            for (int i2 = n_fwd; i2 < n_it && T2 != 0.f; ++i2) {          // PIPE: iteration n_fwd is already in flight (rawn)
                 float4 c[SPL];
+                if (!PIPE) fetch(i2);
 #pragma unroll
                 for (int j = 0; j < SPL; ++j) c[j] = g.clamp ? clamp4(rawn[j]) : rawn[j];
-                if (i2 + 1 < n_it) fetch(i2 + 1);
+                if (PIPE && i2 + 1 < n_it) fetch(i2 + 1);
                 composite_iter<SPL>(c, lane, T2, acc2);
             }
         }
@@ -182,11 +184,12 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
                                                  : cell_at<false>(m, g, a.grid, linn[j] / (g.ny * g.nz), (linn[j] / g.nz) % g.ny, linn[j] % g.nz, linn[j]);
             }
         };
-        if (n_fwd > 0 && any_grad) refetch(n_fwd - 1);
+        if (PIPE && n_fwd > 0 && any_grad) refetch(n_fwd - 1);
         for (int ib = n_fwd - 1; ib >= 0 && any_grad; --ib) {
             int lin[SPL];
             float4 raw[SPL], c[SPL];
             float v[SPL];
+            if (!PIPE) refetch(ib);
 #pragma unroll
             for (int j = 0; j < SPL; ++j) {
                 lin[j] = linn[j];
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
                 c[j] = g.clamp ? clamp4(raw[j]) : raw[j];
                 v[j] = fmaf(c[j].x, gr.x, fmaf(c[j].y, gr.y, fmaf(c[j].z, gr.z, gr.w)));      // c_k . g_rgb + g_A
             }
-            if (ib > 0) refetch(ib - 1);     // next iteration's cells in flight during this iteration's scans
+            if (PIPE && ib > 0) refetch(ib - 1);     // next iteration's cells in flight during this iteration's scans
             bool any_alpha = false;
 #pragma unroll
             for (int j = 0; j < SPL; ++j) any_alpha = any_alpha || c[j].w != 0.f;
@@ -308,14 +311,19 @@ cudaError_t launch_render_train(const PlxRenderTrain& a_in, cudaStream_t st) {
         if (blocks > wave) blocks = wave;
     }
     const bool fast = fast_ok(a.march, a.grid);
+    // software pipelining pays when the gathers are L2-latency bound (grid + gradient resident in L2: +5 % on C2); on grids
+    // far beyond the L2 the extra requests in flight only add DRAM queueing (-8 % on the 256^3 sweep), so it is off there
+    static const int pipe_env = env_int("PLX_TRAIN_PIPE", -1, 0, 1);
+    const bool pipe = pipe_env >= 0 ? pipe_env != 0 : l2_keep_ok((int64_t)a.march.nx * a.march.ny * a.march.nz);
 #define PLX_TRAIN(FASTP, SPLV, MB)                                                                                              \
     do {                                                                                                                    \
         if (smem > 48 * 1024) {                                                                                             \
-            cudaError_t e = cudaFuncSetAttribute(k_render_train<FASTP, SPLV, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                                 (int)smem);                                                                \
+            cudaError_t e = pipe ? cudaFuncSetAttribute(k_render_train<FASTP, SPLV, MB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)   \
+                                 : cudaFuncSetAttribute(k_render_train<FASTP, SPLV, MB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                                 \
         }                                                                                                                   \
-        k_render_train<FASTP, SPLV, MB><<<blocks, wpb * 32, smem, st>>>(a, lin_words, lin_words + ((n_it_max + 3) & ~3));   \
+        if (pipe) k_render_train<FASTP, SPLV, MB, true><<<blocks, wpb * 32, smem, st>>>(a, lin_words, lin_words + ((n_it_max + 3) & ~3));   \
+        else      k_render_train<FASTP, SPLV, MB, false><<<blocks, wpb * 32, smem, st>>>(a, lin_words, lin_words + ((n_it_max + 3) & ~3));  \
     } while (0)
     if (!fast) { if (spl == 2) PLX_TRAIN(false, 2, 8); else PLX_TRAIN(false, 1, 8); }
     else if (spl == 2) { if (minb <= 6) PLX_TRAIN(true, 2, 6); else if (minb == 7) PLX_TRAIN(true, 2, 7); else PLX_TRAIN(true, 2, 8); }

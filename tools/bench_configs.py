@@ -61,9 +61,10 @@ def c5():
     gg = torch.zeros_like(grid)
     gmin = ops.grid_origin(grid.shape, pd)
     poses = synth.lookat_poses(64).to(dev)
-    for S in (64, 128, 256, 512):
+    quick = os.environ.get("PLX_C5_QUICK") == "1"
+    for S in ((256, 512) if quick else (64, 128, 256, 512)):
         delta = 6.0 / S
-        for logn in (10, 12, 14, 16, 18, 20):
+        for logn in ((16, 20) if quick else (10, 12, 14, 16, 18, 20)):
             n = 1 << logn
             R = n // 64
             uv = torch.rand(64, R, 2, device=dev, generator=torch.Generator(device=dev).manual_seed(logn))

@@ -1,0 +1,128 @@
+"""Parity at BASELINE.json's FULL sizes through size-independent properties (the oracle only checks a ray subsample here).
+
+Config #2 geometry: 128^3 ball grid, 100 cameras x 128 rays = 12 800 rays, 600 samples/ray (delta = 0.0125, pd = 0.025);
+config #3: 256^3 grid, 4096 rays x 256 samples.  Properties: two independent implementations agree (fused K12 vs K1 + K2),
+the gradient is additive over ray shards (the multi-GPU premise) and linear in the pixel gradient, clipping / early
+termination never change a pixel, per-ray counts equal the per-sample index dump, a transparent grid renders exactly 0.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import plenoxel_oracle as po
+from plenoxels_b200 import ops, synth
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class Full:
+    def __init__(self, name):
+        sc = synth.make_scene(name, H=8)                    # tiny images: targets are drawn directly below
+        self.sc = sc
+        self.C, self.R, self.S = sc.poses.shape[0], sc.rays_per_cam, sc.num_samples
+        self.N = self.C * self.R
+        self.grid = sc.grid.to(DEV)
+        self.poses = sc.poses.to(DEV)
+        self.gmin = ops.grid_origin(sc.grid.shape, sc.points_distance)
+        self.uv = synth.random_uv(self.C, self.R, seed=77).to(DEV)
+        self.dirs, _ = ops.generate_rays(None, self.poses, sc.fov, uv=self.uv, want_targets=False)
+        self.origins = self.poses[:, :3, 3]
+        self.targets = torch.rand(self.N, 4, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+
+    def render(self, grid=None, **kw):
+        g = self.grid if grid is None else grid
+        return ops.render_rays(g, self.origins, self.dirs, self.S, self.sc.delta_step, self.gmin, self.sc.points_distance,
+                               rays_per_origin=self.R, **kw)
+
+    def train(self, sel=None, n_global=None):
+        gg = torch.zeros_like(self.grid)
+        if sel is None:
+            o, d, t, rpo = self.origins, self.dirs, self.targets, self.R
+        else:                                               # per-ray origins for an arbitrary subset
+            o = self.origins.repeat_interleave(self.R, 0)[sel].contiguous()
+            d, t, rpo = self.dirs[sel].contiguous(), self.targets[sel].contiguous(), 1
+        rgba, loss = ops.render_train(self.grid, gg, self.S, self.sc.delta_step, self.gmin, self.sc.points_distance, origins=o,
+                                      dirs=d, targets=t, rays_per_origin=rpo, n_rays_global=n_global)
+        return rgba, loss, gg
+
+
+@pytest.fixture(scope="module", params=["c2", "c3"])
+def full(request, plx_lib):
+    return Full(request.param)
+
+
+def test_fused_march_equals_forward_plus_backward_kernels(full):
+    """K12 and the K1 + K2 pair are separate code paths (shared-memory index cache, 2 samples per lane, two-sided early
+    termination vs recomputation from the chunk transmittances): pixels, loss and gradient must agree."""
+    rgba_f, loss_f, grad_f = full.train()
+    g = full.grid.clone().requires_grad_(True)
+    rgba = full.render(g)
+    loss = torch.nn.functional.mse_loss(rgba, full.targets)
+    loss.backward()
+    assert rel_err(rgba_f.cpu().numpy(), rgba.detach().cpu().numpy()) <= 2e-6
+    assert abs(float(loss_f) - float(loss)) <= 2e-6 * float(loss)
+    assert rel_err(grad_f.cpu().numpy(), g.grad.cpu().numpy()) <= 5e-6
+
+
+def test_gradient_is_additive_over_ray_shards(full):
+    """sum over shards of grad(shard, scaled by the global ray count) == grad(all rays): what the multi-GPU sum relies on."""
+    _, loss_all, grad_all = full.train()
+    idx = torch.randperm(full.N, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
+    parts = torch.tensor_split(idx, 3)
+    acc, loss_acc = torch.zeros_like(grad_all), 0.0
+    for p in parts:
+        _, l, gpart = full.train(sel=p, n_global=full.N)
+        acc += gpart
+        loss_acc += float(l)
+    assert abs(loss_acc - float(loss_all)) <= 5e-6 * float(loss_all)
+    assert rel_err(acc.cpu().numpy(), grad_all.cpu().numpy()) <= 5e-6
+
+
+def test_backward_is_linear_in_the_pixel_gradient(full):
+    g = full.grid.clone().requires_grad_(True)
+    rgba = full.render(g)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    a, b = torch.randn(full.N, 4, device=DEV, generator=gen), torch.randn(full.N, 4, device=DEV, generator=gen)
+    ga, = torch.autograd.grad(rgba, g, a, retain_graph=True)
+    gb, = torch.autograd.grad(rgba, g, b, retain_graph=True)
+    gab, = torch.autograd.grad(rgba, g, 2.0 * a - 0.5 * b)
+    assert rel_err(gab.cpu().numpy(), (2.0 * ga - 0.5 * gb).cpu().numpy()) <= 5e-6
+
+
+def test_clipping_and_early_termination_never_change_a_pixel(full):
+    """Default march (ray/box pre-filter + stop at T == 0) vs the full march the count path forces, and vs ray packets."""
+    base = full.render()
+    rgba_full, depth_full, count = full.render(return_depth=True, return_count=True)
+    packet, depth_p = full.render(return_depth=True, coherent=True)
+    assert rel_err(base.cpu().numpy(), rgba_full.cpu().numpy()) <= 2e-6
+    assert rel_err(packet.cpu().numpy(), rgba_full.cpu().numpy()) <= 2e-6
+    assert rel_err(depth_p.cpu().numpy(), depth_full.cpu().numpy()) <= 2e-6
+    assert int(count.sum()) > 0 and int(count.max()) <= full.S
+
+
+def test_counts_equal_the_index_dump_and_match_the_oracle_on_a_subsample(full):
+    idx, count = ops.sample_indices(full.grid, full.origins, full.dirs, full.S, full.sc.delta_step, full.gmin,
+                                    full.sc.points_distance, rays_per_origin=full.R)
+    assert torch.equal((idx >= 0).sum(1).to(torch.int32), count)
+    assert int(idx.max()) < full.grid.shape[0] * full.grid.shape[1] * full.grid.shape[2]
+    # oracle on every 97th ray: bit-exact linear indices at full grid size / sample count
+    sel = np.arange(0, full.N, 97)
+    o = np.repeat(full.sc.poses[:, :3, 3].numpy(), full.R, axis=0)[sel]
+    d = full.dirs.cpu().numpy()[sel]
+    orgba, odepth, ocount, olin = po.render_forward(full.sc.grid.numpy(), o, d, full.S, full.sc.delta_step, np.float32(full.gmin),
+                                                    full.sc.points_distance)
+    assert np.array_equal(idx.cpu().numpy()[sel].astype(np.int64), olin)
+    assert np.array_equal(count.cpu().numpy()[sel], ocount)
+    assert rel_err(full.render().cpu().numpy()[sel], orgba) <= 1e-5
+
+
+def test_transparent_grid_renders_exactly_zero_and_only_alpha_gets_gradient(full):
+    g = torch.zeros_like(full.grid).requires_grad_(True)
+    g.data[..., :3] = 0.5                                   # colour without opacity must stay invisible
+    rgba = full.render(g)
+    assert float(rgba.abs().max()) == 0.0
+    torch.nn.functional.mse_loss(rgba, full.targets).backward()
+    assert float(g.grad[..., :3].abs().max()) == 0.0, "d colour = alpha * T * g_rgb = 0 exactly"
+    assert float(g.grad[..., 3].abs().max()) > 0.0

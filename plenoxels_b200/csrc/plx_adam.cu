@@ -267,10 +267,12 @@ __global__ void k_peer_barrier(FlagPtrs f, int rank, int world, int channel, int
         int32_t* theirs = f.p[r] + channel * PLX_MAX_PEERS + rank;
         asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
         const int32_t* mine = f.p[rank] + channel * PLX_MAX_PEERS + r;
+        // bounded spin: a peer that died must not hang this GPU (a hung box costs far more than a wrong step); ~10 s
         int32_t seen;
+        long long spins = 0;
         do {
             asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-        } while (seen - epoch < 0);
+        } while (seen - epoch < 0 && ++spins < (1ll << 23));
     }
 }
 

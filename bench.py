@@ -261,6 +261,7 @@ def run_gpu_arm(args):
     e0.record()
     for i in range(K):
         tr.step(uv_dev[(W + i) % n_batches])
+    tr.flush()                                                 # multi-GPU: every replica complete (no-op on one GPU)
     e1.record()
     barrier()
     sampler.stop()
@@ -280,6 +281,7 @@ def run_gpu_arm(args):
     for i in range(K):
         tr2.step_host(uv_host[(W + i) % n_batches])
         host_losses.append(tr2.wait_result())                  # the host reads the loss of THIS step (scripts/train.py:159)
+    tr2.flush()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     sampler.stop()
@@ -405,7 +407,7 @@ def run_gpu_arm(args):
                             "that loss before issuing the next step; images/poses/grid stay resident as in the reference "
                             "(scripts/train.py:75)",
                     "last_loss": host_losses[-1]},
-            "gpu_launches": (2 if fused else 4) * K,
+            "gpu_launches": (getattr(tr, "launches_per_step", 2) if world > 1 else (2 if fused else 4)) * K,
             "clocks": sampler.summary(),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -143,6 +143,28 @@ typedef struct PlxRayGen {
     const float* poses; float fov;
     const float* uv; int32_t rays_per_cam;
 } PlxRayGen;
+/*
+ * Cross-GPU ordering fused into a kernel (multi-GPU only; all-zero = none).  `flags[r]` is rank r's int32 flag array
+ * (PLX_BARRIER_CHANNELS x PLX_MAX_PEERS, symmetric / peer-mapped, zero before the first step; the array plx_peer_barrier
+ * uses).  A kernel given a PlxPeerSync
+ *   - at its START, if wait_epoch > 0: every block spins (bounded) until its OWN flags[rank][wait_channel][r] >= wait_epoch
+ *     for every r < world, i.e. until every peer has signalled that epoch on that channel;
+ *   - at its END, if signal_epoch > 0: the last block to finish (counted in `block_counter`, one device int32 that is 0
+ *     before the first launch and wraps back to 0 by itself) stores signal_epoch into flags[r][signal_channel][rank] of
+ *     every peer r with release semantics at system scope, after all of the grid's writes.
+ * This replaces the two stand-alone barrier launches around plx_adam_step_peer: the march signals "my partial gradient
+ * is complete", the exchange kernel waits for that from everyone and signals "my slab is stored in every replica", and the
+ * next march waits for that.
+ */
+#define PLX_MAX_PEERS 8
+typedef struct PlxPeerSync {
+    int32_t* flags[PLX_MAX_PEERS];
+    int32_t rank, world;
+    int32_t wait_channel, wait_epoch;
+    int32_t signal_channel, signal_epoch;
+    int32_t* block_counter;
+} PlxPeerSync;
+
 typedef struct PlxRenderTrain {
     PlxMarch march;
     PlxRays rays;
@@ -155,6 +177,7 @@ typedef struct PlxRenderTrain {
     float grad_scale, loss_scale, beta_over_m;
     int32_t* work_counter;   /* optional: one device int32 that is 0 at launch; rays are then claimed dynamically by the warps
                                 of a one-wave grid (better balance for rays of unequal length).  NULL = static assignment */
+    PlxPeerSync sync;        /* optional cross-GPU wait at the start / signal at the end (all-zero = none) */
 } PlxRenderTrain;
 int plx_render_train(const PlxRenderTrain* args, void* stream);
 
@@ -177,7 +200,6 @@ int plx_adam_step(float* p, float* g, float* m, float* v, float* gabs, int64_t n
  * stores in flight together, no staging copy and no atomics on the fabric.  The caller orders it between two
  * cross-rank barriers (gradients complete before / parameters visible after) and clears its own gradient buffer.
  */
-#define PLX_MAX_PEERS 8
 typedef struct PlxAdamPeer {
     int32_t world, rank;
     float* grids[PLX_MAX_PEERS];
@@ -198,6 +220,7 @@ typedef struct PlxAdamPeer {
     float* loss_clear;
     void* result_host;
     int32_t* counter_clear;  /* optional: the march's work counter, reset to 0 for the next step */
+    PlxPeerSync sync;        /* optional fused barriers (all-zero = the caller orders the kernel with plx_peer_barrier) */
 } PlxAdamPeer;
 int plx_adam_step_peer(const PlxAdamPeer* args, void* stream);
 
@@ -309,6 +332,8 @@ typedef struct PlxTrainStep {
     /* optional dynamic work distribution for the fused march (see PlxRenderTrain.work_counter): one device int32, zero
      * before the first step; the optimiser phase resets it for the next step */
     int32_t* work_counter;
+    /* optional (multi-GPU): cross-GPU wait / signal fused into the march of the render phase (see PlxPeerSync) */
+    const PlxPeerSync* render_sync;
 } PlxTrainStep;
 int plx_train_step(const PlxTrainStep* args, int32_t phase, void* stream);
 

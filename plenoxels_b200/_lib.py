@@ -53,13 +53,19 @@ class PlxRayGen(C.Structure):
                 ("poses", c_void), ("fov", C.c_float), ("uv", c_void), ("rays_per_cam", C.c_int32)]
 
 
+PLX_MAX_PEERS = 8
+
+
+class PlxPeerSync(C.Structure):
+    _fields_ = [("flags", c_void * PLX_MAX_PEERS), ("rank", C.c_int32), ("world", C.c_int32),
+                ("wait_channel", C.c_int32), ("wait_epoch", C.c_int32), ("signal_channel", C.c_int32),
+                ("signal_epoch", C.c_int32), ("block_counter", c_void)]
+
+
 class PlxRenderTrain(C.Structure):
     _fields_ = [("march", PlxMarch), ("rays", PlxRays), ("targets", c_void), ("gen", PlxRayGen), ("grid", c_void),
                 ("grad_grid", c_void), ("rgba", c_void), ("loss", c_void), ("grad_scale", C.c_float),
-                ("loss_scale", C.c_float), ("beta_over_m", C.c_float), ("work_counter", c_void)]
-
-
-PLX_MAX_PEERS = 8
+                ("loss_scale", C.c_float), ("beta_over_m", C.c_float), ("work_counter", c_void), ("sync", PlxPeerSync)]
 
 
 class PlxAdamPeer(C.Structure):
@@ -67,7 +73,8 @@ class PlxAdamPeer(C.Structure):
                 ("grads", c_void * PLX_MAX_PEERS), ("exp_avg", c_void), ("exp_avg_sq", c_void), ("grad_abs_sum", c_void),
                 ("begin", C.c_int64), ("end", C.c_int64), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
                 ("eps", C.c_double), ("step", C.c_int64), ("grid_mc", c_void), ("grad_mc", c_void),
-                ("loss_src", c_void), ("loss_clear", c_void), ("result_host", c_void), ("counter_clear", c_void)]
+                ("loss_src", c_void), ("loss_clear", c_void), ("result_host", c_void), ("counter_clear", c_void),
+                ("sync", PlxPeerSync)]
 
 
 class PlxTrainStep(C.Structure):
@@ -82,7 +89,7 @@ class PlxTrainStep(C.Structure):
                 ("step", C.c_int64),
                 ("beta_over_m", C.c_float),
                 ("dirs", c_void), ("targets", c_void), ("rgba", c_void), ("grad_rgba", c_void), ("tcarry", c_void),
-                ("loss", c_void), ("work_counter", c_void)]
+                ("loss", c_void), ("work_counter", c_void), ("render_sync", C.POINTER(PlxPeerSync))]
 
 
 # name -> (restype, argtypes); every symbol include/plenoxel_abi.h declares

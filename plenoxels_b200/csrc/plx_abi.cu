@@ -82,11 +82,24 @@ int plx_render_bwd(const PlxRenderBwd* a, void* stream) {
     return cuda_result(plx::launch_render_bwd(*a, (cudaStream_t)stream), "plx_render_bwd");
 }
 
+// PlxPeerSync (optional fused cross-GPU ordering): all-zero = none; `has_work` = the launch will actually run a grid
+static int check_sync(const PlxPeerSync& s, bool has_work) {
+    if (s.wait_epoch <= 0 && s.signal_epoch <= 0) return PLX_OK;
+    if (s.world < 1 || s.world > PLX_MAX_PEERS || s.rank < 0 || s.rank >= s.world) return fail(PLX_E_SHAPE, "peer sync: bad world / rank");
+    if (s.wait_channel < 0 || s.wait_channel >= PLX_BARRIER_CHANNELS || s.signal_channel < 0 || s.signal_channel >= PLX_BARRIER_CHANNELS)
+        return fail(PLX_E_SHAPE, "peer sync: channel out of range");
+    for (int r = 0; r < s.world; ++r) if (!s.flags[r]) return fail(PLX_E_NULL, "peer sync: flag array of rank %d is NULL", r);
+    if (s.signal_epoch > 0 && !s.block_counter) return fail(PLX_E_NULL, "peer sync: block_counter is NULL");
+    if (s.signal_epoch > 0 && !has_work) return fail(PLX_E_SHAPE, "peer sync: a launch without work cannot signal its peers");
+    return PLX_OK;
+}
+
 int plx_render_train(const PlxRenderTrain* a, void* stream) {
     if (!a) return fail(PLX_E_NULL, "args is NULL");
     int rc;
     if ((rc = check_march(a->march, a->grid)) != PLX_OK) return rc;
     if (a->rays.n_rays < 0) return fail(PLX_E_SHAPE, "n_rays < 0");
+    if ((rc = check_sync(a->sync, a->rays.n_rays > 0)) != PLX_OK) return rc;
     if (a->rays.n_rays == 0) return PLX_OK;
     if (!a->grad_grid) return fail(PLX_E_NULL, "grad_grid is NULL");
     if ((uintptr_t)a->grad_grid % 16 || (uintptr_t)a->rgba % 16) return fail(PLX_E_ALIGN, "grad_grid/rgba must be 16-byte aligned");
@@ -142,6 +155,8 @@ int plx_adam_step_peer(const PlxAdamPeer* a, void* stream) {
     }
     if ((uintptr_t)a->exp_avg % 16 || (uintptr_t)a->exp_avg_sq % 16 || (uintptr_t)a->grad_abs_sum % 16)
         return fail(PLX_E_ALIGN, "optimizer state must be 16-byte aligned");
+    int rc;
+    if ((rc = check_sync(a->sync, a->end > a->begin)) != PLX_OK) return rc;
     const plx::StepTail tail{a->loss_src, a->loss_clear, (float*)a->result_host, (int32_t)a->step, a->counter_clear};
     return cuda_result(plx::launch_adam_peer(*a, adam_scalars(a->lr, a->beta1, a->beta2, a->eps, a->step), tail, (cudaStream_t)stream),
                        "plx_adam_step_peer");
@@ -312,6 +327,10 @@ static int train_step_impl(const PlxTrainStep* a, const float* uv, void* result_
         t.grid = a->grid; t.grad_grid = a->grad; t.rgba = a->rgba; t.loss = loss_now;
         t.grad_scale = grad_scale; t.loss_scale = loss_scale; t.beta_over_m = a->beta_over_m;
         t.work_counter = a->work_counter;
+        if (a->render_sync) t.sync = *a->render_sync;
+        const bool synced = t.sync.wait_epoch > 0 || t.sync.signal_epoch > 0;
+        if (synced && !(allow_fused && a->img_h == a->img_w && plx::render_train_supported(t)))
+            return fail(PLX_E_UNSUPPORTED, "train step: render_sync needs the fused march (nearest mode, square images)");
         if (allow_fused && a->img_h == a->img_w && plx::render_train_supported(t)) {
             if ((rc = plx_render_train(&t, stream)) != PLX_OK) return rc;
         } else {

@@ -94,8 +94,10 @@ struct PeerPtrs {
 template <int UNROLL>
 __global__ void __launch_bounds__(256) k_adam_peer(PeerPtrs pp, int world, int world_st, float4* __restrict__ m, float4* __restrict__ v,
                                                    float4* __restrict__ ga, int64_t begin4, int64_t end4, const AdamScalars s,
-                                                   const StepTail tail) {
+                                                   const StepTail tail, const PlxPeerSync sync) {
     step_tail(tail);
+    peer_wait(sync);                         // every rank's partial gradient is complete
+    __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const FastDiv bc = make_fastdiv(s.bc2_sqrt);
     for (int64_t i0 = begin4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end4; i0 += stride * UNROLL) {
@@ -139,6 +141,10 @@ __global__ void __launch_bounds__(256) k_adam_peer(PeerPtrs pp, int world, int w
             }
         }
     }
+    if (sync.signal_epoch > 0) {             // this rank's slab is stored in every replica (and the peers' gradients are read)
+        __syncthreads();
+        if (threadIdx.x == 0) peer_signal(sync);
+    }
 }
 
 // NVLS variant: in-switch reduction of the partial gradients and in-switch replication of the new parameters
@@ -156,8 +162,11 @@ __device__ __forceinline__ void multimem_st(float4* mc, float4 v) {
 template <int UNROLL>
 __global__ void __launch_bounds__(256) k_adam_mc(const float4* __restrict__ p_local, float4* p_mc, const float4* g_mc,
                                                  float4* __restrict__ m, float4* __restrict__ v, float4* __restrict__ ga,
-                                                 int64_t begin4, int64_t end4, const AdamScalars s, const StepTail tail) {
+                                                 int64_t begin4, int64_t end4, const AdamScalars s, const StepTail tail,
+                                                 const PlxPeerSync sync) {
     step_tail(tail);
+    peer_wait(sync);                         // every rank's partial gradient is complete
+    __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const FastDiv bc = make_fastdiv(s.bc2_sqrt);
     for (int64_t i0 = begin4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end4; i0 += stride * UNROLL) {
@@ -191,6 +200,10 @@ __global__ void __launch_bounds__(256) k_adam_mc(const float4* __restrict__ p_lo
             }
         }
     }
+    if (sync.signal_epoch > 0) {             // this rank's slab is stored in every replica (and the peers' gradients are read)
+        __syncthreads();
+        if (threadIdx.x == 0) peer_signal(sync);
+    }
 }
 
 cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, const StepTail& tail, cudaStream_t st) {
@@ -220,7 +233,7 @@ cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, const S
             unsigned blocks = (unsigned)(want < resident ? want : resident);                                           \
             if (mc_blocks > 0 && (unsigned)mc_blocks < blocks) blocks = (unsigned)mc_blocks;                           \
             k_adam_mc<U><<<blocks, 256, 0, st>>>((const float4*)a.grids[a.rank], (float4*)a.grid_mc, (const float4*)a.grad_mc,   \
-                                                 (float4*)a.exp_avg, (float4*)a.exp_avg_sq, (float4*)a.grad_abs_sum, begin4, end4, s, tail); \
+                                                 (float4*)a.exp_avg, (float4*)a.exp_avg_sq, (float4*)a.grad_abs_sum, begin4, end4, s, tail, a.sync); \
         } while (0)
         if (unroll >= 4) PLX_MC(4); else if (unroll >= 2) PLX_MC(2); else PLX_MC(1);
 #undef PLX_MC
@@ -251,7 +264,7 @@ cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, const S
         const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);                                           \
         const unsigned blocks = (unsigned)(want < resident ? want : resident);                                       \
         k_adam_peer<U><<<blocks, 256, 0, st>>>(pp, dbg_ld ? dbg_ld : a.world, dbg_st ? dbg_st : a.world, (float4*)a.exp_avg, (float4*)a.exp_avg_sq,               \
-                                               (float4*)a.grad_abs_sum, begin4, end4, s, tail);                      \
+                                               (float4*)a.grad_abs_sum, begin4, end4, s, tail, a.sync);              \
     } while (0)
     if (unroll >= 4) PLX_PEER(4); else if (unroll >= 2) PLX_PEER(2); else PLX_PEER(1);
 #undef PLX_PEER

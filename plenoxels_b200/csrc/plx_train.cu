@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const PlxMarch& m = a.march;
     if (threadIdx.x == 0) { s_loss = 0.f; s_done = 0; }
+    peer_wait(a.sync);                       // multi-GPU: every peer has stored its slab of the previous step's parameters
     __syncthreads();                         // every warp arrives here at once: free
     float ray_loss = 0.f;
     int* lc = s_dyn + wib * warp_words;
@@ -257,11 +258,16 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
         ray_loss += this_loss;
         __syncwarp();                        // the per-warp shared-memory cache is reused by the next ray
     }
-    // ---- loss: shared-memory partial per block, the last warp to finish adds it to the global accumulator
-    if (a.loss && lane == 0) {
-        atomicAdd(&s_loss, ray_loss);
-        __threadfence_block();
-        if (atomicAdd(&s_done, 1) == wpb - 1) atomicAdd(a.loss, atomicAdd(&s_loss, 0.f));
+    // ---- loss: shared-memory partial per block, the last warp to finish adds it to the global accumulator; that warp
+    // also counts the block as done for the cross-GPU signal (its lanes' gradient reductions are ordered before lane 0's
+    // fence by the __syncwarp above, the other warps' by their own fence before they bump s_done)
+    if (lane == 0 && (a.loss || a.sync.signal_epoch > 0)) {
+        if (a.loss) atomicAdd(&s_loss, ray_loss);
+        if (a.sync.signal_epoch > 0) __threadfence(); else __threadfence_block();
+        if (atomicAdd(&s_done, 1) == wpb - 1) {
+            if (a.loss) atomicAdd(a.loss, atomicAdd(&s_loss, 0.f));
+            peer_signal(a.sync);
+        }
     }
 }
 

@@ -186,6 +186,10 @@ class VoxelTrainer:
                         "plx_train_step_host")
         return self.loss_host
 
+    def flush(self) -> None:
+        """Everything a step promised is complete once the stream is (single GPU / NCCL exchange): nothing to do here.
+        PeerVoxelTrainer overrides it."""
+
     def checkpoint(self, extra_param: dict | None = None) -> dict:
         """The reference's `.pth` payload (scripts/train.py:194-210): {grid, grid_grad, param{...}} on the CPU."""
         param = {"device": str(self.device), "number_of_rays": self.rays_per_cam, "num_samples": self.num_samples,
@@ -278,6 +282,21 @@ class PeerVoxelTrainer(VoxelTrainer):
         self._epoch = 0
         self._own_barrier = os.environ.get("PLX_PEER_BARRIER", "own") == "own"
         self._args = self._make_args()
+        # fused ordering (PlxPeerSync, opt-in with PLX_PEER_FUSED=1): the march signals "partial gradient complete"
+        # (channel 0) and waits for "all slabs of the previous step stored" (channel 1); the exchange kernel waits on 0 and
+        # signals 1.  No stand-alone barrier launches on the step; `flush()` (channel 2) is the full barrier before anyone
+        # reads a replica from outside.  Measured neutral (N=2: 123.7 vs 126.1 us/step, N=4: 150.3 vs 146.0): the two
+        # barrier launches were already hidden behind the kernels they order, what remains is waiting for the slowest
+        # rank — so the default stays the simpler contract (a finished stream = a complete replica).
+        self._fused = self._own_barrier and os.environ.get("PLX_PEER_FUSED", "0") == "1"
+        self._sync_counters = torch.zeros((2,), dtype=torch.int32, device=dev)
+        self._sync_render, self._sync_adam = L.PlxPeerSync(), L.PlxPeerSync()
+        for k, sy in enumerate((self._sync_render, self._sync_adam)):
+            for r in range(self.world):
+                sy.flags[r] = int(self._h_flags.buffer_ptrs[r])
+            sy.rank, sy.world = self.rank, self.world
+            sy.block_counter = self._sync_counters.data_ptr() + 4 * k
+        self._flush_epoch = 0
         slab = slab_range(self.grid.numel() // 4, self.rank, self.world)
         self.multicast = False
         self._peers = []
@@ -301,17 +320,26 @@ class PeerVoxelTrainer(VoxelTrainer):
             self._peers.append(p)
         self._peer = self._peers[0]
         self._cur = 0
-        self.launches_per_step = 2
+        self.launches_per_step = 2 if self._fused else (4 if self._own_barrier else 2)   # march, [barrier], exchange+Adam, [barrier]
         torch.cuda.synchronize(dev)
         dist.barrier(group)
 
-    def render_phase(self, uv=None) -> None:
+    def _select_buffer(self) -> None:
         b = self.step_count % 2                 # buffer of the step about to run
         self._cur = b
         self.grad = self._grads[b]
         self._args.grad = self.grad.data_ptr()
         if self._cleared[b] is not None:        # its clear (issued two steps ago on the side stream) must have finished
             torch.cuda.current_stream(self.device).wait_event(self._cleared[b])
+        if self._fused:
+            e = self._epoch + 1                 # this step's epoch (the exchange below advances self._epoch to it)
+            sy = self._sync_render
+            sy.wait_channel, sy.wait_epoch = 1, e - 1
+            sy.signal_channel, sy.signal_epoch = 0, e
+            self._args.render_sync = C.pointer(sy)
+
+    def render_phase(self, uv=None) -> None:
+        self._select_buffer()
         super().render_phase(uv)
 
     def _exchange_and_update(self, st, result_host=None):
@@ -325,8 +353,15 @@ class PeerVoxelTrainer(VoxelTrainer):
         peer.counter_clear = self._work_counter.data_ptr() if self._dynamic else None
         h = self._h_grads[b]
         self._epoch += 1
-        self._barrier(h, 0, st)                               # every rank's partial gradient is complete
-        # the buffer consumed by the PREVIOUS step (its readers passed that step's closing barrier) is cleared now, on
+        if self._fused:
+            sy = peer.sync
+            sy.flags, sy.rank, sy.world, sy.block_counter = self._sync_adam.flags, self.rank, self.world, self._sync_adam.block_counter
+            sy.wait_channel, sy.wait_epoch = 0, self._epoch
+            sy.signal_channel, sy.signal_epoch = 1, self._epoch
+        else:
+            self._barrier(h, 0, st)                           # every rank's partial gradient is complete
+        # the buffer consumed by the PREVIOUS step (its readers passed that step's closing barrier / signalled channel 1,
+        # which this step's march waited for) is cleared now, on
         # the side stream, behind this step's exchange kernel: that kernel is NVLink-bound and leaves HBM idle, whereas
         # clearing during the march (measured) slowed the march by as much as the clear itself takes
         if self._dirty is not None:
@@ -339,8 +374,24 @@ class PeerVoxelTrainer(VoxelTrainer):
                 ev.record(self._clear_stream)
             self._cleared[o] = ev
         L.check(self.lib.plx_adam_step_peer(C.byref(peer), st), "plx_adam_step_peer")
-        self._barrier(h, 1, st)                               # every replica holds the new parameters; peers done reading
+        if not self._fused:
+            self._barrier(h, 1, st)                           # every replica holds the new parameters; peers done reading
         self._dirty = b
+
+    def flush(self) -> None:
+        """Full cross-rank barrier on the stream: after it, this rank's replica holds every peer's slab of the latest step.
+        With the fused ordering a step only guarantees that to the NEXT step's march; call this before reading `grid`
+        from anywhere else (checkpoint, evaluation render, end of a timed region)."""
+        if not self._fused:
+            return
+        self._flush_epoch += 1
+        with torch.cuda.device(self.device):
+            L.check(self.lib.plx_peer_barrier(self._flag_ptrs, self.rank, self.world, 2, self._flush_epoch,
+                                              L.stream_ptr(self.device)), "plx_peer_barrier(flush)")
+
+    def checkpoint(self, extra_param=None) -> dict:
+        self.flush()
+        return super().checkpoint(extra_param)
 
     def _barrier(self, handle, channel, st):
         if self._own_barrier:
@@ -360,12 +411,7 @@ class PeerVoxelTrainer(VoxelTrainer):
     def step_host(self, uv_host):
         if uv_host.is_cuda or not uv_host.is_pinned() or uv_host.numel() != self.uv.numel():
             raise L.PlxError("uv_host must be a pinned float32 host tensor of shape (C,R,2)")
-        b = self.step_count % 2
-        self._cur = b
-        self.grad = self._grads[b]
-        self._args.grad = self.grad.data_ptr()
-        if self._cleared[b] is not None:
-            torch.cuda.current_stream(self.device).wait_event(self._cleared[b])
+        self._select_buffer()
         self._begin_step()
         st = L.stream_ptr(self.device)
         with torch.cuda.device(self.device):
@@ -376,6 +422,7 @@ class PeerVoxelTrainer(VoxelTrainer):
 
     def gathered_grad_abs_sum(self):
         """Full `grid_grad` (scripts/train.py:184): each rank accumulated |grad| for the cells it owns only."""
+        self.flush()
         full = self.grad_abs_sum.clone()
         b, e = self._peers[0].begin, self._peers[0].end
         flat = full.view(-1)

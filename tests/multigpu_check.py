@@ -53,6 +53,7 @@ def main():
     for step in range(4):
         u = synth.random_uv(C, R, seed=50 + step)[cams].to(dev)
         la, lb = ta.step(u).clone(), tb.step(u).clone()
+    tb.flush()
     torch.cuda.synchronize()
     dgrid = float((ta.grid - tb.grid).abs().max())
     q = float(torch.quantile((ta.grid - tb.grid).abs().flatten()[::7], 0.999))

@@ -44,17 +44,19 @@ def test_library_exports_every_declared_symbol(plx_lib):
 def test_ctypes_structs_match_c_layout(tmp_path):
     prog = tmp_path / "layout.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "plenoxel_abi.h"\nint main(){'
-                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(PlxMarch), sizeof(PlxRays), sizeof(PlxRenderFwd),'
+                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(PlxMarch), sizeof(PlxRays), sizeof(PlxRenderFwd),'
                     'sizeof(PlxRenderBwd), sizeof(PlxTrainStep), offsetof(PlxRenderFwd, loss), offsetof(PlxTrainStep, lr),'
                     'offsetof(PlxTrainStep, loss), sizeof(PlxRenderTrain), offsetof(PlxRenderTrain, beta_over_m),'
-                    'sizeof(PlxAdamPeer), offsetof(PlxAdamPeer, result_host));return 0;}')
+                    'sizeof(PlxAdamPeer), offsetof(PlxAdamPeer, result_host), sizeof(PlxPeerSync), offsetof(PlxPeerSync, block_counter),'
+                    'offsetof(PlxAdamPeer, sync), offsetof(PlxTrainStep, render_sync));return 0;}')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), str(prog), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(L.PlxMarch), C.sizeof(L.PlxRays), C.sizeof(L.PlxRenderFwd), C.sizeof(L.PlxRenderBwd),
             C.sizeof(L.PlxTrainStep), L.PlxRenderFwd.loss.offset, L.PlxTrainStep.lr.offset, L.PlxTrainStep.loss.offset,
             C.sizeof(L.PlxRenderTrain), L.PlxRenderTrain.beta_over_m.offset, C.sizeof(L.PlxAdamPeer),
-            L.PlxAdamPeer.result_host.offset]
+            L.PlxAdamPeer.result_host.offset, C.sizeof(L.PlxPeerSync), L.PlxPeerSync.block_counter.offset,
+            L.PlxAdamPeer.sync.offset, L.PlxTrainStep.render_sync.offset]
     assert got == want
 
 

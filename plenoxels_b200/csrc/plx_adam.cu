@@ -36,7 +36,7 @@ __device__ __forceinline__ void step_tail(const StepTail& t) {
     }
 }
 
-template <bool HAS_ABS, bool ZERO, int UNROLL>
+template <bool HAS_ABS, bool ZERO, int UNROLL, bool SKIP>
 __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                               float4* __restrict__ v, float4* __restrict__ ga, int64_t n4,
                                               const AdamScalars s, const StepTail tail) {
@@ -70,11 +70,14 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
                 st_hint(p + i, P[u], pol);
                 __stcs(m + i, M[u]);
                 __stcs(v + i, V[u]);
-                if (HAS_ABS) {
+                // a cell no ray touched this step has g == 0 exactly: |g| adds nothing and the gradient is already clear,
+                // so neither store is issued (about half the cells of a C2 step; saves their 32 B/cell of write-back)
+                const bool touched = !SKIP || G[u].x != 0.f || G[u].y != 0.f || G[u].z != 0.f || G[u].w != 0.f;
+                if (HAS_ABS && touched) {
                     A[u].x += fabsf(G[u].x); A[u].y += fabsf(G[u].y); A[u].z += fabsf(G[u].z); A[u].w += fabsf(G[u].w);
                     __stcs(ga + i, A[u]);
                 }
-                if (ZERO) st_hint(g + i, make_float4(0.f, 0.f, 0.f, 0.f), pol_g);
+                if (ZERO && touched) st_hint(g + i, make_float4(0.f, 0.f, 0.f, 0.f), pol_g);
             }
         }
     }
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(256) k_adam_peer(PeerPtrs pp, int world, int w
                     if (r < world_st) pp.grids[r][i] = P[u];
                 __stcs(m + i, M[u]);
                 __stcs(v + i, V[u]);
-                if (ga) {
+                if (ga && (G[u].x != 0.f || G[u].y != 0.f || G[u].z != 0.f || G[u].w != 0.f)) {     // untouched cell: |g| adds nothing
                     A[u].x += fabsf(G[u].x); A[u].y += fabsf(G[u].y); A[u].z += fabsf(G[u].z); A[u].w += fabsf(G[u].w);
                     __stcs(ga + i, A[u]);
                 }
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(256) k_adam_mc(const float4* __restrict__ p_lo
                 multimem_st(p_mc + i, P[u]);
                 __stcs(m + i, M[u]);
                 __stcs(v + i, V[u]);
-                if (ga) {
+                if (ga && (G[u].x != 0.f || G[u].y != 0.f || G[u].z != 0.f || G[u].w != 0.f)) {     // untouched cell: |g| adds nothing
                     A[u].x += fabsf(G[u].x); A[u].y += fabsf(G[u].y); A[u].z += fabsf(G[u].z); A[u].w += fabsf(G[u].w);
                     __stcs(ga + i, A[u]);
                 }
@@ -312,11 +315,11 @@ __global__ void k_adam_scalar(float* p, float* g, float* m, float* v, float* ga,
     }
 }
 
-template <bool HAS_ABS, bool ZERO, int UNROLL>
-static cudaError_t launch_adam_vec(float4* p, float4* g, float4* m, float4* v, float4* ga, int64_t n4, const AdamScalars& s,
-                                   int blocks_per_sm_cap, const StepTail& tail, cudaStream_t st) {
+template <bool HAS_ABS, bool ZERO, int UNROLL, bool SKIP>
+static cudaError_t launch_adam_vec2(float4* p, float4* g, float4* m, float4* v, float4* ga, int64_t n4, const AdamScalars& s,
+                                    int blocks_per_sm_cap, const StepTail& tail, cudaStream_t st) {
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adam<HAS_ABS, ZERO, UNROLL>, 256, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adam<HAS_ABS, ZERO, UNROLL, SKIP>, 256, 0);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -326,8 +329,17 @@ static cudaError_t launch_adam_vec(float4* p, float4* g, float4* m, float4* v, f
     int64_t want = (n4 + 256 * UNROLL - 1) / (256 * UNROLL);
     const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
     const unsigned blocks = (unsigned)(want < resident ? want : resident);
-    k_adam<HAS_ABS, ZERO, UNROLL><<<blocks, 256, 0, st>>>(p, g, m, v, ga, n4, s, tail);
+    k_adam<HAS_ABS, ZERO, UNROLL, SKIP><<<blocks, 256, 0, st>>>(p, g, m, v, ga, n4, s, tail);
     return cudaGetLastError();
+}
+
+template <bool HAS_ABS, bool ZERO, int UNROLL>
+static cudaError_t launch_adam_vec(float4* p, float4* g, float4* m, float4* v, float4* ga, int64_t n4, const AdamScalars& s,
+                                   int blocks_per_sm_cap, const StepTail& tail, cudaStream_t st) {
+    // skipping the |g| / clear stores of untouched cells only matters where either store exists
+    static const bool skip = adam_env("PLX_ADAM_SKIP", 1) != 0;
+    if ((HAS_ABS || ZERO) && skip) return launch_adam_vec2<HAS_ABS, ZERO, UNROLL, true>(p, g, m, v, ga, n4, s, blocks_per_sm_cap, tail, st);
+    return launch_adam_vec2<HAS_ABS, ZERO, UNROLL, false>(p, g, m, v, ga, n4, s, blocks_per_sm_cap, tail, st);
 }
 
 __global__ void k_step_tail_only(const StepTail tail) { step_tail(tail); }

@@ -130,6 +130,8 @@ static plx::AdamScalars adam_scalars(double lr, double beta1, double beta2, doub
     s.eps = (float)eps;
     s.neg_step_size = (float)(-(lr / bc1));
     s.keep_p = s.keep_g = false;
+    s.reverse = (step & 1) != 0;
+    s.stream_state = true;
     return s;
 }
 

@@ -45,37 +45,39 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
     const FastDiv bc = make_fastdiv(s.bc2_sqrt);
     // parameters and gradient are re-used by the march of the next step: keep them in L2 when they fit (plx_device.cuh)
     const uint64_t pol = l2_policy(s.keep_p), pol_g = l2_policy(s.keep_g);
+    const bool rev = s.reverse, cs = s.stream_state;
     for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * UNROLL) {
         float4 P[UNROLL], G[UNROLL], M[UNROLL], V[UNROLL], A[UNROLL];
         // all loads of the iteration are issued before the first use: 5 * UNROLL independent 16-byte requests per thread
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const int64_t i = i0 + u * stride;
-            if (i < n4) {
+            const int64_t k = i0 + u * stride;
+            if (k < n4) {
+                const int64_t i = rev ? n4 - 1 - k : k;
                 P[u] = ld_hint(p + i, pol);
                 G[u] = ld_hint(g + i, pol_g);
-                M[u] = __ldcs(m + i);
-                V[u] = __ldcs(v + i);
-                if (HAS_ABS) A[u] = __ldcs(ga + i);
+                M[u] = cs ? __ldcs(m + i) : m[i];
+                V[u] = cs ? __ldcs(v + i) : v[i];
+                if (HAS_ABS) A[u] = cs ? __ldcs(ga + i) : ga[i];
             }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const int64_t i = i0 + u * stride;
-            if (i < n4) {
+            const int64_t k = i0 + u * stride;
+            if (k < n4) {
+                const int64_t i = rev ? n4 - 1 - k : k;
                 adam1(P[u].x, G[u].x, M[u].x, V[u].x, s, bc);
                 adam1(P[u].y, G[u].y, M[u].y, V[u].y, s, bc);
                 adam1(P[u].z, G[u].z, M[u].z, V[u].z, s, bc);
                 adam1(P[u].w, G[u].w, M[u].w, V[u].w, s, bc);
                 st_hint(p + i, P[u], pol);
-                __stcs(m + i, M[u]);
-                __stcs(v + i, V[u]);
+                if (cs) { __stcs(m + i, M[u]); __stcs(v + i, V[u]); } else { m[i] = M[u]; v[i] = V[u]; }
                 // a cell no ray touched this step has g == 0 exactly: |g| adds nothing and the gradient is already clear,
                 // so neither store is issued (about half the cells of a C2 step; saves their 32 B/cell of write-back)
                 const bool touched = !SKIP || G[u].x != 0.f || G[u].y != 0.f || G[u].z != 0.f || G[u].w != 0.f;
                 if (HAS_ABS && touched) {
                     A[u].x += fabsf(G[u].x); A[u].y += fabsf(G[u].y); A[u].z += fabsf(G[u].z); A[u].w += fabsf(G[u].w);
-                    __stcs(ga + i, A[u]);
+                    if (cs) __stcs(ga + i, A[u]); else ga[i] = A[u];
                 }
                 if (ZERO && touched) st_hint(g + i, make_float4(0.f, 0.f, 0.f, 0.f), pol_g);
             }
@@ -349,10 +351,13 @@ cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int
     if (n == 0) return cudaSuccess;
     AdamScalars s = s_in;
     {
-        static const int mode = adam_env("PLX_L2_KEEP", 0);
+        static const int mode = adam_env("PLX_L2_KEEP", 2);
         const bool fits = l2_keep_ok(n / 4);
         s.keep_p = fits && mode != 0;
         s.keep_g = fits && mode == 1;
+        static const int pingpong = adam_env("PLX_ADAM_PINGPONG", 1), cs = adam_env("PLX_ADAM_CS", 1);
+        s.reverse = s.reverse && pingpong != 0;
+        s.stream_state = cs != 0;
     }
     const bool aligned = ((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                          ((uintptr_t)v % 16 == 0) && (!gabs || (uintptr_t)gabs % 16 == 0);

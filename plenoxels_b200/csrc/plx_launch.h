@@ -23,6 +23,8 @@ struct AdamScalars {
     float eps;
     float neg_step_size;     // -lr / (1 - beta1^step)
     bool keep_p, keep_g;     // L2 evict_last tags for parameters / gradient (set by launch_adam)
+    bool reverse;            // walk the arrays from the top down (odd steps): the tail the previous step left in L2 is read first
+    bool stream_state;       // m / v / |g| with evict-first (.cs) accesses
 };
 // what one thread of the optimiser kernel does besides Adam: publish this step's loss to pinned host memory
 // { float loss; int32 step } and clear the other loss slot for the next step

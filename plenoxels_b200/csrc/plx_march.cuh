@@ -202,7 +202,7 @@ __device__ __forceinline__ Sample lookup(const PlxMarch& m, const Geo& g, const 
 
 // host side: which of grid / gradient get the evict_last tag for this launch (PLX_L2_KEEP: 0 none, 1 both, 2 grid only)
 static inline uint32_t l2_keep_flags(const PlxMarch& m) {
-    static const int mode = [] { const char* e = std::getenv("PLX_L2_KEEP"); return e ? std::atoi(e) : 0; }();
+    static const int mode = [] { const char* e = std::getenv("PLX_L2_KEEP"); return e ? std::atoi(e) : 2; }();
     if (mode == 0 || !l2_keep_ok((int64_t)m.nx * m.ny * m.nz)) return 0;
     return mode == 2 ? PLX_FLAG_KEEP_GRID : (PLX_FLAG_KEEP_GRID | PLX_FLAG_KEEP_GRAD);
 }

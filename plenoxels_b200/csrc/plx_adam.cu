@@ -364,10 +364,10 @@ cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int
     const int64_t n4 = aligned ? n / 4 : 0;
     const int threads = 256;
     static const int unroll = adam_env("PLX_ADAM_UNROLL", 1);
-    // resident 256-thread blocks per SM, measured: 128^3 (state partly L2-resident) 4 -> 52.0 us, 3 -> 57.9, 5 -> 53.0;
-    // 256^3 (pure HBM streaming) 3 -> 450 us (0.92 of peak), 4 -> 467, 5 -> 466, 2 -> 520
+    // resident 256-thread blocks per SM, measured with the store skipping / alternating walk in place: 128^3 4 -> 88.6 us per
+    // step, 5 / 6 -> 88.5 (flat); 256^3 3 -> 424 us, 4 -> 410, 5 -> 410
     static const int cap_env = adam_env("PLX_ADAM_BLOCKS_PER_SM", 0);
-    const int cap = cap_env > 0 ? cap_env : (n4 >= (int64_t(1) << 23) ? 3 : 4);
+    const int cap = cap_env > 0 ? cap_env : 4;
     if (n4 > 0) {
         cudaError_t e;
 #define PLX_ADAM_V(U)                                                                                                         \

@@ -60,11 +60,15 @@ __global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain
     // there is no partial last wave); without one, ray = block * warps + warp.
     int64_t ray = (int64_t)blockIdx.x * wpb + wib;
     const int64_t static_stride = (int64_t)gridDim.x * wpb;
+    // dynamic mode: every ray is a ticket drawn from the counter, and the ticket for the NEXT ray is drawn before the current
+    // ray is processed, so the atomic's round trip (~1 us) is hidden behind the march instead of stalling the warp
+    // between rays (a warp stops at its first ticket >= n_rays without drawing another: no ticket is ever dropped)
+    int ticket = 0;
+    if (a.work_counter && lane == 0) ticket = atomicAdd(a.work_counter, 1);
     for (bool first = true;; first = false) {
         if (a.work_counter) {
-            int claimed = 0;
-            if (lane == 0) claimed = atomicAdd(a.work_counter, 1);
-            ray = __shfl_sync(FULL, claimed, 0);
+            ray = __shfl_sync(FULL, ticket, 0);
+            if (lane == 0 && ray < a.rays.n_rays) ticket = atomicAdd(a.work_counter, 1);
         } else if (!first) {
             ray += static_stride;
         }

@@ -113,11 +113,12 @@ def sample_indices(grid, origins, dirs, num_samples, delta_step, gmin, points_di
 
 def render_train(grid, grad_grid, num_samples, delta_step, gmin, points_distance, *, origins=None, dirs=None,
                  targets=None, rays_per_origin=1, imgs=None, poses=None, fov=None, uv=None, n_rays_global=None,
-                 beta_over_m=0.0, clamp=True):
+                 beta_over_m=0.0, clamp=True, dynamic=False):
     """K12, the fused training march (nearest lookup): forward + mean-MSE + backward in one kernel; the gradient is
     ACCUMULATED into `grad_grid` (contiguous (X,Y,Z,4)).  Rays are either given (`origins`, `dirs`, `targets`) or
     generated in the kernel from (`imgs`, `poses`, `fov`, `uv` (C,R,2)).  Returns (rgba (N,4), loss (1,) device tensor)
-    = the pixels and mean((rgba - targets)^2) of scripts/train.py:151-156."""
+    = the pixels and mean((rgba - targets)^2) of scripts/train.py:151-156.  `dynamic`: rays are claimed from a device
+    counter by the warps of a one-wave grid (PlxRenderTrain.work_counter) instead of the static block -> ray mapping."""
     dev = L.require_cuda(grid, grad_grid, origins, dirs, targets, imgs, poses, uv)
     lib = L.load()
     a = L.PlxRenderTrain()
@@ -145,6 +146,10 @@ def render_train(grid, grad_grid, num_samples, delta_step, gmin, points_distance
     loss = torch.zeros((1,), dtype=torch.float32, device=dev)
     a.grid, a.grad_grid, a.rgba, a.loss = grid.data_ptr(), grad_grid.data_ptr(), rgba.data_ptr(), loss.data_ptr()
     a.grad_scale, a.loss_scale, a.beta_over_m = 2.0 / (4.0 * n_glob), 1.0 / (4.0 * n_glob), float(beta_over_m)
+    if dynamic:
+        counter = torch.zeros((1,), dtype=torch.int32, device=dev)
+        keep.append(counter)
+        a.work_counter = counter.data_ptr()
     with torch.cuda.device(dev):
         L.check(lib.plx_render_train(C.byref(a), L.stream_ptr(dev)), "plx_render_train")
     return rgba, loss

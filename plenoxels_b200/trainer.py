@@ -78,7 +78,7 @@ class VoxelTrainer:
         # work counter of the fused march (rays are claimed dynamically by the warps of a one-wave grid); the optimiser
         # kernel resets it every step.  Opt-in (PLX_TRAIN_DYNAMIC=1): the hardware block scheduler balanced C2 better.
         self._work_counter = torch.zeros((1,), dtype=torch.int32, device=dev)
-        self._dynamic = os.environ.get("PLX_TRAIN_DYNAMIC", "0") == "1"      # measured slower on C2 (53.7 vs 47.7 us): off
+        self._dynamic = os.environ.get("PLX_TRAIN_DYNAMIC", "0") == "1"      # measured slower on C2 (61 vs 48 us, even with the ticket drawn one ray ahead): off
         self.loss = self._loss2[1:2]                                   # view of the slot of the latest step
         # pinned { float loss; int32 step } the optimiser kernel publishes to on the host path
         self.result_host = torch.zeros((2,), dtype=torch.float32).pin_memory()

@@ -374,6 +374,9 @@ def run_gpu_arm(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
                 "kernel_ms": kms, "kernel_gbs": {k: alg[k] / (v * 1e-3) / 1e9 for k, v in timed.items()},
+                "note": "algorithmic bytes follow SURVEY.md 8d (160 B/cell for the optimiser); K3 does not store |grad| nor "
+                        "re-clear the gradient of cells no ray touched this step (32 of those 160 B/cell), so its moved bytes "
+                        "(traffic) are below the model and its fraction can exceed 1",
                 "step": {"algorithmic_bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak,
                          "model": "64*M_in + 96*N + 160*cells", "m_in": m_in, "n_rays": n_rays, "cells": cells}}
 

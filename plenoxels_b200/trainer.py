@@ -7,14 +7,19 @@ GLOBAL ray count so a plain SUM reproduces the single-GPU mean-MSE gradient exac
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
+import weakref
 
 import torch
 import torch.distributed as dist
 
 from . import _lib as L
 from . import ops
+
+
+_NO_CONTEXT = contextlib.nullcontext()
 
 
 def shard_cameras(n_cams: int, rank: int, world: int) -> range:
@@ -85,6 +90,9 @@ class VoxelTrainer:
         self.loss_host = self.result_host[:1]
         self._result_f32 = self.result_host.numpy()
         self._result_i32 = self._result_f32.view("int32")
+        self._result_ptr = self.result_host.data_ptr()
+        self._dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        self._uv_host_ok = {}
         self._args = self._make_args()
         self.launches_per_step = 4        # generate_rays, render_fwd, render_bwd, adam (memset/memcpy are not kernels)
 
@@ -164,17 +172,30 @@ class VoxelTrainer:
             pass
         return float(self._result_f32[0])
 
+    def _check_uv_host(self, uv_host: torch.Tensor) -> None:
+        """Pinned, contiguous fp32 (C,R,2) on the host.  `is_pinned()` is a driver query, so a tensor object that passed once
+        is remembered (by identity, through a weak reference) and not asked again on every step."""
+        ref = self._uv_host_ok.get(id(uv_host))
+        if ref is not None and ref() is uv_host:
+            return
+        if uv_host.is_cuda or uv_host.dtype != torch.float32 or not uv_host.is_contiguous() or \
+                uv_host.numel() != self.uv.numel() or not uv_host.is_pinned():
+            raise L.PlxError("uv_host must be a pinned, contiguous float32 host tensor of shape (C,R,2)")
+        if len(self._uv_host_ok) > 64:
+            self._uv_host_ok.clear()
+        self._uv_host_ok[id(uv_host)] = weakref.ref(uv_host)
+
     def step_host(self, uv_host: torch.Tensor) -> torch.Tensor:
         """End-to-end step from HOST memory: the march reads this step's uv straight out of pinned `uv_host` (C,R,2)
         (zero-copy) and the optimiser kernel publishes {loss, step} into pinned `self.result_host`; two kernel launches,
         asynchronous.  Read the loss with `wait_result()` (or synchronise the stream and read `self.loss_host`)."""
-        if uv_host.is_cuda or uv_host.dtype != torch.float32 or not uv_host.is_contiguous() or \
-                uv_host.numel() != self.uv.numel() or not uv_host.is_pinned():
-            raise L.PlxError("uv_host must be a pinned, contiguous float32 host tensor of shape (C,R,2)")
+        self._check_uv_host(uv_host)
         self._begin_step()
         st = L.stream_ptr(self.device)
-        res = self.result_host.data_ptr()
-        with torch.cuda.device(self.device):
+        res = self._result_ptr
+        # the host is on the critical path here (it may only issue step t+1 once it has read the loss of step t): no device
+        # context switch when this trainer's device is already current
+        with (_NO_CONTEXT if torch.cuda.current_device() == self._dev_index else torch.cuda.device(self.device)):
             if self._distributed():
                 L.check(self.lib.plx_train_step_host(C.byref(self._args), uv_host.data_ptr(), res, L.PLX_STEP_RENDER, st),
                         "plx_train_step_host(render)")
@@ -409,8 +430,7 @@ class PeerVoxelTrainer(VoxelTrainer):
         return self.loss
 
     def step_host(self, uv_host):
-        if uv_host.is_cuda or not uv_host.is_pinned() or uv_host.numel() != self.uv.numel():
-            raise L.PlxError("uv_host must be a pinned float32 host tensor of shape (C,R,2)")
+        self._check_uv_host(uv_host)
         self._select_buffer()
         self._begin_step()
         st = L.stream_ptr(self.device)

@@ -24,6 +24,7 @@ _ref_src = types.ModuleType("src")
 _ref_src.__path__ = [os.path.join(REF, "src")]
 sys.modules["src"] = _ref_src
 
+from oracle import c_oracle as co              # noqa: E402
 from oracle import plenoxel_oracle as po      # noqa: E402
 from oracle import torch_port as tp           # noqa: E402
 from plenoxels_b200 import synth              # noqa: E402
@@ -125,6 +126,26 @@ def run_scene(tag, G, C, H, R, S, delta, kind, mode="nearest"):
     gerr = np.abs(grad - gref).max() / np.abs(gref).max()
     check(f"{tag}: grid gradient <= 1e-6 rel (hand-derived reverse recurrence vs reference autograd)",
           gerr <= 1e-6, f"rel err {gerr:.2e}, nonzero cells {int((np.abs(gref).sum(-1) > 0).sum())}")
+
+    # ---- C oracle (oracle/plenoxel_oracle.c): the same quantities straight against the live reference
+    dirs_c, targets_c, _ = co.generate_rays(imgs.numpy(), poses.numpy(), fov, uv.numpy())
+    check(f"{tag}: C dirs bit-exact", np.array_equal(dirs_c, ref["dirs"].numpy()))
+    check(f"{tag}: C targets bit-exact", np.array_equal(targets_c, ref["targets"].numpy()))
+    rgba_c, _, count_c, lin_c = co.render_forward(grid.numpy(), o, d_ref, S, delta, gmin, pd, mode)
+    check(f"{tag}: C in-bounds mask / counts equal", np.array_equal((lin_c >= 0).reshape(-1), ref["inb"].numpy()) and
+          np.array_equal(count_c, ref["inb"].reshape(N, S).sum(1).numpy().astype(np.int32)))
+    if mode == "nearest":
+        ridx = ref["idx"].numpy().reshape(N, S, 3)
+        rlin = (ridx[..., 0] * grid.shape[1] + ridx[..., 1]) * grid.shape[2] + ridx[..., 2]
+        check(f"{tag}: C linear indices bit-exact", np.array_equal(lin_c[lin_c >= 0], rlin[lin_c >= 0]))
+    cerr = np.abs(rgba_c - ref["pix"].numpy()).max() / scale
+    check(f"{tag}: C pixels <= 1e-6 rel (and == numpy oracle: {np.array_equal(rgba_c, rgba)})", cerr <= 1e-6 and np.array_equal(rgba_c, rgba),
+          f"rel err {cerr:.2e}")
+    loss_c, gpix_c = co.mse_loss(rgba_c, ref["targets"].numpy())
+    grad_c = co.render_backward(grid.numpy(), o, d_ref, S, delta, gmin, pd, gpix_c, mode)
+    gcerr = np.abs(grad_c - gref).max() / np.abs(gref).max()
+    check(f"{tag}: C loss / grid gradient <= 1e-6 rel", abs(loss_c - float(ref["loss"])) <= 1e-6 * abs(float(ref["loss"])) and
+          gcerr <= 1e-6, f"grad rel err {gcerr:.2e}")
 
     # ---- torch port (what the cpu_baseline / --impl reference legs time)
     port = tp.ReferenceStep(grid, pd, poses, fov, imgs, R, S, delta, lr=0.0075, mode=mode)

@@ -1,0 +1,128 @@
+"""The plain-C restatement (oracle/plenoxel_oracle.c) against the reference's golden vectors and against the numpy oracle.
+
+Three statements of the same algorithm now have to agree: the reference (frozen in tests/golden/*.npz), the numpy oracle
+and the C oracle.  Bit-exact: ray directions, target pixels, linear indices, masks, counts, pixels and depth (C vs numpy),
+Adam state.  Summation order only (1e-12): the float64 gradients.  1e-6: pixels / loss / gradient against the reference.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import plenoxel_oracle as po
+from plenoxels_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+STEP_CASES = ["nn_dense_g24", "nn_ball_g32", "tri_ball_g24", "tri_dense_g16"]
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, f"{name}.npz"))
+
+
+def test_library_builds_and_loads():
+    assert os.path.exists(co.build())
+    assert co.load().plxo_version() == 1
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_c_oracle_step_matches_reference_golden(name):
+    z = load(name)
+    mode, S, R = str(z["mode"]), int(z["S"]), int(z["R"])
+    grid, poses, imgs, uv = z["grid"], z["poses"], z["imgs"], z["uv"]
+    pd, delta, fov = float(z["pd"]), float(z["delta"]), float(z["fov"])
+    gmin = z["gmin"]
+    dirs, targets, _ = co.generate_rays(imgs, poses, fov, uv)
+    assert np.array_equal(dirs, z["dirs"]), "ray directions must be bit-exact against the reference"
+    assert np.array_equal(targets, z["targets"])
+    o = np.repeat(poses[:, :3, 3], R, axis=0)
+    rgba, depth, count, lin = co.render_forward(grid, o, dirs, S, delta, gmin, pd, mode)
+    assert np.array_equal(lin >= 0, z["inb"])
+    assert np.array_equal(count, z["inb"].sum(1).astype(np.int32))
+    if mode == "nearest":
+        assert np.array_equal(lin.astype(np.int32), z["lin"]), "nearest-neighbour linear indices must be bit-exact"
+    assert np.abs(rgba - z["pix"]).max() <= 1e-6 * np.abs(z["pix"]).max()
+    loss, gpix = co.mse_loss(rgba, targets)
+    assert abs(loss - float(z["loss"])) <= 1e-6 * float(z["loss"])
+    grad = co.render_backward(grid, o, dirs, S, delta, gmin, pd, gpix, mode)
+    assert np.abs(grad - z["grad"]).max() <= 1e-6 * np.abs(z["grad"]).max()
+
+
+@pytest.mark.parametrize("mode", ["nearest", "trilinear"])
+@pytest.mark.parametrize("clamp", [True, False])
+def test_c_oracle_equals_numpy_oracle(mode, clamp):
+    G, C_, R, S = 20, 3, 40, 56
+    pd, delta = synth.GRID_EXTENT / G, 6.0 / S
+    grid = synth.dense_grid(G, seed=3)[:, :19, :17].numpy().copy()           # non-cubic, values in [-0.2, 1.2]
+    poses, imgs, uv = synth.lookat_poses(C_).numpy(), synth.random_images(C_, 12, 12, seed=4).numpy(), synth.random_uv(C_, R, seed=5).numpy()
+    gmin = po.grid_origin(grid.shape[:3], pd)
+    dn, tn, pn = po.generate_rays(imgs, poses, synth.CAMERA_ANGLE_X, uv)
+    dc, tc, pc = co.generate_rays(imgs, poses, synth.CAMERA_ANGLE_X, uv)
+    assert np.array_equal(dn, dc) and np.array_equal(tn, tc) and np.array_equal(pn, pc)
+    o = np.repeat(poses[:, :3, 3], R, axis=0)
+    rn, depn, cn, ln = po.render_forward(grid, o, dn, S, delta, gmin, pd, mode, clamp)
+    rc, depc, cc, lc = co.render_forward(grid, o, dn, S, delta, gmin, pd, mode, clamp)
+    assert np.array_equal(ln, lc) and np.array_equal(cn, cc)
+    assert np.array_equal(rn, rc), "pixels: same fp32 operations in the same order"
+    assert np.array_equal(depn, depc)
+    lossn, gn = po.mse_loss(rn, tn, n_global=2 * o.shape[0])
+    lossc, gc = co.mse_loss(rc, tc, n_global=2 * o.shape[0])
+    assert abs(lossn - lossc) <= 1e-12 * lossn and np.array_equal(gn, gc)      # loss: summation order only
+    for beta in (0.0, 5e-3):
+        bn = po.render_backward(grid, o, dn, S, delta, gmin, pd, gn, mode, clamp, beta)
+        bc = co.render_backward(grid, o, dn, S, delta, gmin, pd, gn, mode, clamp, beta)
+        assert np.abs(bn - bc).max() <= 1e-12 * np.abs(bn).max()
+
+
+def test_c_oracle_adam_is_bit_identical_to_numpy_oracle_and_matches_torch_golden():
+    z = load("adam3")
+    p, m, v, ga = z["p0"].copy(), np.zeros_like(z["p0"]), np.zeros_like(z["p0"]), np.zeros_like(z["p0"])
+    pn, mn, vn, gan = p.copy(), m.copy(), v.copy(), ga.copy()
+    for step in range(1, 4):
+        g = z["grads"][step - 1]
+        p, m, v, ga = co.adam_step(p, g, m, v, ga, float(z["lr"]), step)
+        pn, mn, vn, gan = po.adam_step(pn, g, mn, vn, gan, float(z["lr"]), step)
+        assert np.array_equal(p, pn) and np.array_equal(m, mn) and np.array_equal(v, vn) and np.array_equal(ga, gan)
+        # torch-CPU's sqrt is not correctly rounded (see the numpy oracle): parameters agree to 1 ulp, moments exactly
+        assert np.abs(p - z["params"][step - 1]).max() <= 2e-7
+    assert np.array_equal(m, z["exp_avg"]) and np.array_equal(v, z["exp_avg_sq"]) and np.array_equal(ga, z["gabs"])
+
+
+def test_c_oracle_whole_steps_equal_numpy_oracle():
+    G, C_, R, S = 16, 2, 32, 48
+    pd, delta = synth.GRID_EXTENT / G, 6.0 / S
+    grid = synth.ball_grid(G, seed=8).numpy().copy()
+    poses, imgs = synth.lookat_poses(C_).numpy(), synth.random_images(C_, 10, 10, seed=9).numpy()
+    gmin = po.grid_origin(grid.shape[:3], pd)
+    o = np.repeat(poses[:, :3, 3], R, axis=0)
+    sn = [grid.copy(), np.zeros_like(grid), np.zeros_like(grid), np.zeros_like(grid)]
+    sc = [a.copy() for a in sn]
+    for step in range(1, 4):
+        uv = synth.random_uv(C_, R, seed=20 + step).numpy()
+        dirs, targets, _ = po.generate_rays(imgs, poses, synth.CAMERA_ANGLE_X, uv)
+        ln, gn, *sn = po.train_step(*sn, o, dirs, targets, S, delta, gmin, pd, 0.0075, step)
+        lc, gc, *sc = co.train_step(*sc, o, dirs, targets, S, delta, gmin, pd, 0.0075, step)
+        assert abs(ln - lc) <= 1e-12 * abs(ln)
+        assert np.abs(gn - gc).max() <= 1e-12 * np.abs(gn).max()
+        # the fp32 cast of the float64 gradient may differ in the last bit between the two summation orders; Adam's first
+        # steps move every touched cell by ~lr * sign(g), so compare the state to 1e-6 instead of bitwise
+        for a, b in zip(sn, sc):
+            assert np.quantile(np.abs(a - b), 0.999) <= 1e-6
+
+
+def test_c_oracle_full_baseline_size_finishes_in_seconds():
+    """BASELINE config #2 geometry at full size (12 800 rays x 600 samples, 128^3): what the numpy oracle only subsamples."""
+    sc = synth.make_scene("c2", H=8)
+    uv = synth.random_uv(sc.poses.shape[0], sc.rays_per_cam, seed=77).numpy()
+    dirs, _, _ = co.generate_rays(sc.imgs.numpy(), sc.poses.numpy(), sc.fov, uv)
+    o = np.repeat(sc.poses.numpy()[:, :3, 3], sc.rays_per_cam, axis=0)
+    gmin = po.grid_origin(sc.grid.shape[:3], sc.points_distance)
+    rgba, depth, count, lin = co.render_forward(sc.grid.numpy(), o, dirs, sc.num_samples, sc.delta_step, gmin, sc.points_distance)
+    assert rgba.shape == (12800, 4) and lin.shape == (12800, 600)
+    frac = (lin >= 0).mean()
+    assert 0.3 < frac < 0.6, f"in-bounds fraction {frac}"
+    # every 97th ray against the numpy oracle, bit for bit
+    sel = np.arange(0, 12800, 97)
+    rn, dn, cn, ln = po.render_forward(sc.grid.numpy(), o[sel], dirs[sel], sc.num_samples, sc.delta_step, gmin, sc.points_distance)
+    assert np.array_equal(ln, lin[sel]) and np.array_equal(cn, count[sel]) and np.array_equal(rn, rgba[sel]) and np.array_equal(dn, depth[sel])

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import c_oracle as co
 from oracle import plenoxel_oracle as po
 from plenoxels_b200 import ops, synth
 from tests.helpers import rel_err
@@ -136,3 +137,26 @@ def test_transparent_grid_renders_exactly_zero_and_only_alpha_gets_gradient(full
     torch.nn.functional.mse_loss(rgba, full.targets).backward()
     assert float(g.grad[..., :3].abs().max()) == 0.0, "d colour = alpha * T * g_rgb = 0 exactly"
     assert float(g.grad[..., 3].abs().max()) > 0.0
+
+
+def test_every_ray_of_the_full_batch_matches_the_c_oracle(full):
+    """No subsampling: the plain-C oracle (oracle/plenoxel_oracle.c, bit-identical to the numpy one) restates the whole
+    batch in a fraction of a second, so indices and counts are compared bit for bit for EVERY sample of EVERY ray, and
+    pixels, depth, loss and the grid gradient of the fused training march within the 1e-5 bar."""
+    grid = full.sc.grid.numpy()
+    o = np.repeat(full.sc.poses[:, :3, 3].numpy(), full.R, axis=0)
+    d = full.dirs.cpu().numpy()
+    gmin, pd, delta = np.float32(full.gmin), full.sc.points_distance, full.sc.delta_step
+    rgba_o, depth_o, count_o, lin_o = co.render_forward(grid, o, d, full.S, delta, gmin, pd)
+    idx, count = ops.sample_indices(full.grid, full.origins, full.dirs, full.S, delta, full.gmin, pd, rays_per_origin=full.R)
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), lin_o), "linear indices of all samples, bit-exact"
+    assert np.array_equal(count.cpu().numpy(), count_o)
+    rgba, depth = full.render(return_depth=True)
+    assert rel_err(rgba.cpu().numpy(), rgba_o) <= 1e-5
+    assert rel_err(depth.cpu().numpy(), depth_o) <= 1e-5
+    rgba_f, loss_f, grad_f = full.train()
+    loss_o, gpix = co.mse_loss(rgba_o, full.targets.cpu().numpy())
+    grad_o = co.render_backward(grid, o, d, full.S, delta, gmin, pd, gpix)
+    assert rel_err(rgba_f.cpu().numpy(), rgba_o) <= 1e-5
+    assert abs(float(loss_f) - loss_o) <= 1e-5 * loss_o
+    assert rel_err(grad_f.cpu().numpy(), grad_o) <= 1e-5

@@ -154,6 +154,34 @@ def time_reference_port(sc: synth.Scene, uvs, steps: int, warmup: int, budget_s:
             "subsampled": cams is not None}
 
 
+def time_c_port(sc: synth.Scene, uvs, steps: int, warmup: int):
+    """The same step through the plain-C restatement (oracle/plenoxel_oracle.c, OpenMP on all host cores): ray generation,
+    forward, MSE, backward, Adam.  Reported beside the torch-CPU figure as a second, faster CPU data point."""
+    from oracle import c_oracle as co
+    from oracle import plenoxel_oracle as po
+    imgs, poses = sc.imgs.numpy(), sc.poses.numpy()
+    grid = sc.grid.numpy().copy()
+    m, v, ga = np.zeros_like(grid), np.zeros_like(grid), np.zeros_like(grid)
+    o = np.repeat(poses[:, :3, 3], sc.rays_per_cam, axis=0)
+    gmin = po.grid_origin(grid.shape[:3], sc.points_distance)
+    S, delta, pd = sc.num_samples, sc.delta_step, sc.points_distance
+    times = []
+    for i in range(warmup + steps):
+        uv = uvs[i % len(uvs)].numpy()
+        t0 = time.perf_counter()
+        dirs, targets, _ = co.generate_rays(imgs, poses, sc.fov, uv)
+        rgba, _, _, _ = co.render_forward(grid, o, dirs, S, delta, gmin, pd, want_lin=False)
+        _, gpix = co.mse_loss(rgba, targets)
+        grad = co.render_backward(grid, o, dirs, S, delta, gmin, pd, gpix).astype(np.float32)
+        co.adam_step_(grid, grad, m, v, ga, sc.lr, i + 1)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = float(sum(times))
+    return {"value": sc.n_rays * steps / total, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{steps} steps of {sc.n_rays} rays after {warmup} warm-up ({1e3 * total / steps:.0f} ms/step), plain-C "
+                      "restatement with OpenMP (oracle/plenoxel_oracle.c)"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -173,6 +201,10 @@ def run_reference_arm(args):
         "e2e": {"value": r["rays_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:            # second CPU data point: the C / OpenMP restatement (never allowed to break the line)
+        line["cpu_baseline"]["c_port"] = time_c_port(sc, uvs, steps=min(args.steps, 3), warmup=1)
+    except Exception as e:
+        log(f"[bench] C port not timed ({type(e).__name__}: {e})")
     print(json.dumps(line), flush=True)
     return 0
 
@@ -388,6 +420,10 @@ def run_gpu_arm(args):
         cpu_baseline = {"value": r["rays_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                         "sample": f"3 steps of {r['rays_per_step']} rays after 1 warm-up ({r['ms_per_step']:.0f} ms/step), torch-CPU port "
                                   "of scripts/train.py:130-184 (oracle/torch_port.py)"}
+        try:        # second CPU data point: the C / OpenMP restatement (never allowed to break the bench line)
+            cpu_baseline["c_port"] = time_c_port(sc, uvs, steps=3, warmup=1)
+        except Exception as e:
+            log(f"[bench] C port not timed ({type(e).__name__}: {e})")
 
     if rank == 0:
         line = {

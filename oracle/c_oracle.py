@@ -70,12 +70,14 @@ def _geometry(grid, origins, dirs, gmin):
     return grid, origins, dirs, dims, _f32(gmin)
 
 
-def render_forward(grid, origins, dirs, num_samples, delta_step, gmin, points_distance, mode="nearest", clamp=True):
-    """rgba (N,4) f32, depth (N,) f32, count (N,) int32, lin (N,S) int64 (-1 = out of bounds; 0 in bounds for trilinear)."""
+def render_forward(grid, origins, dirs, num_samples, delta_step, gmin, points_distance, mode="nearest", clamp=True,
+                   want_lin=True):
+    """rgba (N,4) f32, depth (N,) f32, count (N,) int32, lin (N,S) int64 (-1 = out of bounds; 0 in bounds for trilinear;
+    None with want_lin=False)."""
     grid, origins, dirs, dims, gmin = _geometry(grid, origins, dirs, gmin)
     n = dirs.shape[0]
     rgba, depth = np.zeros((n, 4), np.float32), np.zeros(n, np.float32)
-    count, lin = np.zeros(n, np.int32), np.zeros((n, num_samples), np.int64)
+    count, lin = np.zeros(n, np.int32), (np.zeros((n, num_samples), np.int64) if want_lin else None)
     load().plxo_render_forward(_p(grid, C.c_float), _p(dims, C.c_int64), _p(origins, C.c_float), _p(dirs, C.c_float), n,
                                int(num_samples), float(np.float32(delta_step)), _p(gmin, C.c_float),
                                float(np.float32(points_distance)), MODES[mode], int(clamp), _p(rgba, C.c_float),
@@ -106,6 +108,15 @@ def mse_loss(pixels, targets, n_global=None):
     loss = load().plxo_mse_loss(_p(pixels, C.c_float), _p(targets, C.c_float), pixels.shape[0], int(n_global or 0),
                                 _p(grad, C.c_double))
     return float(loss), grad
+
+
+def adam_step_(p, g, m, v, gabs, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    """In place on contiguous float32 arrays (the timing loop of bench.py uses this to avoid four grid-sized copies)."""
+    for a in (p, g, m, v, gabs):
+        if a.dtype != np.float32 or not a.flags.c_contiguous or a.size != p.size:
+            raise ValueError("adam_step_ needs contiguous float32 arrays of equal size")
+    load().plxo_adam_step(_p(p, C.c_float), _p(g, C.c_float), _p(m, C.c_float), _p(v, C.c_float), _p(gabs, C.c_float), p.size,
+                          float(lr), int(step), float(beta1), float(beta2), float(eps))
 
 
 def adam_step(p, g, m, v, gabs, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):

@@ -41,6 +41,27 @@ def test_library_exports_every_declared_symbol(plx_lib):
     assert plx_lib.plx_num_chunks(600) >= 19 and plx_lib.plx_num_chunks(0) >= 1
 
 
+def test_ctypes_prototypes_match_the_header_declarations():
+    """Every function declared in plenoxel_abi.h has a ctypes prototype with the same number of parameters and, position by
+    position, the matching scalar type (pointers and arrays map to c_void_p / POINTER(...))."""
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    decls = re.findall(r"^\s*(?:int|int32_t|const char\s*\*)\s+(plx_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.M | re.S)
+    assert len(decls) >= 24 and {d[0] for d in decls} == set(declared_symbols())
+    scalars = [("int32_t", C.c_int32), ("uint32_t", C.c_uint32), ("int64_t", C.c_int64), ("uint64_t", C.c_uint64),
+               ("float", C.c_float), ("double", C.c_double), ("int", C.c_int)]
+    for name, params in decls:
+        plist = [" ".join(x.split()) for x in params.split(",")]
+        plist = [x for x in plist if x not in ("", "void")]
+        _, argtypes = L.PROTOTYPES[name]
+        assert len(argtypes) == len(plist), f"{name}: {len(argtypes)} ctypes arguments, {len(plist)} in the header"
+        for i, (param, at) in enumerate(zip(plist, argtypes)):
+            if "*" in param or "[" in param:
+                assert at is L.c_void or at is C.c_char_p or issubclass(at, C._Pointer), f"{name} arg {i}: {param} vs {at}"
+                continue
+            want = next(ct for cname, ct in scalars if re.match(rf"(const )?{cname}\b", param))
+            assert at is want, f"{name} arg {i}: {param} vs {at}"
+
+
 def test_ctypes_structs_match_c_layout(tmp_path):
     prog = tmp_path / "layout.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "plenoxel_abi.h"\nint main(){'

@@ -81,6 +81,25 @@ def test_ctypes_structs_match_c_layout(tmp_path):
     assert got == want
 
 
+def test_every_struct_field_has_the_c_offset(tmp_path):
+    """All fields of all ABI structs: offsetof() from the header (compiled with gcc) == the ctypes offset."""
+    structs = [L.PlxMarch, L.PlxRays, L.PlxRenderFwd, L.PlxRenderBwd, L.PlxRayGen, L.PlxPeerSync, L.PlxRenderTrain,
+               L.PlxAdamPeer, L.PlxTrainStep]
+    lines, want = [], []
+    for st in structs:
+        lines.append(f'printf("%zu\\n", sizeof({st.__name__}));')
+        want.append(C.sizeof(st))
+        for fname, _ in st._fields_:
+            lines.append(f'printf("%zu\\n", offsetof({st.__name__}, {fname}));')
+            want.append(getattr(st, fname).offset)
+    prog = tmp_path / "offsets.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "plenoxel_abi.h"\nint main(){' + "".join(lines) + "return 0;}")
+    exe = tmp_path / "offsets"
+    subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), str(prog), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == want
+
+
 def test_argument_errors_are_reported_not_thrown(plx_lib):
     a = L.PlxRenderFwd()
     assert plx_lib.plx_render_fwd(C.byref(a), None) == -1            # PLX_E_NULL: grid

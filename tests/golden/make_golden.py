@@ -148,7 +148,37 @@ def make_inference(name):
     print(name, img.shape, img.dtype, int(img[..., 3].max()))
 
 
+def sha(a: np.ndarray) -> str:
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def make_fullsize(name, scene):
+    """The reference at a BASELINE config's FULL size (config #2: 12 800 rays x 600 samples through a 128^3 grid; #3: 4096 x
+    256 through 256^3), frozen compactly: the inputs are regenerated from their seeds (their SHA-256 is stored), the
+    7.68 M / 1.05 M linear indices are stored as a SHA-256, the gradient as sums plus a strided subset."""
+    sc = synth.make_scene(scene, H=8)
+    C_, R, S = sc.poses.shape[0], sc.rays_per_cam, sc.num_samples
+    uv = synth.random_uv(C_, R, seed=77)
+    out = reference_step(sc.grid, sc.points_distance, sc.poses, sc.fov, sc.imgs, R, S, sc.delta_step, uv, "nearest")
+    grad = out["grad"].astype(np.float64)
+    np.savez_compressed(
+        os.path.join(HERE, f"{name}.npz"), scene=np.array(scene), uv_seed=np.int64(77), H=np.int64(8),
+        sha_grid=np.array(sha(sc.grid.numpy())), sha_uv=np.array(sha(uv.numpy())), sha_poses=np.array(sha(sc.poses.numpy())),
+        sha_imgs=np.array(sha(sc.imgs.numpy())), gmin=out["gmin"], sha_dirs=np.array(sha(out["dirs"])),
+        sha_targets=np.array(sha(out["targets"])), sha_lin=np.array(sha(out["lin"])),
+        count=out["inb"].sum(1).astype(np.int32), pix=out["pix"], loss=out["loss"],
+        grad_max=np.float64(np.abs(grad).max()), grad_sum=grad.reshape(-1, 4).sum(0), grad_abs_sum=np.abs(grad).reshape(-1, 4).sum(0),
+        grad_nonzero_cells=np.int64((np.abs(grad).sum(-1) > 0).sum()), grad_subset=out["grad"][::7, ::5, ::3].copy())
+    print(name, "rays", C_ * R, "samples", S, "in-bounds", float(out["inb"].mean()), "loss", float(out["loss"]),
+          "nonzero gradient cells", int((np.abs(grad).sum(-1) > 0).sum()))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "full":            # only the full-size fixtures (slow: the reference on M = 7.7 M samples)
+        make_fullsize("full_c2", "c2")
+        make_fullsize("full_c3", "c3")
+        sys.exit(0)
     make_inference("inference_g24")
     make_tv("tv_g12")
     make_case("nn_dense_g24", 24, 2, 8, 64, 48, 6.0 / 48, "dense", "nearest", seed=11)

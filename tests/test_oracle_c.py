@@ -4,6 +4,7 @@ Three statements of the same algorithm now have to agree: the reference (frozen 
 and the C oracle.  Bit-exact: ray directions, target pixels, linear indices, masks, counts, pixels and depth (C vs numpy),
 Adam state.  Summation order only (1e-12): the float64 gradients.  1e-6: pixels / loss / gradient against the reference.
 """
+import hashlib
 import os
 
 import numpy as np
@@ -126,3 +127,40 @@ def test_c_oracle_full_baseline_size_finishes_in_seconds():
     sel = np.arange(0, 12800, 97)
     rn, dn, cn, ln = po.render_forward(sc.grid.numpy(), o[sel], dirs[sel], sc.num_samples, sc.delta_step, gmin, sc.points_distance)
     assert np.array_equal(ln, lin[sel]) and np.array_equal(cn, count[sel]) and np.array_equal(rn, rgba[sel]) and np.array_equal(dn, depth[sel])
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("name", ["full_c2", "full_c3"])
+def test_c_oracle_matches_the_reference_at_full_baseline_size(name):
+    """tests/golden/full_c2.npz / full_c3.npz hold what the UNMODIFIED reference computed for a whole config-#2 / #3 batch
+    (make_golden.py full): the inputs are regenerated from their seeds and checked by SHA-256, then every ray direction,
+    target pixel and linear sample index (7.68 M / 1.05 M of them, by SHA-256) must be bit-exact, per-ray counts equal,
+    pixels / loss / gradient (sums + strided subset) within 1e-6."""
+    z = load(name)
+    sc = synth.make_scene(str(z["scene"]), H=int(z["H"]))
+    C_, R, S = sc.poses.shape[0], sc.rays_per_cam, sc.num_samples
+    uv = synth.random_uv(C_, R, seed=int(z["uv_seed"])).numpy()
+    grid, poses, imgs = sc.grid.numpy(), sc.poses.numpy(), sc.imgs.numpy()
+    assert (_sha(grid), _sha(uv), _sha(poses), _sha(imgs)) == (str(z["sha_grid"]), str(z["sha_uv"]), str(z["sha_poses"]), str(z["sha_imgs"])), \
+        "the seeded inputs no longer reproduce the ones the fixture was made from"
+    gmin = po.grid_origin(grid.shape[:3], sc.points_distance)
+    assert np.array_equal(gmin, z["gmin"])
+    dirs, targets, _ = co.generate_rays(imgs, poses, sc.fov, uv)
+    assert _sha(dirs) == str(z["sha_dirs"]) and _sha(targets) == str(z["sha_targets"])
+    o = np.repeat(poses[:, :3, 3], R, axis=0)
+    rgba, _, count, lin = co.render_forward(grid, o, dirs, S, sc.delta_step, gmin, sc.points_distance)
+    assert _sha(lin.astype(np.int32)) == str(z["sha_lin"]), "every linear index of the full batch, bit-exact"
+    assert np.array_equal(count, z["count"])
+    assert np.abs(rgba - z["pix"]).max() <= 1e-6 * np.abs(z["pix"]).max()
+    loss, gpix = co.mse_loss(rgba, targets)
+    assert abs(loss - float(z["loss"])) <= 1e-6 * float(z["loss"])
+    grad = co.render_backward(grid, o, dirs, S, sc.delta_step, gmin, sc.points_distance, gpix)
+    gmax = float(z["grad_max"])
+    assert abs(np.abs(grad).max() - gmax) <= 1e-6 * gmax
+    assert np.abs(grad[::7, ::5, ::3] - z["grad_subset"]).max() <= 1e-6 * gmax
+    assert np.abs(grad.reshape(-1, 4).sum(0) - z["grad_sum"]).max() <= 1e-5 * np.abs(z["grad_abs_sum"]).max()
+    assert np.abs(np.abs(grad).reshape(-1, 4).sum(0) - z["grad_abs_sum"]).max() <= 1e-5 * np.abs(z["grad_abs_sum"]).max()
+    assert int((np.abs(grad).sum(-1) > 0).sum()) == int(z["grad_nonzero_cells"])

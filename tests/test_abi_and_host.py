@@ -150,3 +150,25 @@ def test_shard_cameras_partitions(n, world):
     assert seen == list(range(n))
     sizes = [len(shard_cameras(n, r, world)) for r in range(world)]
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_receptive_field_schedule_is_the_references():
+    """scripts/train.py:91-92,:108: odd window sizes 93, 91, ..., 3, five steps each, then full resolution (0)."""
+    from plenoxels_b200.fit import STEPS_PER_FIELD, receptive_field_at, receptive_field_schedule
+    sched = receptive_field_schedule()
+    assert sched == list(range(93, 2, -2)) and len(sched) == 46 and STEPS_PER_FIELD == 5
+    assert [receptive_field_at(i) for i in (0, 4, 5, 9, 10, 224, 225, 229, 230, 10_000)] == [93, 93, 91, 91, 89, 5, 3, 3, 0, 0]
+    assert receptive_field_at(7, schedule=[9, 5]) == 5 and receptive_field_at(10, schedule=[9, 5]) == 0
+
+
+@pytest.mark.parametrize("n_cells,world", [(2097152, 1), (2097152, 2), (2097152, 8), (1000003, 3), (7, 8), (93 * 91 * 89, 5)])
+def test_slab_ranges_partition_the_grid(n_cells, world):
+    """Each rank owns a contiguous block of whole cells (multiples of 4 floats); blocks tile [0, 4 * n_cells) in rank order and
+    differ by at most one cell — what plx_adam_step_peer's [begin, end) relies on."""
+    from plenoxels_b200.trainer import slab_range
+    edges = [slab_range(n_cells, r, world) for r in range(world)]
+    assert edges[0][0] == 0 and edges[-1][1] == 4 * n_cells
+    for (b0, e0), (b1, e1) in zip(edges, edges[1:]):
+        assert e0 == b1
+    sizes = [(e - b) // 4 for b, e in edges]
+    assert all(b % 4 == 0 and e % 4 == 0 and e >= b for b, e in edges) and max(sizes) - min(sizes) <= 1

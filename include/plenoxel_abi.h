@@ -3,7 +3,7 @@
  *
  * The reference (DanJbk/Plenoxels) has no FFI: its boundary is a set of Python free functions on torch
  * tensors.  Each entry point below names the reference function(s) it stands under
- * (`file:line` in the reference tree); `plenoxels_b200/*.py` binds them with ctypes and keeps the
+ * (`file:line` in the reference tree); the Python modules under `plenoxels_b200/` bind them with ctypes and keep the
  * reference's Python signatures on top (INTEGRATION.md shows the stub).
  *
  * Conventions

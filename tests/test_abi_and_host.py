@@ -172,3 +172,33 @@ def test_slab_ranges_partition_the_grid(n_cells, world):
         assert e0 == b1
     sizes = [(e - b) // 4 for b, e in edges]
     assert all(b % 4 == 0 and e % 4 == 0 and e >= b for b, e in edges) and max(sizes) - min(sizes) <= 1
+
+
+def test_abi_links_and_runs_from_plain_c(plx_lib, tmp_path):
+    """The boundary is a C ABI, not a Python one: a C program that includes plenoxel_abi.h and links libplenoxel_b200.so
+    must build with gcc and get the documented error codes / messages back (no GPU needed for the argument checks)."""
+    src = tmp_path / "abi_smoke.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <string.h>
+#include "plenoxel_abi.h"
+int main(void) {
+    if (plx_version() != 1) return 1;
+    if (plx_num_chunks(600) < 19) return 2;
+    PlxRenderFwd f; memset(&f, 0, sizeof f);
+    if (plx_render_fwd(&f, NULL) != -1 || !strstr(plx_last_error(), "grid")) return 3;      /* PLX_E_NULL */
+    if (plx_render_fwd(NULL, NULL) != -1) return 4;
+    if (plx_adam_step(NULL, NULL, NULL, NULL, NULL, 0, 1e-3, 0.9, 0.999, 1e-8, 0, 1, NULL) != -2) return 5;   /* step < 1 */
+    PlxAdamPeer p; memset(&p, 0, sizeof p);
+    if (plx_adam_step_peer(&p, NULL) >= 0) return 6;                                         /* world == 0 */
+    printf("abi ok: %s\n", plx_last_error());
+    return 0;
+}
+""")
+    exe = tmp_path / "abi_smoke"
+    libdir = os.path.dirname(build.LIB_PATH)
+    subprocess.run(["gcc", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe), "-L", libdir,
+                    "-lplenoxel_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "abi ok" in out.stdout

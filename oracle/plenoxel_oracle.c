@@ -45,6 +45,12 @@ static inline float norm_coord(float o, float d, float t, float gmin, float pd) 
     return q / pd;
 }
 
+/* float -> int64 as numpy / torch do it for values an int64 cannot hold (NaN, inf, |x| >= 2^63): INT64_MIN, i.e. out of bounds;
+ * the plain C cast would be undefined behaviour there */
+static inline int64_t to_index(float r) {
+    return (r >= -9.0e18f && r <= 9.0e18f) ? (int64_t)r : INT64_MIN;
+}
+
 typedef struct {
     const float* grid;
     int64_t nx, ny, nz;
@@ -60,7 +66,7 @@ static inline const float* cell(const Grid* g, int64_t ix, int64_t iy, int64_t i
  * as SURVEY.md section 8a row T. */
 static inline int64_t lookup(const Grid* g, int mode, float nx_, float ny_, float nz_, float out[4]) {
     if (mode == PLXO_NEAREST) {
-        const int64_t ix = (int64_t)rintf(nx_), iy = (int64_t)rintf(ny_), iz = (int64_t)rintf(nz_);   /* half to even */
+        const int64_t ix = to_index(rintf(nx_)), iy = to_index(rintf(ny_)), iz = to_index(rintf(nz_));   /* half to even */
         const int inb = ix >= 0 && ix < g->nx && iy >= 0 && iy < g->ny && iz >= 0 && iz < g->nz;
         if (!inb) { out[0] = out[1] = out[2] = out[3] = 0.f; return -1; }
         const float* c = cell(g, ix, iy, iz);

@@ -164,3 +164,22 @@ def test_c_oracle_matches_the_reference_at_full_baseline_size(name):
     assert np.abs(grad.reshape(-1, 4).sum(0) - z["grad_sum"]).max() <= 1e-5 * np.abs(z["grad_abs_sum"]).max()
     assert np.abs(np.abs(grad).reshape(-1, 4).sum(0) - z["grad_abs_sum"]).max() <= 1e-5 * np.abs(z["grad_abs_sum"]).max()
     assert int((np.abs(grad).sum(-1) > 0).sum()) == int(z["grad_nonzero_cells"])
+
+
+def test_c_oracle_handles_non_finite_and_degenerate_rays_like_numpy():
+    """NaN / inf / astronomically large coordinates are out of bounds (numpy's float -> int64 cast gives INT64_MIN there; the
+    C cast would be undefined behaviour without the guard), a zero direction stays at the origin, S = 0 renders nothing."""
+    G, S = 12, 24
+    pd, delta = synth.GRID_EXTENT / G, 6.0 / S
+    grid = synth.dense_grid(G, seed=1).numpy()
+    gmin = po.grid_origin(grid.shape[:3], pd)
+    o = np.array([[0, 0, 4], [0, 0, 4], [0, 0, 0], [0, 0, 4], [1e30, 0, 0], [0, 0, 4]], np.float32)
+    d = np.array([[0, 0, -1], [np.nan, 0, -1], [0, 0, 0], [np.inf, 0, -1], [0, 0, -1], [1e38, 1e38, -1e38]], np.float32)
+    with np.errstate(all="ignore"):
+        rn, dn, cn, ln = po.render_forward(grid, o, d, S, delta, gmin, pd)
+    rc, dc, cc, lc = co.render_forward(grid, o, d, S, delta, gmin, pd)
+    assert np.array_equal(ln, lc) and np.array_equal(cn, cc)
+    assert cn[0] > 0 and cn[1] == 0 and cn[2] == S and cn[3] == 0 and cn[4] == 0
+    assert np.array_equal(rn, rc, equal_nan=True) and np.array_equal(dn, dc, equal_nan=True)
+    r0 = co.render_forward(grid, o, d, 0, delta, gmin, pd)
+    assert not r0[0].any() and not r0[2].any() and r0[3].shape == (6, 0)

@@ -54,6 +54,9 @@ def load():
         lib.plxo_adam_step.restype = None
         lib.plxo_generate_rays.argtypes = [f32p, C.c_int32, C.c_int32, C.c_int32, f32p, C.c_float, f32p, C.c_int32, f32p, f32p,
                                            i64p]
+        lib.plxo_even_spread_uv.argtypes = [C.c_int32, C.c_int32, f32p]
+        lib.plxo_tv_loss.argtypes = [f32p, i64p, f64p]
+        lib.plxo_tv_loss.restype = C.c_double
         _lib = lib
     return _lib
 
@@ -148,3 +151,21 @@ def train_step(grid, m, v, gabs, origins, dirs, targets, num_samples, delta_step
     grad = render_backward(grid, origins, dirs, num_samples, delta_step, gmin, points_distance, gpix, mode)
     p2, m2, v2, ga2 = adam_step(grid, grad.astype(np.float32), m, v, gabs, lr, step)
     return loss, grad, p2, m2, v2, ga2
+
+
+def even_spread_uv(n_cams, number_of_rays):
+    """(C, round(sqrt(R))^2, 2) u-major lattice on [0,1]^2 — src/ray_sampling.py:220-223."""
+    n = int(np.round(np.sqrt(number_of_rays)))
+    uv = np.zeros((n_cams, n * n, 2), np.float32)
+    if load().plxo_even_spread_uv(int(n_cams), n, _p(uv, C.c_float)):
+        raise MemoryError("plxo_even_spread_uv")
+    return uv
+
+
+def tv_loss(grid):
+    """(loss, gradient (X,Y,Z,4) float64) of scripts/train.py:44-65."""
+    grid = _f32(grid)
+    dims = np.asarray(grid.shape[:3], dtype=np.int64)
+    grad = np.zeros(grid.shape, np.float64)
+    loss = load().plxo_tv_loss(_p(grid, C.c_float), _p(dims, C.c_int64), _p(grad, C.c_double))
+    return float(loss), grad

@@ -312,4 +312,68 @@ int plxo_generate_rays(const float* imgs, int32_t n_cams, int32_t H, int32_t W, 
     return 0;
 }
 
+/*
+ * `torch.linspace(0, 1, n)` in fp32 (src/ray_sampling.py:222) and the even-spread uv lattice built from it (:220-223):
+ * lower half 0 + step * i (mul, add), upper half 1 - step * (n - 1 - i) contracted to one multiply-add (ATen's CPU kernel,
+ * pinned by the numpy oracle); uv (C, n*n, 2) u-major, n = round(sqrt(R)).
+ */
+void plxo_linspace01(int32_t n, float* out) {
+    if (n == 1) { out[0] = 0.f; return; }
+    const float step = 1.f / (float)(n - 1);
+    for (int32_t i = 0; i < n; ++i)
+        out[i] = i < n / 2 ? 0.f + step * (float)i : (float)(1.0 - (double)step * (double)(n - 1 - i));
+}
+
+int plxo_even_spread_uv(int32_t n_cams, int32_t n_side, float* uv) {
+    float* line = (float*)malloc(sizeof(float) * (size_t)(n_side > 0 ? n_side : 1));
+    if (!line) return -1;
+    plxo_linspace01(n_side, line);
+    for (int32_t c = 0; c < n_cams; ++c)
+        for (int32_t iu = 0; iu < n_side; ++iu)
+            for (int32_t iv = 0; iv < n_side; ++iv) {
+                float* o = uv + (((int64_t)c * n_side + iu) * n_side + iv) * 2;
+                o[0] = line[iu];
+                o[1] = line[iv];
+            }
+    free(line);
+    return 0;
+}
+
+/*
+ * `tv_loss` of scripts/train.py:44-65 in double: sqrt of the summed squared neighbour differences along the three grid axes
+ * (all four channels) and its gradient w.r.t. the grid (autograd of :63).  An all-equal grid gives loss 0 and gradient 0 (the
+ * reference's autograd gives 0/0 = NaN there).
+ */
+double plxo_tv_loss(const float* grid, const int64_t dims[3], double* grad) {
+    const int64_t X = dims[0], Y = dims[1], Z = dims[2];
+    const int64_t sx = Y * Z * 4, sy = Z * 4, sz = 4, n = X * sx;
+    double s = 0.0;
+    for (int64_t x = 0; x < X; ++x)
+        for (int64_t y = 0; y < Y; ++y)
+            for (int64_t z = 0; z < Z; ++z)
+                for (int ch = 0; ch < 4; ++ch) {
+                    const int64_t i = x * sx + y * sy + z * sz + ch;
+                    const double v = grid[i];
+                    if (x + 1 < X) { const double d = v - (double)grid[i + sx]; s += d * d; }
+                    if (y + 1 < Y) { const double d = v - (double)grid[i + sy]; s += d * d; }
+                    if (z + 1 < Z) { const double d = v - (double)grid[i + sz]; s += d * d; }
+                }
+    const double loss = sqrt(s);
+    if (grad) {
+        memset(grad, 0, sizeof(double) * (size_t)n);
+        if (loss > 0.0)
+            for (int64_t x = 0; x < X; ++x)
+                for (int64_t y = 0; y < Y; ++y)
+                    for (int64_t z = 0; z < Z; ++z)
+                        for (int ch = 0; ch < 4; ++ch) {
+                            const int64_t i = x * sx + y * sy + z * sz + ch;
+                            const double v = grid[i];
+                            if (x + 1 < X) { const double d = (v - (double)grid[i + sx]) / loss; grad[i] += d; grad[i + sx] -= d; }
+                            if (y + 1 < Y) { const double d = (v - (double)grid[i + sy]) / loss; grad[i] += d; grad[i + sy] -= d; }
+                            if (z + 1 < Z) { const double d = (v - (double)grid[i + sz]) / loss; grad[i] += d; grad[i + sz] -= d; }
+                        }
+    }
+    return loss;
+}
+
 int plxo_version(void) { return 1; }

@@ -183,3 +183,24 @@ def test_c_oracle_handles_non_finite_and_degenerate_rays_like_numpy():
     assert np.array_equal(rn, rc, equal_nan=True) and np.array_equal(dn, dc, equal_nan=True)
     r0 = co.render_forward(grid, o, d, 0, delta, gmin, pd)
     assert not r0[0].any() and not r0[2].any() and r0[3].shape == (6, 0)
+
+
+def test_c_oracle_even_spread_lattice_matches_reference_golden():
+    z = load("even_spread")
+    uv = co.even_spread_uv(2, 100)
+    assert np.array_equal(uv, po.even_spread_uv(2, 100))
+    for n in (1, 2, 17, 100, 800):
+        assert np.array_equal(co.even_spread_uv(1, n * n), po.even_spread_uv(1, n * n)), n
+    dirs, targets, _ = co.generate_rays(z["imgs"], z["poses"], float(z["fov"]), uv)
+    assert np.array_equal(dirs, z["dirs"]) and np.array_equal(targets, z["targets"])
+
+
+def test_c_oracle_tv_loss_matches_reference_golden():
+    z = load("tv_g12")
+    loss, grad = co.tv_loss(z["grid"])
+    assert abs(loss - float(z["loss"])) <= 1e-6 * float(z["loss"])
+    assert np.abs(grad - z["grad"]).max() <= 1e-6 * np.abs(z["grad"]).max()
+    ln, gn = po.tv_loss(z["grid"])
+    assert abs(loss - ln) <= 1e-12 * ln and np.abs(grad - gn).max() <= 1e-12
+    l0, g0 = co.tv_loss(np.full((3, 4, 5, 4), 0.25, np.float32))
+    assert l0 == 0.0 and not g0.any()

@@ -204,3 +204,20 @@ def test_c_oracle_tv_loss_matches_reference_golden():
     assert abs(loss - ln) <= 1e-12 * ln and np.abs(grad - gn).max() <= 1e-12
     l0, g0 = co.tv_loss(np.full((3, 4, 5, 4), 0.25, np.float32))
     assert l0 == 0.0 and not g0.any()
+
+
+def test_c_oracle_inference_image_matches_reference_golden():
+    """visulize_3d_in_2d (src/visualization.py:111-154) restated on the C oracle: clip, alpha threshold, even-spread rays of
+    one camera, nearest lookup without further clamping, composite, x255 round clip uint8, transpose — the reference's uint8
+    image bit for bit."""
+    z = load("inference_g24")
+    grid = np.clip(z["grid"], 0.0, 1.0).astype(np.float32)
+    grid[..., 3][grid[..., 3] < float(z["threshold"])] = 0.0
+    res, S = int(z["res"]), int(z["S"])
+    uv = co.even_spread_uv(1, res * res)
+    dirs, _, _ = co.generate_rays(z["imgs"], z["poses"], float(z["fov"]), uv)
+    o = np.repeat(z["poses"][:, :3, 3], res * res, axis=0)
+    gmin = po.grid_origin(grid.shape[:3], float(z["pd"]))
+    rgba, _, _, _ = co.render_forward(grid, o, dirs, S, float(z["delta"]), gmin, float(z["pd"]), clamp=False)
+    img = np.transpose((rgba * 255).round().clip(0, 255).astype(np.uint8).reshape(res, res, 4), (1, 0, 2))
+    assert np.array_equal(img, z["image"])

@@ -258,7 +258,6 @@ cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, const S
     const int64_t n4 = end4 - begin4;
     // remote loads have microseconds of latency: keep `world * UNROLL` 16-byte requests in flight per thread
     static const int unroll_env = adam_env("PLX_PEER_UNROLL", 0);
-    static const int dbg_ld = adam_env("PLX_PEER_DBG_LD", 0), dbg_st = adam_env("PLX_PEER_DBG_ST", 0);   // timing experiments only
     const int unroll = unroll_env ? unroll_env : 1;
 #define PLX_PEER(U)                                                                                                  \
     do {                                                                                                             \
@@ -268,7 +267,7 @@ cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, const S
         const int64_t want = (n4 + 256 * U - 1) / (256 * U);                                                         \
         const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);                                           \
         const unsigned blocks = (unsigned)(want < resident ? want : resident);                                       \
-        k_adam_peer<U><<<blocks, 256, 0, st>>>(pp, dbg_ld ? dbg_ld : a.world, dbg_st ? dbg_st : a.world, (float4*)a.exp_avg, (float4*)a.exp_avg_sq,               \
+        k_adam_peer<U><<<blocks, 256, 0, st>>>(pp, a.world, a.world, (float4*)a.exp_avg, (float4*)a.exp_avg_sq,                                   \
                                                (float4*)a.grad_abs_sum, begin4, end4, s, tail, a.sync);              \
     } while (0)
     if (unroll >= 4) PLX_PEER(4); else if (unroll >= 2) PLX_PEER(2); else PLX_PEER(1);

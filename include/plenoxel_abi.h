@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PLX_ABI_VERSION 1
+#define PLX_ABI_VERSION 2
 
 /* error codes */
 #define PLX_OK 0
@@ -34,6 +34,7 @@ extern "C" {
 #define PLX_E_SHAPE (-2)       /* a size / stride is invalid */
 #define PLX_E_UNSUPPORTED (-3) /* valid request the library does not implement */
 #define PLX_E_ALIGN (-4)       /* pointer not aligned for the vector path */
+#define PLX_E_PEER_TIMEOUT (-5) /* a cross-GPU wait gave up (a peer died or stalled): the step must not be trusted */
 
 /* lookup mode */
 #define PLX_NEAREST 0   /* get_nearest_voxels, src/grid_functions.py:103-114 */
@@ -138,10 +139,14 @@ int plx_render_bwd(const PlxRenderBwd* args, void* stream);
  * Returns PLX_E_UNSUPPORTED for trilinear mode or when num_samples exceeds the shared-memory index cache
  * (use K1 + K2 then; plx_train_step does that automatically).
  */
+#define PLX_IMG_F32 0   /* imgs = (C,H,W,4) fp32 in [0,1], what load_image_data_from_path returns (src/data_processing.py:51-60) */
+#define PLX_IMG_U8 1    /* imgs = (C,H,W,4) uint8 as decoded from the PNGs; the kernels evaluate fp32(u8) / 255 (IEEE division)
+                           when they fetch a target pixel, bit-equal to the reference's conversion, at a quarter of the bytes */
 typedef struct PlxRayGen {
-    const float* imgs; int32_t n_cams, img_h, img_w;
+    const void* imgs; int32_t n_cams, img_h, img_w;
     const float* poses; float fov;
     const float* uv; int32_t rays_per_cam;
+    int32_t img_format;       /* PLX_IMG_F32 | PLX_IMG_U8 */
 } PlxRayGen;
 /*
  * Cross-GPU ordering fused into a kernel (multi-GPU only; all-zero = none).  `flags[r]` is rank r's int32 flag array
@@ -157,12 +162,46 @@ typedef struct PlxRayGen {
  * next march waits for that.
  */
 #define PLX_MAX_PEERS 8
+/*
+ * Failure record of the cross-GPU waits.  Every device-side wait is BOUNDED (`timeout_ns` of %globaltimer; 0 = 10 s): a peer
+ * that died or stalled must not hang this GPU.  A wait that gives up stores a non-zero code
+ *   (channel + 1) | (epoch << 8)   into *device_word (device memory) and into *host_word (pinned host memory, may be NULL)
+ * and every kernel that is handed the same `device_word` and finds it non-zero at its start SKIPS its parameter / state
+ * stores, so a step after a failed wait never writes stale gradients into any replica.  The host checks *host_word (or
+ * copies *device_word back) in flush / wait_result / checkpoint and raises; the words are sticky until the caller clears
+ * them.
+ */
+typedef struct PlxPeerError {
+    int32_t* device_word;
+    int32_t* host_word;
+    uint64_t timeout_ns;
+} PlxPeerError;
+
+/*
+ * Multi-GPU "push" exchange: where the fused march adds the gradient of cell `lin`.  Every rank r owns
+ * a contiguous slab of cells, owner(lin) = umulhi(lin, owner_mul) (plx_slab_partition gives owner_mul and the slab
+ * bounds), and the march issues its 16-byte vector reduction straight into the OWNER's gradient buffer
+ * grads[owner] (peer-mapped, full grid size, only the owner's slab of each buffer is ever written).  After a cross-rank
+ * barrier every rank holds the complete gradient sum of its slab, and only the touched cells crossed NVLink
+ * (16 B x merged in-bounds samples instead of 16 B x cells).  world == 0: not used, the march adds into `grad_grid`.
+ */
+typedef struct PlxPeerGrad {
+    float* grads[PLX_MAX_PEERS];
+    uint32_t owner_mul;
+    int32_t world;
+} PlxPeerGrad;
+/* Slab partition used by PlxPeerGrad / plx_adam_step_slab: owner_mul = floor(2^32 * world / n_cells) and rank r owns the
+ * cells [begin, end) = [ceil(r * 2^32 / owner_mul), ceil((r+1) * 2^32 / owner_mul)) clipped to n_cells.  Needs
+ * n_cells >= world.  Any output pointer may be NULL. */
+int plx_slab_partition(int64_t n_cells, int32_t world, int32_t rank, uint32_t* owner_mul, int64_t* begin_cell, int64_t* end_cell);
+
 typedef struct PlxPeerSync {
     int32_t* flags[PLX_MAX_PEERS];
     int32_t rank, world;
     int32_t wait_channel, wait_epoch;
     int32_t signal_channel, signal_epoch;
     int32_t* block_counter;
+    PlxPeerError err;        /* where a wait that gave up is recorded (see PlxPeerError); all-zero = ~10 s bound, no record */
 } PlxPeerSync;
 
 typedef struct PlxRenderTrain {
@@ -175,9 +214,8 @@ typedef struct PlxRenderTrain {
     float* rgba;
     float* loss;
     float grad_scale, loss_scale, beta_over_m;
-    int32_t* work_counter;   /* optional: one device int32 that is 0 at launch; rays are then claimed dynamically by the warps
-                                of a one-wave grid (better balance for rays of unequal length).  NULL = static assignment */
     PlxPeerSync sync;        /* optional cross-GPU wait at the start / signal at the end (all-zero = none) */
+    PlxPeerGrad peer_grad;   /* optional multi-GPU push exchange (world == 0: gradient goes to grad_grid) */
 } PlxRenderTrain;
 int plx_render_train(const PlxRenderTrain* args, void* stream);
 
@@ -214,25 +252,59 @@ typedef struct PlxAdamPeer {
      * (`multimem.st.v4.f32`), which halves the bytes every GPU moves over its NVLink ports. */
     float* grid_mc;
     const float* grad_mc;
-    /* optional step tail (same contract as plx_train_step / plx_train_step_host): publish *loss_src to result_host
-     * { float loss; int32_t step; } and clear *loss_clear.  Any of the three may be NULL. */
+    /* optional step tail (same contract as plx_train_step / plx_train_step_host): publish the step's loss to result_host
+     * { float loss; int32_t step; } and clear *loss_clear.  The loss is *loss_src (this rank's partial) or, when
+     * loss_peers[0] != NULL, the sum over r < world of *loss_peers[r] in rank order (the global loss, identical bits on
+     * every rank; also stored to *loss_out).  Any pointer may be NULL. */
     const float* loss_src;
     float* loss_clear;
     void* result_host;
-    int32_t* counter_clear;  /* optional: the march's work counter, reset to 0 for the next step */
+    const float* loss_peers[PLX_MAX_PEERS];
+    float* loss_out;
     PlxPeerSync sync;        /* optional fused barriers (all-zero = the caller orders the kernel with plx_peer_barrier) */
 } PlxAdamPeer;
 int plx_adam_step_peer(const PlxAdamPeer* args, void* stream);
+
+/*
+ * K3s — the optimiser step of the multi-GPU "push" exchange (PlxPeerGrad): after the cross-rank barrier that follows the
+ * march, `grad` (this rank's own gradient buffer) holds the COMPLETE gradient sum of the owned slab [begin, end) (element
+ * offsets, multiples of 4), because every rank's march reduced its contributions straight into it.  The kernel is
+ * plx_adam_step over that slab with its single-GPU refinements (no |grad| store / gradient clear for untouched cells,
+ * alternating walk) whose parameter store goes to ALL replicas: one `multimem.st.v4.f32` through the NVSwitch when
+ * `grid_mc` is given, else one 16-byte store per peer pointer in `grids` (grids[rank] = the local replica).  The gradient
+ * slab is cleared in place (the next march may only start after the closing barrier, so one buffer suffices).
+ * Step tail (any pointer may be NULL): thread 0 sums loss_peers[r][0] over r < world IN RANK ORDER (every rank obtains the
+ * same bits) = the global loss of scripts/train.py:156, stores it to *loss_out and to result_host { float loss; int32
+ * step; }, and clears *loss_clear.  `err`: see PlxPeerError (a recorded failure skips every store of this kernel).
+ */
+typedef struct PlxAdamSlab {
+    int32_t world, rank;
+    float* grids[PLX_MAX_PEERS];
+    float* grid_mc;
+    float* grad;
+    float* exp_avg; float* exp_avg_sq; float* grad_abs_sum;
+    int64_t begin, end;
+    double lr, beta1, beta2, eps;
+    int64_t step;
+    const float* loss_peers[PLX_MAX_PEERS];
+    float* loss_out;
+    float* loss_clear;
+    void* result_host;
+    PlxPeerError err;
+} PlxAdamSlab;
+int plx_adam_step_slab(const PlxAdamSlab* args, void* stream);
 
 /*
  * Cross-GPU barrier on the launching stream (one tiny kernel): rank `rank` stores `epoch` into slot [channel][rank] of
  * every peer's flag array (release, system scope) and then waits until all `world` slots of its OWN array hold a value
  * >= epoch (acquire).  flags[r] = peer-mapped pointer to rank r's int32[PLX_BARRIER_CHANNELS * PLX_MAX_PEERS] array in
  * symmetric memory, zero-initialised; `epoch` must increase by one per call and channel.  Orders everything enqueued
- * before it on every rank's stream before everything enqueued after it on this rank's stream.
+ * before it on every rank's stream before everything enqueued after it on this rank's stream.  The wait is bounded and a
+ * give-up is recorded in `err` (may be NULL: 10 s, unrecorded) — see PlxPeerError.
  */
 #define PLX_BARRIER_CHANNELS 4
-int plx_peer_barrier(int32_t* const* flags, int32_t rank, int32_t world, int32_t channel, int32_t epoch, void* stream);
+int plx_peer_barrier(int32_t* const* flags, int32_t rank, int32_t world, int32_t channel, int32_t epoch,
+                     const PlxPeerError* err, void* stream);
 
 /*
  * Ray generation — generate_rays_batched, src/ray_sampling.py:195-264.
@@ -242,6 +314,8 @@ int plx_peer_barrier(int32_t* const* flags, int32_t rank, int32_t world, int32_t
  */
 int plx_generate_rays(const float* imgs, int32_t n_cams, int32_t img_h, int32_t img_w, const float* poses, float fov,
                       const float* uv, int32_t rays_per_cam, int32_t n_side, float* dirs, float* targets, void* stream);
+/* the same with the image set described by a PlxRayGen (gen->uv / gen->rays_per_cam as above; uint8 images allowed) */
+int plx_generate_rays_gen(const PlxRayGen* gen, int32_t n_side, float* dirs, float* targets, void* stream);
 
 /* Eager per-function kernels (reference semantics, materialised tensors) ------------------------------------------- */
 
@@ -291,6 +365,10 @@ int plx_avgpool3d_bwd(const float* grad_out, const int32_t dims[3], int32_t kern
  * is 0/0 (a constant grid) nothing is added.
  */
 int plx_tv_loss(const float* grid, const int32_t dims[3], float tv, float* grad, double* scratch, float* loss_out, void* stream);
+/* the same with the gradient added only for the cells [cell_begin, cell_end) (linear cell indices): the share of a rank that
+ * owns that slab of the gradient in the multi-GPU exchange; the loss value is still that of the whole grid */
+int plx_tv_loss_range(const float* grid, const int32_t dims[3], float tv, float* grad, int64_t cell_begin, int64_t cell_end,
+                      double* scratch, float* loss_out, void* stream);
 
 /*
  * Self-test of the library's exact fp32 helpers: evaluates the hoisted-reciprocal quotient x / y (the march's divisor
@@ -313,10 +391,12 @@ int plx_selftest_arith(float y, uint64_t n, uint64_t seed, uint64_t* mismatches,
 #define PLX_STEP_RENDER 1
 #define PLX_STEP_OPTIM 2
 #define PLX_STEP_ALL 3
+#define PLX_STEP_UNFUSED 4  /* OR-ed into `phase`: render with plx_generate_rays + plx_render_fwd + plx_render_bwd (three kernels and
+                               their (N,.) buffers) instead of the fused march — the path the fused kernel is checked against */
 typedef struct PlxTrainStep {
     PlxMarch march;
-    /* scene, resident on the device */
-    const float* imgs; int32_t n_cams, img_h, img_w;
+    /* scene, resident on the device (imgs: fp32 or uint8 RGBA, see img_format at the end of the struct) */
+    const void* imgs; int32_t n_cams, img_h, img_w;
     const float* poses; float fov;
     /* this step's rays */
     const float* uv; int32_t rays_per_cam;
@@ -329,11 +409,11 @@ typedef struct PlxTrainStep {
     float* dirs; float* targets; float* rgba; float* grad_rgba; float* tcarry;
     /* result */
     float* loss;
-    /* optional dynamic work distribution for the fused march (see PlxRenderTrain.work_counter): one device int32, zero
-     * before the first step; the optimiser phase resets it for the next step */
-    int32_t* work_counter;
     /* optional (multi-GPU): cross-GPU wait / signal fused into the march of the render phase (see PlxPeerSync) */
     const PlxPeerSync* render_sync;
+    /* optional (multi-GPU): push exchange — the march reduces into the slab owners' buffers instead of `grad` (PlxPeerGrad) */
+    const PlxPeerGrad* peer_grad;
+    int32_t img_format;       /* PLX_IMG_F32 | PLX_IMG_U8 */
 } PlxTrainStep;
 int plx_train_step(const PlxTrainStep* args, int32_t phase, void* stream);
 

@@ -17,7 +17,10 @@ c_void = C.c_void_p
 
 PLX_NEAREST, PLX_TRILINEAR = 0, 1
 PLX_CLAMP01, PLX_NO_CLIP, PLX_NO_EARLY_STOP, PLX_COHERENT_RAYS = 1, 2, 4, 8
-PLX_STEP_RENDER, PLX_STEP_OPTIM, PLX_STEP_ALL = 1, 2, 3
+PLX_STEP_RENDER, PLX_STEP_OPTIM, PLX_STEP_ALL, PLX_STEP_UNFUSED = 1, 2, 3, 4
+PLX_IMG_F32, PLX_IMG_U8 = 0, 1
+PLX_E_PEER_TIMEOUT = -5
+ABI_VERSION = 2
 MODES = {"nearest": PLX_NEAREST, "trilinear": PLX_TRILINEAR}
 
 
@@ -50,22 +53,31 @@ class PlxRenderBwd(C.Structure):
 
 class PlxRayGen(C.Structure):
     _fields_ = [("imgs", c_void), ("n_cams", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
-                ("poses", c_void), ("fov", C.c_float), ("uv", c_void), ("rays_per_cam", C.c_int32)]
+                ("poses", c_void), ("fov", C.c_float), ("uv", c_void), ("rays_per_cam", C.c_int32),
+                ("img_format", C.c_int32)]
 
 
 PLX_MAX_PEERS = 8
 
 
+class PlxPeerError(C.Structure):
+    _fields_ = [("device_word", c_void), ("host_word", c_void), ("timeout_ns", C.c_uint64)]
+
+
+class PlxPeerGrad(C.Structure):
+    _fields_ = [("grads", c_void * PLX_MAX_PEERS), ("owner_mul", C.c_uint32), ("world", C.c_int32)]
+
+
 class PlxPeerSync(C.Structure):
     _fields_ = [("flags", c_void * PLX_MAX_PEERS), ("rank", C.c_int32), ("world", C.c_int32),
                 ("wait_channel", C.c_int32), ("wait_epoch", C.c_int32), ("signal_channel", C.c_int32),
-                ("signal_epoch", C.c_int32), ("block_counter", c_void)]
+                ("signal_epoch", C.c_int32), ("block_counter", c_void), ("err", PlxPeerError)]
 
 
 class PlxRenderTrain(C.Structure):
     _fields_ = [("march", PlxMarch), ("rays", PlxRays), ("targets", c_void), ("gen", PlxRayGen), ("grid", c_void),
                 ("grad_grid", c_void), ("rgba", c_void), ("loss", c_void), ("grad_scale", C.c_float),
-                ("loss_scale", C.c_float), ("beta_over_m", C.c_float), ("work_counter", c_void), ("sync", PlxPeerSync)]
+                ("loss_scale", C.c_float), ("beta_over_m", C.c_float), ("sync", PlxPeerSync), ("peer_grad", PlxPeerGrad)]
 
 
 class PlxAdamPeer(C.Structure):
@@ -73,8 +85,16 @@ class PlxAdamPeer(C.Structure):
                 ("grads", c_void * PLX_MAX_PEERS), ("exp_avg", c_void), ("exp_avg_sq", c_void), ("grad_abs_sum", c_void),
                 ("begin", C.c_int64), ("end", C.c_int64), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
                 ("eps", C.c_double), ("step", C.c_int64), ("grid_mc", c_void), ("grad_mc", c_void),
-                ("loss_src", c_void), ("loss_clear", c_void), ("result_host", c_void), ("counter_clear", c_void),
-                ("sync", PlxPeerSync)]
+                ("loss_src", c_void), ("loss_clear", c_void), ("result_host", c_void),
+                ("loss_peers", c_void * PLX_MAX_PEERS), ("loss_out", c_void), ("sync", PlxPeerSync)]
+
+
+class PlxAdamSlab(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("grids", c_void * PLX_MAX_PEERS), ("grid_mc", c_void),
+                ("grad", c_void), ("exp_avg", c_void), ("exp_avg_sq", c_void), ("grad_abs_sum", c_void),
+                ("begin", C.c_int64), ("end", C.c_int64), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("eps", C.c_double), ("step", C.c_int64), ("loss_peers", c_void * PLX_MAX_PEERS), ("loss_out", c_void),
+                ("loss_clear", c_void), ("result_host", c_void), ("err", PlxPeerError)]
 
 
 class PlxTrainStep(C.Structure):
@@ -89,7 +109,8 @@ class PlxTrainStep(C.Structure):
                 ("step", C.c_int64),
                 ("beta_over_m", C.c_float),
                 ("dirs", c_void), ("targets", c_void), ("rgba", c_void), ("grad_rgba", c_void), ("tcarry", c_void),
-                ("loss", c_void), ("work_counter", c_void), ("render_sync", C.POINTER(PlxPeerSync))]
+                ("loss", c_void), ("render_sync", C.POINTER(PlxPeerSync)), ("peer_grad", C.POINTER(PlxPeerGrad)),
+                ("img_format", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/plenoxel_abi.h declares
@@ -103,7 +124,12 @@ PROTOTYPES = {
     "plx_adam_step": (C.c_int, [c_void, c_void, c_void, c_void, c_void, C.c_int64, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_int64, C.c_int32, c_void]),
     "plx_adam_step_peer": (C.c_int, [C.POINTER(PlxAdamPeer), c_void]),
-    "plx_peer_barrier": (C.c_int, [C.POINTER(c_void), C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_void]),
+    "plx_adam_step_slab": (C.c_int, [C.POINTER(PlxAdamSlab), c_void]),
+    "plx_slab_partition": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_int64)]),
+    "plx_peer_barrier": (C.c_int, [C.POINTER(c_void), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(PlxPeerError),
+                                   c_void]),
+    "plx_generate_rays_gen": (C.c_int, [C.POINTER(PlxRayGen), C.c_int32, c_void, c_void, c_void]),
     "plx_generate_rays": (C.c_int, [c_void, C.c_int32, C.c_int32, C.c_int32, c_void, C.c_float, c_void, C.c_int32,
                                     C.c_int32, c_void, c_void, c_void]),
     "plx_sample_points": (C.c_int, [C.POINTER(PlxRays), C.c_int32, C.c_float, c_void, c_void]),
@@ -119,6 +145,8 @@ PROTOTYPES = {
     "plx_avgpool3d_fwd": (C.c_int, [c_void, C.POINTER(C.c_int32), C.c_int32, C.c_int32, c_void, c_void, c_void, c_void]),
     "plx_avgpool3d_bwd": (C.c_int, [c_void, C.POINTER(C.c_int32), C.c_int32, C.c_int32, c_void, c_void, c_void, c_void]),
     "plx_tv_loss": (C.c_int, [c_void, C.POINTER(C.c_int32), C.c_float, c_void, c_void, c_void, c_void]),
+    "plx_tv_loss_range": (C.c_int, [c_void, C.POINTER(C.c_int32), C.c_float, c_void, C.c_int64, C.c_int64, c_void, c_void,
+                                    c_void]),
     "plx_selftest_arith": (C.c_int, [C.c_float, C.c_uint64, C.c_uint64, c_void, c_void]),
     "plx_train_step": (C.c_int, [C.POINTER(PlxTrainStep), C.c_int32, c_void]),
     "plx_train_step_host": (C.c_int, [C.POINTER(PlxTrainStep), c_void, c_void, C.c_int32, c_void]),
@@ -145,7 +173,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header / library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.plx_version() != 1:
+    if lib.plx_version() != ABI_VERSION:
         raise PlxError(f"ABI version mismatch: library reports {lib.plx_version()}")
     _lib = lib
     return lib

@@ -94,6 +94,40 @@ static int check_sync(const PlxPeerSync& s, bool has_work) {
     return PLX_OK;
 }
 
+// push exchange: `world` peer-mapped gradient buffers and the owner multiplier of plx_slab_partition; contiguous grids only
+static int check_peer_grad(const PlxPeerGrad& p, const PlxMarch& m, const float* grid) {
+    if (p.world == 0) return PLX_OK;
+    if (p.world < 1 || p.world > PLX_MAX_PEERS) return fail(PLX_E_SHAPE, "peer_grad: world must be 1..%d", PLX_MAX_PEERS);
+    for (int r = 0; r < p.world; ++r) {
+        if (!p.grads[r]) return fail(PLX_E_NULL, "peer_grad: gradient buffer of rank %d is NULL", r);
+        if ((uintptr_t)p.grads[r] % 16) return fail(PLX_E_ALIGN, "peer_grad: gradient buffers must be 16-byte aligned");
+    }
+    const int64_t cells = (int64_t)m.nx * m.ny * m.nz;
+    uint32_t mul = 0;
+    if (plx_slab_partition(cells, p.world, 0, &mul, nullptr, nullptr) != PLX_OK) return PLX_E_SHAPE;
+    if (mul != p.owner_mul) return fail(PLX_E_SHAPE, "peer_grad: owner_mul %u does not match plx_slab_partition (%u)", p.owner_mul, mul);
+    if (!(m.sc == 1 && m.sz == 4 && m.sy == 4 * (int64_t)m.nz && m.sx == 4 * (int64_t)m.nz * m.ny) || (uintptr_t)grid % 16)
+        return fail(PLX_E_UNSUPPORTED, "peer_grad: the push exchange needs a contiguous, 16-byte aligned (X,Y,Z,4) grid");
+    if (m.mode != PLX_NEAREST && m.mode != PLX_TRILINEAR) return fail(PLX_E_UNSUPPORTED, "peer_grad: unknown mode");
+    return PLX_OK;
+}
+
+int plx_slab_partition(int64_t n_cells, int32_t world, int32_t rank, uint32_t* owner_mul, int64_t* begin_cell, int64_t* end_cell) {
+    if (world < 1 || world > PLX_MAX_PEERS || rank < 0 || rank >= world) return fail(PLX_E_SHAPE, "slab partition: bad world / rank");
+    if (n_cells <= world || n_cells > 0x7fffffffLL) return fail(PLX_E_SHAPE, "slab partition: need world < n_cells < 2^31 (got %lld)", (long long)n_cells);
+    const unsigned __int128 one = (unsigned __int128)1 << 32;
+    const uint64_t mul = (uint64_t)((one * (unsigned)world) / (uint64_t)n_cells);        // < 2^32 because n_cells > world
+    auto first_of = [&](int r) -> int64_t {                                              // smallest lin with umulhi(lin, mul) >= r
+        const unsigned __int128 num = one * (unsigned)r;
+        const int64_t b = (int64_t)((num + mul - 1) / mul);
+        return b > n_cells ? n_cells : b;
+    };
+    if (owner_mul) *owner_mul = (uint32_t)mul;
+    if (begin_cell) *begin_cell = first_of(rank);
+    if (end_cell) *end_cell = rank + 1 == world ? n_cells : first_of(rank + 1);
+    return PLX_OK;
+}
+
 int plx_render_train(const PlxRenderTrain* a, void* stream) {
     if (!a) return fail(PLX_E_NULL, "args is NULL");
     int rc;
@@ -108,13 +142,15 @@ int plx_render_train(const PlxRenderTrain* a, void* stream) {
         if (a->gen.img_h <= 0 || a->gen.img_h != a->gen.img_w)
             return fail(PLX_E_UNSUPPORTED, "in-kernel ray generation needs square images (src/ray_sampling.py:238-248), got %dx%d", a->gen.img_h, a->gen.img_w);
         if ((int64_t)a->gen.n_cams * a->gen.rays_per_cam != a->rays.n_rays) return fail(PLX_E_SHAPE, "n_rays != n_cams * rays_per_cam");
-        if ((uintptr_t)a->gen.imgs % 16) return fail(PLX_E_ALIGN, "imgs must be 16-byte aligned");
+        if ((uintptr_t)a->gen.imgs % (a->gen.img_format == PLX_IMG_U8 ? 4 : 16)) return fail(PLX_E_ALIGN, "imgs must be 16-byte (fp32) / 4-byte (uint8) aligned");
     } else {
         if ((rc = check_rays(a->rays)) != PLX_OK) return rc;
         if (!a->targets) return fail(PLX_E_NULL, "targets is NULL");
         if ((uintptr_t)a->targets % 16) return fail(PLX_E_ALIGN, "targets must be 16-byte aligned");
     }
-    if (!plx::render_train_supported(*a)) return fail(PLX_E_UNSUPPORTED, "fused training march: nearest mode and num_samples within the shared-memory cache only");
+    if (a->gen.uv && a->gen.img_format != PLX_IMG_F32 && a->gen.img_format != PLX_IMG_U8) return fail(PLX_E_UNSUPPORTED, "unknown image format %d", a->gen.img_format);
+    if (!plx::render_train_supported(*a)) return fail(PLX_E_UNSUPPORTED, "fused training march: num_samples beyond the shared-memory cache or grid beyond 32-bit cell indices");
+    if ((rc = check_peer_grad(a->peer_grad, a->march, a->grid)) != PLX_OK) return rc;
     return cuda_result(plx::launch_render_train(*a, (cudaStream_t)stream), "plx_render_train");
 }
 
@@ -131,7 +167,6 @@ static plx::AdamScalars adam_scalars(double lr, double beta1, double beta2, doub
     s.neg_step_size = (float)(-(lr / bc1));
     s.keep_p = s.keep_g = false;
     s.reverse = (step & 1) != 0;
-    s.stream_state = true;
     return s;
 }
 
@@ -141,7 +176,7 @@ int plx_adam_step(float* p, float* g, float* m, float* v, float* gabs, int64_t n
     if (n > 0 && (!p || !g || !m || !v)) return fail(PLX_E_NULL, "p/g/m/v is NULL");
     if (step < 1) return fail(PLX_E_SHAPE, "step counts from 1");
     return cuda_result(plx::launch_adam(p, g, m, v, gabs, n, adam_scalars(lr, beta1, beta2, eps, step), zero_grad != 0,
-                                        plx::StepTail{nullptr, nullptr, nullptr, 0, nullptr}, (cudaStream_t)stream), "plx_adam_step");
+                                        plx::StepTail{nullptr, nullptr, nullptr, 0}, (cudaStream_t)stream), "plx_adam_step");
 }
 
 int plx_adam_step_peer(const PlxAdamPeer* a, void* stream) {
@@ -159,17 +194,48 @@ int plx_adam_step_peer(const PlxAdamPeer* a, void* stream) {
         return fail(PLX_E_ALIGN, "optimizer state must be 16-byte aligned");
     int rc;
     if ((rc = check_sync(a->sync, a->end > a->begin)) != PLX_OK) return rc;
-    const plx::StepTail tail{a->loss_src, a->loss_clear, (float*)a->result_host, (int32_t)a->step, a->counter_clear};
+    plx::StepTail tail{a->loss_src, a->loss_clear, (float*)a->result_host, (int32_t)a->step};
+    if (a->loss_peers[0]) {
+        for (int r = 0; r < a->world; ++r) {
+            if (!a->loss_peers[r]) return fail(PLX_E_NULL, "loss accumulator of rank %d is NULL", r);
+            tail.src_peers[r] = a->loss_peers[r];
+        }
+        tail.n_peers = a->world;
+        tail.global_out = a->loss_out;
+    }
     return cuda_result(plx::launch_adam_peer(*a, adam_scalars(a->lr, a->beta1, a->beta2, a->eps, a->step), tail, (cudaStream_t)stream),
                        "plx_adam_step_peer");
 }
 
-int plx_peer_barrier(int32_t* const* flags, int32_t rank, int32_t world, int32_t channel, int32_t epoch, void* stream) {
+int plx_adam_step_slab(const PlxAdamSlab* a, void* stream) {
+    if (!a) return fail(PLX_E_NULL, "args is NULL");
+    if (a->world < 1 || a->world > PLX_MAX_PEERS || a->rank < 0 || a->rank >= a->world)
+        return fail(PLX_E_SHAPE, "world must be 1..%d and 0 <= rank < world (got world %d, rank %d)", PLX_MAX_PEERS, a->world, a->rank);
+    if (a->begin < 0 || a->end < a->begin || a->begin % 4 || a->end % 4) return fail(PLX_E_SHAPE, "owned range must be multiples of 4 floats");
+    if (a->step < 1) return fail(PLX_E_SHAPE, "step counts from 1");
+    if (!a->exp_avg || !a->exp_avg_sq || !a->grad) return fail(PLX_E_NULL, "grad/exp_avg/exp_avg_sq is NULL");
+    for (int r = 0; r < a->world; ++r) {
+        if (!a->grids[r]) return fail(PLX_E_NULL, "grid pointer of rank %d is NULL", r);
+        if ((uintptr_t)a->grids[r] % 16) return fail(PLX_E_ALIGN, "peer buffers must be 16-byte aligned");
+    }
+    if ((uintptr_t)a->exp_avg % 16 || (uintptr_t)a->exp_avg_sq % 16 || (uintptr_t)a->grad_abs_sum % 16 || (uintptr_t)a->grad % 16 ||
+        (uintptr_t)a->grid_mc % 16)
+        return fail(PLX_E_ALIGN, "optimizer state must be 16-byte aligned");
+    if ((uintptr_t)a->result_host % 8) return fail(PLX_E_ALIGN, "result_host must be 8-byte aligned");
+    if (a->loss_peers[0])
+        for (int r = 0; r < a->world; ++r) if (!a->loss_peers[r]) return fail(PLX_E_NULL, "loss accumulator of rank %d is NULL", r);
+    return cuda_result(plx::launch_adam_slab(*a, adam_scalars(a->lr, a->beta1, a->beta2, a->eps, a->step), (cudaStream_t)stream),
+                       "plx_adam_step_slab");
+}
+
+int plx_peer_barrier(int32_t* const* flags, int32_t rank, int32_t world, int32_t channel, int32_t epoch, const PlxPeerError* err,
+                     void* stream) {
     if (!flags) return fail(PLX_E_NULL, "flags is NULL");
     if (world < 1 || world > PLX_MAX_PEERS || rank < 0 || rank >= world) return fail(PLX_E_SHAPE, "bad world / rank");
     if (channel < 0 || channel >= PLX_BARRIER_CHANNELS) return fail(PLX_E_SHAPE, "channel out of range");
     for (int r = 0; r < world; ++r) if (!flags[r]) return fail(PLX_E_NULL, "flag array of rank %d is NULL", r);
-    return cuda_result(plx::launch_peer_barrier(flags, rank, world, channel, epoch, (cudaStream_t)stream), "plx_peer_barrier");
+    const PlxPeerError none{nullptr, nullptr, 0};
+    return cuda_result(plx::launch_peer_barrier(flags, rank, world, channel, epoch, err ? *err : none, (cudaStream_t)stream), "plx_peer_barrier");
 }
 
 int plx_generate_rays(const float* imgs, int32_t n_cams, int32_t img_h, int32_t img_w, const float* poses, float fov,
@@ -187,8 +253,28 @@ int plx_generate_rays(const float* imgs, int32_t n_cams, int32_t img_h, int32_t 
         if (img_h != img_w) return fail(PLX_E_UNSUPPORTED, "non-square images index out of range in the reference (H=%d, W=%d)", img_h, img_w);
         if ((uintptr_t)imgs % 16 || (uintptr_t)targets % 16) return fail(PLX_E_ALIGN, "imgs/targets must be 16-byte aligned");
     }
-    return cuda_result(plx::launch_generate_rays(imgs, n_cams, img_h, img_w, poses, fov, uv, rays_per_cam, n_side, dirs,
-                                                 targets, (cudaStream_t)stream), "plx_generate_rays");
+    PlxRayGen gen;
+    gen.imgs = imgs; gen.n_cams = n_cams; gen.img_h = img_h; gen.img_w = img_w; gen.poses = poses; gen.fov = fov; gen.uv = uv;
+    gen.rays_per_cam = rays_per_cam; gen.img_format = PLX_IMG_F32;
+    return cuda_result(plx::launch_generate_rays(gen, n_side, dirs, targets, (cudaStream_t)stream), "plx_generate_rays");
+}
+
+int plx_generate_rays_gen(const PlxRayGen* gen, int32_t n_side, float* dirs, float* targets, void* stream) {
+    if (!gen) return fail(PLX_E_NULL, "gen is NULL");
+    if (gen->img_format == PLX_IMG_F32)
+        return plx_generate_rays((const float*)gen->imgs, gen->n_cams, gen->img_h, gen->img_w, gen->poses, gen->fov, gen->uv, gen->rays_per_cam,
+                                 n_side, dirs, targets, stream);
+    if (gen->img_format != PLX_IMG_U8) return fail(PLX_E_UNSUPPORTED, "unknown image format %d", gen->img_format);
+    if (gen->n_cams < 0 || gen->rays_per_cam < 0) return fail(PLX_E_SHAPE, "negative camera / ray count");
+    if (gen->n_cams == 0 || gen->rays_per_cam == 0) return PLX_OK;
+    if (!gen->poses || !dirs) return fail(PLX_E_NULL, "poses/dirs is NULL");
+    if (!gen->uv && (n_side <= 0 || n_side * n_side != gen->rays_per_cam)) return fail(PLX_E_SHAPE, "even-spread lattice needs rays_per_cam == n_side^2");
+    if (targets) {
+        if (!gen->imgs) return fail(PLX_E_NULL, "imgs is NULL but targets requested");
+        if (gen->img_h <= 0 || gen->img_h != gen->img_w) return fail(PLX_E_UNSUPPORTED, "non-square images index out of range in the reference (H=%d, W=%d)", gen->img_h, gen->img_w);
+        if ((uintptr_t)gen->imgs % 4 || (uintptr_t)targets % 16) return fail(PLX_E_ALIGN, "imgs (uint8 RGBA) must be 4-byte, targets 16-byte aligned");
+    }
+    return cuda_result(plx::launch_generate_rays(*gen, n_side, dirs, targets, (cudaStream_t)stream), "plx_generate_rays_gen");
 }
 
 int plx_sample_points(const PlxRays* rays, int32_t num_samples, float delta_step, float* samples, void* stream) {
@@ -290,11 +376,19 @@ int plx_avgpool3d_bwd(const float* grad_out, const int32_t dims[3], int32_t kern
     return cuda_result(plx::launch_avgpool3d_bwd(grad_out, dims, kernel, stride, tmp2, tmp1, grad_in, (cudaStream_t)stream), "plx_avgpool3d_bwd");
 }
 
-int plx_tv_loss(const float* grid, const int32_t dims[3], float tv, float* grad, double* scratch, float* loss_out, void* stream) {
+int plx_tv_loss_range(const float* grid, const int32_t dims[3], float tv, float* grad, int64_t cell_begin, int64_t cell_end,
+                      double* scratch, float* loss_out, void* stream) {
     if (!dims || !grid || !scratch) return fail(PLX_E_NULL, "grid/dims/scratch is NULL");
     if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return fail(PLX_E_SHAPE, "grid dims must be positive");
     if ((uintptr_t)grid % 16 || (uintptr_t)grad % 16 || (uintptr_t)scratch % 8) return fail(PLX_E_ALIGN, "tv buffers are misaligned");
-    return cuda_result(plx::launch_tv_loss(grid, dims, tv, grad, scratch, loss_out, (cudaStream_t)stream), "plx_tv_loss");
+    const int64_t n = (int64_t)dims[0] * dims[1] * dims[2];
+    if (cell_begin < 0 || cell_end < cell_begin || cell_end > n) return fail(PLX_E_SHAPE, "cell range outside the grid");
+    return cuda_result(plx::launch_tv_loss(grid, dims, tv, grad, cell_begin, cell_end, scratch, loss_out, (cudaStream_t)stream), "plx_tv_loss");
+}
+
+int plx_tv_loss(const float* grid, const int32_t dims[3], float tv, float* grad, double* scratch, float* loss_out, void* stream) {
+    if (!dims) return fail(PLX_E_NULL, "grid/dims/scratch is NULL");
+    return plx_tv_loss_range(grid, dims, tv, grad, 0, (int64_t)dims[0] * dims[1] * dims[2], scratch, loss_out, stream);
 }
 
 int plx_selftest_arith(float y, uint64_t n, uint64_t seed, uint64_t* mismatches, void* stream) {
@@ -318,26 +412,26 @@ static int train_step_impl(const PlxTrainStep* a, const float* uv, void* result_
         if (a->n_rays_global < n_rays) return fail(PLX_E_SHAPE, "n_rays_global < local ray count");
         const float grad_scale = (float)(2.0 / (4.0 * (double)a->n_rays_global));
         const float loss_scale = (float)(1.0 / (4.0 * (double)a->n_rays_global));
-        // preferred: one fused kernel (ray generation + forward + loss + backward); PLX_TRAIN_FUSED=0 forces the 3-kernel path
-        static const bool allow_fused = !(std::getenv("PLX_TRAIN_FUSED") && std::getenv("PLX_TRAIN_FUSED")[0] == '0');
+        // preferred: one fused kernel (ray generation + forward + loss + backward); PLX_STEP_UNFUSED asks for the 3-kernel path
+        const bool allow_fused = !(phase & PLX_STEP_UNFUSED);
         PlxRenderTrain t;
         std::memset(&t, 0, sizeof(t));
         t.march = a->march;
         t.rays.n_rays = n_rays;
         t.gen.imgs = a->imgs; t.gen.n_cams = a->n_cams; t.gen.img_h = a->img_h; t.gen.img_w = a->img_w;
         t.gen.poses = a->poses; t.gen.fov = a->fov; t.gen.uv = uv; t.gen.rays_per_cam = a->rays_per_cam;
+        t.gen.img_format = a->img_format;
+        if (a->peer_grad) t.peer_grad = *a->peer_grad;
         t.grid = a->grid; t.grad_grid = a->grad; t.rgba = a->rgba; t.loss = loss_now;
         t.grad_scale = grad_scale; t.loss_scale = loss_scale; t.beta_over_m = a->beta_over_m;
-        t.work_counter = a->work_counter;
         if (a->render_sync) t.sync = *a->render_sync;
         const bool synced = t.sync.wait_epoch > 0 || t.sync.signal_epoch > 0;
-        if (synced && !(allow_fused && a->img_h == a->img_w && plx::render_train_supported(t)))
-            return fail(PLX_E_UNSUPPORTED, "train step: render_sync needs the fused march (nearest mode, square images)");
+        if ((synced || t.peer_grad.world > 0) && !(allow_fused && a->img_h == a->img_w && plx::render_train_supported(t)))
+            return fail(PLX_E_UNSUPPORTED, "train step: render_sync / peer_grad need the fused march (square images, samples within the shared-memory cache)");
         if (allow_fused && a->img_h == a->img_w && plx::render_train_supported(t)) {
             if ((rc = plx_render_train(&t, stream)) != PLX_OK) return rc;
         } else {
-            if ((rc = plx_generate_rays(a->imgs, a->n_cams, a->img_h, a->img_w, a->poses, a->fov, uv, a->rays_per_cam, 0,
-                                        a->dirs, a->targets, stream)) != PLX_OK) return rc;
+            if ((rc = plx_generate_rays_gen(&t.gen, 0, a->dirs, a->targets, stream)) != PLX_OK) return rc;
             PlxRenderFwd f;
             std::memset(&f, 0, sizeof(f));
             f.march = a->march;
@@ -365,7 +459,7 @@ static int train_step_impl(const PlxTrainStep* a, const float* uv, void* result_
         const int64_t n = (int64_t)a->march.nx * a->march.ny * a->march.nz * 4;
         if (n > 0 && (!a->grid || !a->grad || !a->exp_avg || !a->exp_avg_sq)) return fail(PLX_E_NULL, "train step: optimiser state is NULL");
         if (a->step < 1) return fail(PLX_E_SHAPE, "step counts from 1");
-        const plx::StepTail tail{loss_now, loss_next, (float*)result_host, (int32_t)a->step, a->work_counter};
+        const plx::StepTail tail{loss_now, loss_next, (float*)result_host, (int32_t)a->step};
         return cuda_result(plx::launch_adam(a->grid, a->grad, a->exp_avg, a->exp_avg_sq, a->grad_abs_sum, n,
                                             adam_scalars(a->lr, a->beta1, a->beta2, a->eps, a->step), true, tail,
                                             (cudaStream_t)stream), "plx_train_step(optim)");

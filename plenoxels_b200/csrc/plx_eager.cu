@@ -17,32 +17,28 @@ static inline unsigned blocks_for(int64_t n, int threads) {
 // ---------------------------------------------------------------------------------------------------------------
 // generate_rays_batched — src/ray_sampling.py:195-264
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_generate_rays(const float* __restrict__ imgs, int n_cams, int H, int W,
-                                                       const float* __restrict__ poses, float fov,
-                                                       const float* __restrict__ uv, int R, int n_side,
-                                                       float* __restrict__ dirs, float* __restrict__ targets) {
-    const int64_t n = (int64_t)n_cams * R;
+__global__ void __launch_bounds__(256) k_generate_rays(const PlxRayGen gen, int n_side, float* __restrict__ dirs,
+                                                       float* __restrict__ targets) {
+    const int R = gen.rays_per_cam;
+    const int64_t n = (int64_t)gen.n_cams * R;
     for (int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ray < n; ray += (int64_t)gridDim.x * blockDim.x) {
         const int cam = (int)(ray / R), j = (int)(ray % R);
         float u, v;
-        if (uv) { u = __ldg(uv + ray * 2); v = __ldg(uv + ray * 2 + 1); }
+        if (gen.uv) { u = __ldg(gen.uv + ray * 2); v = __ldg(gen.uv + ray * 2 + 1); }
         else { u = linspace01(j / n_side, n_side); v = linspace01(j % n_side, n_side); }     // cartesian_prod, u-major (:223)
-        const RayOut o = ray_from_uv(poses + (int64_t)cam * 16, fov, u, v, H, W);
+        const RayOut o = ray_from_uv(gen.poses + (int64_t)cam * 16, gen.fov, u, v, gen.img_h, gen.img_w);
         if (targets)                                                                                      // :248
-            reinterpret_cast<float4*>(targets)[ray] = __ldg(reinterpret_cast<const float4*>(imgs) + ((int64_t)cam * H + o.vp) * W + o.up);
+            reinterpret_cast<float4*>(targets)[ray] = load_target(gen, ((int64_t)cam * gen.img_h + o.vp) * gen.img_w + o.up);
         dirs[ray * 3 + 0] = o.dx;
         dirs[ray * 3 + 1] = o.dy;
         dirs[ray * 3 + 2] = o.dz;
     }
 }
 
-cudaError_t launch_generate_rays(const float* imgs, int n_cams, int img_h, int img_w, const float* poses, float fov,
-                                 const float* uv, int rays_per_cam, int n_side, float* dirs, float* targets,
-                                 cudaStream_t st) {
-    const int64_t n = (int64_t)n_cams * rays_per_cam;
+cudaError_t launch_generate_rays(const PlxRayGen& gen, int n_side, float* dirs, float* targets, cudaStream_t st) {
+    const int64_t n = (int64_t)gen.n_cams * gen.rays_per_cam;
     if (n == 0) return cudaSuccess;
-    k_generate_rays<<<blocks_for(n, 256), 256, 0, st>>>(imgs, n_cams, img_h, img_w, poses, fov, uv, rays_per_cam, n_side,
-                                                        dirs, targets);
+    k_generate_rays<<<blocks_for(n, 256), 256, 0, st>>>(gen, n_side, dirs, targets);
     return cudaGetLastError();
 }
 

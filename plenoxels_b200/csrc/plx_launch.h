@@ -24,33 +24,36 @@ struct AdamScalars {
     float neg_step_size;     // -lr / (1 - beta1^step)
     bool keep_p, keep_g;     // L2 evict_last tags for parameters / gradient (set by launch_adam)
     bool reverse;            // walk the arrays from the top down (odd steps): the tail the previous step left in L2 is read first
-    bool stream_state;       // m / v / |g| with evict-first (.cs) accesses
 };
 // what one thread of the optimiser kernel does besides Adam: publish this step's loss to pinned host memory
 // { float loss; int32 step } and clear the other loss slot for the next step
 struct StepTail {
-    const float* src;
+    const float* src;        // this rank's loss accumulator of the step ...
     float* clear;
     float* dst_host;
     int32_t step;
-    int32_t* counter_clear;  // the fused march's work counter, reset for the next step
+    // ... or (multi-GPU) every rank's accumulator, peer-mapped: summed in rank order = the global loss, same bits on every rank;
+    // the sum is also stored to *global_out (device) so that `loss` reads the same on the device path
+    const float* src_peers[PLX_MAX_PEERS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int32_t n_peers = 0;
+    float* global_out = nullptr;
 };
 cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int64_t n, const AdamScalars& s,
                         bool zero_grad, const StepTail& tail, cudaStream_t st);
 
 cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, const StepTail& tail, cudaStream_t st);
+cudaError_t launch_adam_slab(const PlxAdamSlab& a, const AdamScalars& s, cudaStream_t st);
 
 cudaError_t launch_avgpool3d_fwd(const float* in, const int32_t* dims, int k, int s, float* tmp1, float* tmp2, float* out,
                                  cudaStream_t st);
 cudaError_t launch_avgpool3d_bwd(const float* gout, const int32_t* dims, int k, int s, float* tmp2, float* tmp1, float* gin,
                                  cudaStream_t st);
-cudaError_t launch_tv_loss(const float* grid, const int32_t* dims, float tv, float* grad, double* scratch, float* loss_out,
-                           cudaStream_t st);
-cudaError_t launch_peer_barrier(int32_t* const* flags, int rank, int world, int channel, int epoch, cudaStream_t st);
+cudaError_t launch_tv_loss(const float* grid, const int32_t* dims, float tv, float* grad, int64_t cell_begin, int64_t cell_end,
+                           double* scratch, float* loss_out, cudaStream_t st);
+cudaError_t launch_peer_barrier(int32_t* const* flags, int rank, int world, int channel, int epoch, const PlxPeerError& err,
+                                cudaStream_t st);
 
-cudaError_t launch_generate_rays(const float* imgs, int n_cams, int img_h, int img_w, const float* poses, float fov,
-                                 const float* uv, int rays_per_cam, int n_side, float* dirs, float* targets,
-                                 cudaStream_t st);
+cudaError_t launch_generate_rays(const PlxRayGen& gen, int n_side, float* dirs, float* targets, cudaStream_t st);
 cudaError_t launch_sample_points(const PlxRays& rays, int S, float delta, float* out, cudaStream_t st);
 cudaError_t launch_normalize_points(const float* in, int64_t m, float gx, float gy, float gz, float pd, float* out,
                                     cudaStream_t st);

@@ -104,13 +104,14 @@ __global__ void __launch_bounds__(256) k_tv_sumsq(const float4* __restrict__ g, 
 }
 
 __global__ void __launch_bounds__(256) k_tv_grad(const float4* __restrict__ g, int X, int Y, int Z, const double* __restrict__ sum,
-                                                 float tv, float4* __restrict__ grad, float* __restrict__ loss_out) {
+                                                 float tv, float4* __restrict__ grad, int64_t cell_begin, int64_t cell_end,
+                                                 float* __restrict__ loss_out) {
     const double S = *sum;
     if (blockIdx.x == 0 && threadIdx.x == 0 && loss_out) *loss_out = tv * (float)sqrt(S);
     if (!(S > 0.0) || !grad) return;               // the reference's gradient is 0/0 here; we add nothing
     const float scale = tv / (float)sqrt(S);
-    const int64_t n = (int64_t)X * Y * Z, sx = (int64_t)Z * Y;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t sx = (int64_t)Z * Y;
+    for (int64_t e = cell_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < cell_end; e += (int64_t)gridDim.x * blockDim.x) {
         const int z = (int)(e % Z), y = (int)((e / Z) % Y), x = (int)(e / sx);
         const float4 c = __ldg(g + e);
         float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -127,14 +128,14 @@ __global__ void __launch_bounds__(256) k_tv_grad(const float4* __restrict__ g, i
     }
 }
 
-cudaError_t launch_tv_loss(const float* grid, const int32_t* dims, float tv, float* grad, double* scratch, float* loss_out,
-                           cudaStream_t st) {
+cudaError_t launch_tv_loss(const float* grid, const int32_t* dims, float tv, float* grad, int64_t cell_begin, int64_t cell_end,
+                           double* scratch, float* loss_out, cudaStream_t st) {
     const int X = dims[0], Y = dims[1], Z = dims[2];
     const int64_t n = (int64_t)X * Y * Z;
     cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double), st);
     if (e != cudaSuccess) return e;
     k_tv_sumsq<<<pool_blocks(n), 256, 0, st>>>((const float4*)grid, X, Y, Z, scratch);
-    k_tv_grad<<<pool_blocks(n), 256, 0, st>>>((const float4*)grid, X, Y, Z, scratch, tv, (float4*)grad, loss_out);
+    k_tv_grad<<<pool_blocks(cell_end - cell_begin), 256, 0, st>>>((const float4*)grid, X, Y, Z, scratch, tv, (float4*)grad, cell_begin, cell_end, loss_out);
     return cudaGetLastError();
 }
 

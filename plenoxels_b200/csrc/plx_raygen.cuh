@@ -45,4 +45,15 @@ __device__ __forceinline__ RayOut ray_from_uv(const float* __restrict__ P, float
     return o;
 }
 
+// target pixel `idx` (= (cam*H + v_pix)*W + u_pix) of the image set: fp32 RGBA as the reference keeps it, or the PNG's uint8 RGBA
+// converted here exactly like src/data_processing.py:58 does it once for the whole set (fp32(u8) / 255, IEEE division)
+__device__ __forceinline__ float4 load_target(const PlxRayGen& gen, int64_t idx) {
+    if (gen.img_format == PLX_IMG_U8) {
+        const uchar4 p = __ldg(reinterpret_cast<const uchar4*>(gen.imgs) + idx);
+        return make_float4(__fdiv_rn((float)p.x, 255.f), __fdiv_rn((float)p.y, 255.f), __fdiv_rn((float)p.z, 255.f),
+                           __fdiv_rn((float)p.w, 255.f));
+    }
+    return __ldg(reinterpret_cast<const float4*>(gen.imgs) + idx);
+}
+
 }  // namespace plx

@@ -40,248 +40,286 @@ __device__ __forceinline__ void composite_iter(const float4 (&c)[SPL], int lane,
     T *= total;
 }
 
-template <bool FAST, int SPL, int MINB, bool PIPE>
-__global__ void __launch_bounds__(128, MINB) k_render_train(const PlxRenderTrain a, int lin_words, int warp_words) {
+// where the gradient of cell `lin` goes: the local buffer, or (multi-GPU push exchange, PlxPeerGrad) the buffer of the rank
+// that owns the cell's slab — a peer-mapped pointer, so the reduction travels over NVLink and lands in the owner's L2
+template <bool PEER>
+struct GradDst {
+    float* local;
+    float* const* peers;     // shared-memory copy of PlxPeerGrad.grads
+    uint32_t owner_mul;
+    uint64_t pol;
+    __device__ __forceinline__ void add(int lin, float x, float y, float z, float w) const {
+        if (PEER) red_add_v4(peers[__umulhi((uint32_t)lin, owner_mul)] + (int64_t)lin * 4, x, y, z, w);
+        else      red_add_v4_hint(local + (int64_t)lin * 4, x, y, z, w, pol);
+    }
+};
+
+// per-warp scratch of one ray
+struct RayScratch {
+    int* lc;        // cached linear cell index of every visited sample
+    float* tcs;     // transmittance in front of every iteration
+};
+
+// One ray, start to finish: forward march + compositing, MSE gradient, reverse march + scatter-add.  Returns the ray's loss.
+// FR (fast ray): every coordinate of the ray is in the hoisted-division range — the common case, compiled without any
+// slow-path call in its loops; the FR = false instantiation (coordinates near the ends of the fp32 range, NaN / inf) is the
+// same code on __fdiv_rn and the float bounds test, kept out of line.
+template <bool FAST, bool FR, int SPL, bool PIPE, bool PEER>
+__device__ __forceinline__ float train_ray(const PlxRenderTrain& a, const Geo& g, const GradDst<PEER>& dst, const RayScratch& sc,
+                                           const Ray& r, const float4 tgt, const int64_t ray, const int lane) {
+    constexpr int W = 32 * SPL;
+    const PlxMarch& m = a.march;
+    int* lc = sc.lc;
+    float* tcs = sc.tcs;
+    const float bom = a.beta_over_m;
+    const bool full = bom != 0.f;        // the sparsity term touches every in-bounds sample: no early stop
+    int k0, k1;
+    clip_range(m, r, k0, k1);
+    const int n_it = k0 <= k1 ? (k1 - k0) / W + 1 : 0;
+
+    // ---------------------------------------------------------------------------------------- forward
+    float T = 1.f, T2 = 1.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = acc;
+    bool opaque = false;                 // segment 1 ended on an alpha == 1 sample at (zl, zj)
+    int zl = 0, zj = 0;
+    int it = 0;
+    // software pipeline: the cells of iteration it+1 are requested before iteration it is composited, so the gather
+    // latency (L2 / HBM) overlaps the scans instead of stalling the warp at the first use
+    float4 rawn[SPL];
+    int linn[SPL];
+    auto fetch = [&](int i) {
+        const int kb = k0 + i * W + lane * SPL;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) linn[j] = fetch_nearest<FAST>(m, g, a.grid, r, FR, kb + j, kb + j <= k1, rawn[j]);
+    };
+    if (PIPE && n_it > 0) fetch(0);
+    for (; it < n_it; ++it) {
+        float4 c[SPL];
+        int lin[SPL];
+        if (!PIPE) fetch(it);
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) { c[j] = g.clamp ? clamp4(rawn[j]) : rawn[j]; lin[j] = linn[j]; }
+        if (PIPE && it + 1 < n_it) fetch(it + 1);
+        if (SPL == 1) lc[it * W + lane] = lin[0];
+        else *reinterpret_cast<int2*>(lc + it * W + lane * 2) = make_int2(lin[0], lin[SPL - 1]);
+        if (lane == 0) tcs[it] = T;
+        // empty space is the common case (a trained grid is mostly alpha == 0, fit() even starts from all zeros):
+        // an iteration whose 32*SPL samples are all transparent changes neither T nor the pixel — skip its scan
+        bool any_alpha = false;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) any_alpha = any_alpha || c[j].w != 0.f;
+        if (!__any_sync(FULL, any_alpha)) continue;
+        composite_iter<SPL>(c, lane, T, acc);
+        if (T == 0.f && !full) {
+            // first sample whose factor is exactly 0 (alpha == 1); none => the product merely underflowed
+            int jz = SPL;
+#pragma unroll
+            for (int j = SPL - 1; j >= 0; --j) if (c[j].w == 1.f) jz = j;
+            const unsigned hit = __ballot_sync(FULL, jz < SPL);
+            if (hit) {
+                opaque = true;
+                zl = __ffs(hit) - 1;
+                zj = __shfl_sync(FULL, jz, zl);
+                float4 c2[SPL];
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    const bool after = lane > zl || (lane == zl && j > zj);
+                    c2[j] = after ? c[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                composite_iter<SPL>(c2, lane, T2, acc2);
+            }
+            ++it;
+            break;
+        }
+    }
+    const int n_fwd = it;                // iterations of segment 1 (their indices are cached)
+    if (opaque) {                        // keep compositing behind k* until that segment saturates or the range ends
+        for (int i2 = n_fwd; i2 < n_it && T2 != 0.f; ++i2) {          // PIPE: iteration n_fwd is already in flight (rawn)
+            float4 c[SPL];
+            if (!PIPE) fetch(i2);
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) c[j] = g.clamp ? clamp4(rawn[j]) : rawn[j];
+            if (PIPE && i2 + 1 < n_it) fetch(i2 + 1);
+            composite_iter<SPL>(c, lane, T2, acc2);
+        }
+    }
+    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+
+    // ---------------------------------------------------------------------------------------- loss, scripts/train.py:156
+    const float er = acc.x - tgt.x, eg = acc.y - tgt.y, eb = acc.z - tgt.z, ea = acc.w - tgt.w;
+    const float4 gr = make_float4(er * a.grad_scale, eg * a.grad_scale, eb * a.grad_scale, ea * a.grad_scale);
+    const float this_loss = (er * er + eg * eg + eb * eb + ea * ea) * a.loss_scale;
+    if (lane == 0 && a.rgba) reinterpret_cast<float4*>(a.rgba)[ray] = acc;
+    float s_star = 0.f;                  // colour behind k*, dotted with the pixel gradient
+    if (opaque) {
+        acc2.x = warp_sum(acc2.x); acc2.y = warp_sum(acc2.y); acc2.z = warp_sum(acc2.z); acc2.w = warp_sum(acc2.w);
+        s_star = fmaf(acc2.x, gr.x, fmaf(acc2.y, gr.y, fmaf(acc2.z, gr.z, acc2.w * gr.w)));
+    }
+
+    // ---------------------------------------------------------------------------------------- reverse
+    const bool any_grad = gr.x != 0.f || gr.y != 0.f || gr.z != 0.f || gr.w != 0.f || full;
+    float carry = 0.f;                   // S behind the last visited sample (0: end of ray, or irrelevant behind k*)
+    __syncwarp();
+    auto refetch = [&](int i) {          // indices back from shared memory, cells requested (L1 / L2 hits mostly)
+        if (SPL == 1) linn[0] = lc[i * W + lane];
+        else { const int2 p = *reinterpret_cast<const int2*>(lc + i * W + lane * 2); linn[0] = p.x; linn[SPL - 1] = p.y; }
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            rawn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (linn[j] >= 0) rawn[j] = FAST ? ldg_hint(reinterpret_cast<const float4*>(a.grid) + linn[j], g.pol)
+                                             : cell_at<false>(m, g, a.grid, linn[j] / (g.ny * g.nz), (linn[j] / g.nz) % g.ny, linn[j] % g.nz, linn[j]);
+        }
+    };
+    if (PIPE && n_fwd > 0 && any_grad) refetch(n_fwd - 1);
+    for (int ib = n_fwd - 1; ib >= 0 && any_grad; --ib) {
+        int lin[SPL];
+        float4 raw[SPL], c[SPL];
+        float v[SPL];
+        if (!PIPE) refetch(ib);
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            lin[j] = linn[j];
+            raw[j] = rawn[j];
+            c[j] = g.clamp ? clamp4(raw[j]) : raw[j];
+            v[j] = fmaf(c[j].x, gr.x, fmaf(c[j].y, gr.y, fmaf(c[j].z, gr.z, gr.w)));      // c_k . g_rgb + g_A
+        }
+        if (PIPE && ib > 0) refetch(ib - 1);     // next iteration's cells in flight during this iteration's scans
+        bool any_alpha = false;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) any_alpha = any_alpha || c[j].w != 0.f;
+        float behind[SPL], pf[SPL];
+        float base;
+        if (__any_sync(FULL, any_alpha)) {
+            // lane aggregate of the affine maps s -> alpha v + (1 - alpha) s, last sample innermost
+            float A = 0.f, B = 1.f;
+#pragma unroll
+            for (int j = SPL - 1; j >= 0; --j) { A = fmaf(1.f - c[j].w, A, c[j].w * v[j]); B *= 1.f - c[j].w; }
+            behind[SPL - 1] = warp_behind(A, B, lane, carry);
+#pragma unroll
+            for (int j = SPL - 1; j >= 1; --j) behind[j - 1] = fmaf(1.f - c[j].w, behind[j], c[j].w * v[j]);
+            if (opaque && ib == n_fwd - 1 && lane == zl) {
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) if (j == zj) behind[j] = s_star;
+            }
+            // T_k inside the iteration
+            pf[0] = 1.f;
+#pragma unroll
+            for (int j = 1; j < SPL; ++j) pf[j] = pf[j - 1] * (1.f - c[j - 1].w);
+            float total;
+            base = tcs[ib] * warp_excl_prod(pf[SPL - 1] * (1.f - c[SPL - 1].w), lane, total);
+        } else {
+            // all-transparent iteration: every map is the identity and every factor is 1 — T_k = T at the start of
+            // the iteration, the colour behind each sample is the carried one; no scan needed
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) { behind[j] = carry; pf[j] = 1.f; }
+            base = tcs[ib];
+        }
+        float4 d[SPL];
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const float Tk = base * pf[j];
+            const float wgt = c[j].w * Tk;
+            d[j] = make_float4(wgt * gr.x, wgt * gr.y, wgt * gr.z, Tk * (v[j] - behind[j]));
+            if (full) d[j].w += bom * (1.f / (c[j].w + 1e-4f) + 1.f / (1.f - c[j].w + 1e-4f));   // scripts/train.py:170-177
+            if (g.clamp) { d[j].x *= pass01(raw[j].x); d[j].y *= pass01(raw[j].y); d[j].z *= pass01(raw[j].z); d[j].w *= pass01(raw[j].w); }
+        }
+        if (SPL == 1 && !PEER) {
+            warp_scatter_add(dst.local, lin[0] >= 0, (int64_t)lin[0] * 4, d[0].x, d[0].y, d[0].z, d[0].w, lane, dst.pol);
+        } else {
+            // merge runs inside the lane, then one 16-byte reduction per surviving entry
+#pragma unroll
+            for (int j = SPL - 1; j >= 1; --j) {
+                if (lin[j] >= 0 && lin[j] == lin[j - 1]) {
+                    d[j - 1].x += d[j].x; d[j - 1].y += d[j].y; d[j - 1].z += d[j].z; d[j - 1].w += d[j].w;
+                    lin[j] = -1;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < SPL; ++j)
+                if (lin[j] >= 0 && (d[j].x != 0.f || d[j].y != 0.f || d[j].z != 0.f || d[j].w != 0.f))
+                    dst.add(lin[j], d[j].x, d[j].y, d[j].z, d[j].w);
+        }
+    }
+    __syncwarp();                        // the per-warp shared-memory cache is reused by the next ray
+    return this_loss;
+}
+
+// this ray: precomputed, or generated here from (pose, uv) — src/ray_sampling.py:212-264
+__device__ __forceinline__ void setup_ray(const PlxRenderTrain& a, int64_t ray, Ray& r, float4& tgt) {
+    if (a.gen.uv) {
+        const int R = a.gen.rays_per_cam;
+        const int cam = (int)(ray / R);
+        const float* P = a.gen.poses + (int64_t)cam * 16;
+        const RayOut o = ray_from_uv(P, a.gen.fov, __ldg(a.gen.uv + ray * 2), __ldg(a.gen.uv + ray * 2 + 1), a.gen.img_h, a.gen.img_w);
+        tgt = load_target(a.gen, ((int64_t)cam * a.gen.img_h + o.vp) * a.gen.img_w + o.up);
+        r.ox = __ldg(P + 3); r.oy = __ldg(P + 7); r.oz = __ldg(P + 11);          // camera position, :159
+        r.dx = o.dx; r.dy = o.dy; r.dz = o.dz;
+    } else {
+        r = load_ray(a.rays, ray);
+        tgt = __ldg(reinterpret_cast<const float4*>(a.targets) + ray);
+    }
+}
+
+// the rare ray outside the hoisted-division range (coordinates near the ends of the fp32 range, NaN / inf): the same march on
+// the IEEE division and the float bounds test.  Out of line and self-contained (it rebuilds the ray and the geometry from the
+// kernel argument), so the common path pays neither instructions nor registers nor stack traffic for it.
+template <bool FAST, int SPL, bool PEER>
+__device__ __noinline__ float train_ray_slow(const PlxRenderTrain* ap, float* const* peers, int* lc, float* tcs, int64_t ray, int lane) {
+    const PlxRenderTrain& a = *ap;
+    const Geo g = make_geo(a.march);
+    GradDst<PEER> dst;
+    dst.local = a.grad_grid; dst.peers = peers; dst.owner_mul = a.peer_grad.owner_mul; dst.pol = g.pol_grad;
+    RayScratch sc;
+    sc.lc = lc; sc.tcs = tcs;
+    Ray r;
+    float4 tgt;
+    setup_ray(a, ray, r, tgt);
+    return train_ray<FAST, false, SPL, false, PEER>(a, g, dst, sc, r, tgt, ray, lane);
+}
+
+template <bool FAST, int SPL, bool PIPE, bool PEER>
+__global__ void __launch_bounds__(128, 8) k_render_train(const __grid_constant__ PlxRenderTrain a, int lin_words, int warp_words) {
     extern __shared__ __align__(16) int s_dyn[];   // per warp (warp_words ints, 16-byte multiple): lin cache [lin_words], then chunk transmittances
     __shared__ float s_loss;
     __shared__ int s_done;
-    constexpr int W = 32 * SPL;
+    __shared__ float* s_peer[PLX_MAX_PEERS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const PlxMarch& m = a.march;
     if (threadIdx.x == 0) { s_loss = 0.f; s_done = 0; }
+    if (PEER && threadIdx.x < PLX_MAX_PEERS) s_peer[threadIdx.x] = a.peer_grad.grads[threadIdx.x];
     peer_wait(a.sync);                       // multi-GPU: every peer has stored its slab of the previous step's parameters
     __syncthreads();                         // every warp arrives here at once: free
     float ray_loss = 0.f;
-    int* lc = s_dyn + wib * warp_words;
-    float* tcs = reinterpret_cast<float*>(lc + lin_words);
-    const Geo g = make_geo(m);
-    // work distribution: with a `work_counter` the grid is one resident wave and every warp claims its next ray from a
-    // global counter as soon as it is free (rays differ in length, so warps of a block do not wait for each other and
-    // there is no partial last wave); without one, ray = block * warps + warp.
-    int64_t ray = (int64_t)blockIdx.x * wpb + wib;
-    const int64_t static_stride = (int64_t)gridDim.x * wpb;
-    // dynamic mode: every ray is a ticket drawn from the counter, and the ticket for the NEXT ray is drawn before the current
-    // ray is processed, so the atomic's round trip (~1 us) is hidden behind the march instead of stalling the warp
-    // between rays (a warp stops at its first ticket >= n_rays without drawing another: no ticket is ever dropped)
-    int ticket = 0;
-    if (a.work_counter && lane == 0) ticket = atomicAdd(a.work_counter, 1);
-    for (bool first = true;; first = false) {
-        if (a.work_counter) {
-            ray = __shfl_sync(FULL, ticket, 0);
-            if (lane == 0 && ray < a.rays.n_rays) ticket = atomicAdd(a.work_counter, 1);
-        } else if (!first) {
-            ray += static_stride;
-        }
-        if (ray >= a.rays.n_rays) break;
-        float this_loss = 0.f;
-        // ---- this ray: precomputed, or generated here from (pose, uv) — src/ray_sampling.py:212-264
+    // one ray per warp, ray = block * warps + warp (claiming rays dynamically from a global counter was measured slower on
+    // every config: 61 vs 48 us on C2 even with the ticket drawn one ray ahead)
+    const int64_t ray = (int64_t)blockIdx.x * wpb + wib;
+    if (ray < a.rays.n_rays) {
+        RayScratch sc;
+        sc.lc = s_dyn + wib * warp_words;
+        sc.tcs = reinterpret_cast<float*>(sc.lc + lin_words);
         Ray r;
         float4 tgt;
-        if (a.gen.uv) {
-            const int R = a.gen.rays_per_cam;
-            const int cam = (int)(ray / R);
-            const float* P = a.gen.poses + (int64_t)cam * 16;
-            const RayOut o = ray_from_uv(P, a.gen.fov, __ldg(a.gen.uv + ray * 2), __ldg(a.gen.uv + ray * 2 + 1), a.gen.img_h, a.gen.img_w);
-            tgt = __ldg(reinterpret_cast<const float4*>(a.gen.imgs) + ((int64_t)cam * a.gen.img_h + o.vp) * a.gen.img_w + o.up);
-            r.ox = __ldg(P + 3); r.oy = __ldg(P + 7); r.oz = __ldg(P + 11);          // camera position, :159
-            r.dx = o.dx; r.dy = o.dy; r.dz = o.dz;
+        setup_ray(a, ray, r, tgt);
+        if (FAST && ray_in_fast_range(m, r)) {
+            const Geo g = make_geo(m);
+            GradDst<PEER> dst;
+            dst.local = a.grad_grid; dst.peers = s_peer; dst.owner_mul = a.peer_grad.owner_mul; dst.pol = g.pol_grad;
+            ray_loss = train_ray<FAST, true, SPL, PIPE, PEER>(a, g, dst, sc, r, tgt, ray, lane);
         } else {
-            r = load_ray(a.rays, ray);
-            tgt = __ldg(reinterpret_cast<const float4*>(a.targets) + ray);
+            ray_loss = train_ray_slow<FAST, SPL, PEER>(&a, s_peer, sc.lc, sc.tcs, ray, lane);
         }
-        const bool fast_ray = FAST && ray_in_fast_range(m, r);
-        const float bom = a.beta_over_m;
-        const bool full = bom != 0.f;        // the sparsity term touches every in-bounds sample: no early stop
-        int k0, k1;
-        clip_range(m, r, k0, k1);
-        const int n_it = k0 <= k1 ? (k1 - k0) / W + 1 : 0;
-
-        // ---------------------------------------------------------------------------------------- forward
-        float T = 1.f, T2 = 1.f;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = acc;
-        bool opaque = false;                 // segment 1 ended on an alpha == 1 sample at (zl, zj)
-        int zl = 0, zj = 0;
-        int it = 0;
-        // software pipeline: the cells of iteration it+1 are requested before iteration it is composited, so the gather
-        // latency (L2 / HBM) overlaps the scans instead of stalling the warp at the first use
-        float4 rawn[SPL];
-        int linn[SPL];
-        auto fetch = [&](int i) {
-            const int kb = k0 + i * W + lane * SPL;
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) linn[j] = fetch_nearest<FAST>(m, g, a.grid, r, fast_ray, kb + j, kb + j <= k1, rawn[j]);
-        };
-        if (PIPE && n_it > 0) fetch(0);
-        for (; it < n_it; ++it) {
-            float4 c[SPL];
-            int lin[SPL];
-            if (!PIPE) fetch(it);
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) { c[j] = g.clamp ? clamp4(rawn[j]) : rawn[j]; lin[j] = linn[j]; }
-            if (PIPE && it + 1 < n_it) fetch(it + 1);
-            if (SPL == 1) lc[it * W + lane] = lin[0];
-            else *reinterpret_cast<int2*>(lc + it * W + lane * 2) = make_int2(lin[0], lin[SPL - 1]);
-            if (lane == 0) tcs[it] = T;
-            // empty space is the common case (a trained grid is mostly alpha == 0, fit() even starts from all zeros):
-            // an iteration whose 32*SPL samples are all transparent changes neither T nor the pixel — skip its scan
-            bool any_alpha = false;
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) any_alpha = any_alpha || c[j].w != 0.f;
-            if (!__any_sync(FULL, any_alpha)) continue;
-            composite_iter<SPL>(c, lane, T, acc);
-            if (T == 0.f && !full) {
-                // first sample whose factor is exactly 0 (alpha == 1); none => the product merely underflowed
-                int jz = SPL;
-#pragma unroll
-                for (int j = SPL - 1; j >= 0; --j) if (c[j].w == 1.f) jz = j;
-                const unsigned hit = __ballot_sync(FULL, jz < SPL);
-                if (hit) {
-                    opaque = true;
-                    zl = __ffs(hit) - 1;
-                    zj = __shfl_sync(FULL, jz, zl);
-                    float4 c2[SPL];
-#pragma unroll
-                    for (int j = 0; j < SPL; ++j) {
-                        const bool after = lane > zl || (lane == zl && j > zj);
-                        c2[j] = after ? c[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    composite_iter<SPL>(c2, lane, T2, acc2);
-                }
-                ++it;
-                break;
-            }
-        }
-        const int n_fwd = it;                // iterations of segment 1 (their indices are cached)
-        if (opaque) {                        // keep compositing behind k* until that segment saturates or the range ends
-            for (int i2 = n_fwd; i2 < n_it && T2 != 0.f; ++i2) {          // PIPE: iteration n_fwd is already in flight (rawn)
-                float4 c[SPL];
-                if (!PIPE) fetch(i2);
-#pragma unroll
-                for (int j = 0; j < SPL; ++j) c[j] = g.clamp ? clamp4(rawn[j]) : rawn[j];
-                if (PIPE && i2 + 1 < n_it) fetch(i2 + 1);
-                composite_iter<SPL>(c, lane, T2, acc2);
-            }
-        }
-        acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
-
-        // ---------------------------------------------------------------------------------------- loss, scripts/train.py:156
-        const float er = acc.x - tgt.x, eg = acc.y - tgt.y, eb = acc.z - tgt.z, ea = acc.w - tgt.w;
-        const float4 gr = make_float4(er * a.grad_scale, eg * a.grad_scale, eb * a.grad_scale, ea * a.grad_scale);
-        this_loss = (er * er + eg * eg + eb * eb + ea * ea) * a.loss_scale;
-        if (lane == 0 && a.rgba) reinterpret_cast<float4*>(a.rgba)[ray] = acc;
-        float s_star = 0.f;                  // colour behind k*, dotted with the pixel gradient
-        if (opaque) {
-            acc2.x = warp_sum(acc2.x); acc2.y = warp_sum(acc2.y); acc2.z = warp_sum(acc2.z); acc2.w = warp_sum(acc2.w);
-            s_star = fmaf(acc2.x, gr.x, fmaf(acc2.y, gr.y, fmaf(acc2.z, gr.z, acc2.w * gr.w)));
-        }
-
-        // ---------------------------------------------------------------------------------------- reverse
-        const bool any_grad = gr.x != 0.f || gr.y != 0.f || gr.z != 0.f || gr.w != 0.f || full;
-        float carry = 0.f;                   // S behind the last visited sample (0: end of ray, or irrelevant behind k*)
-        __syncwarp();
-        auto refetch = [&](int i) {          // indices back from shared memory, cells requested (L1 / L2 hits mostly)
-            if (SPL == 1) linn[0] = lc[i * W + lane];
-            else { const int2 p = *reinterpret_cast<const int2*>(lc + i * W + lane * 2); linn[0] = p.x; linn[SPL - 1] = p.y; }
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) {
-                rawn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (linn[j] >= 0) rawn[j] = FAST ? ldg_hint(reinterpret_cast<const float4*>(a.grid) + linn[j], g.pol)
-                                                 : cell_at<false>(m, g, a.grid, linn[j] / (g.ny * g.nz), (linn[j] / g.nz) % g.ny, linn[j] % g.nz, linn[j]);
-            }
-        };
-        if (PIPE && n_fwd > 0 && any_grad) refetch(n_fwd - 1);
-        for (int ib = n_fwd - 1; ib >= 0 && any_grad; --ib) {
-            int lin[SPL];
-            float4 raw[SPL], c[SPL];
-            float v[SPL];
-            if (!PIPE) refetch(ib);
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) {
-                lin[j] = linn[j];
-                raw[j] = rawn[j];
-                c[j] = g.clamp ? clamp4(raw[j]) : raw[j];
-                v[j] = fmaf(c[j].x, gr.x, fmaf(c[j].y, gr.y, fmaf(c[j].z, gr.z, gr.w)));      // c_k . g_rgb + g_A
-            }
-            if (PIPE && ib > 0) refetch(ib - 1);     // next iteration's cells in flight during this iteration's scans
-            bool any_alpha = false;
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) any_alpha = any_alpha || c[j].w != 0.f;
-            float behind[SPL], pf[SPL];
-            float base;
-            if (__any_sync(FULL, any_alpha)) {
-                // lane aggregate of the affine maps s -> alpha v + (1 - alpha) s, last sample innermost
-                float A = 0.f, B = 1.f;
-#pragma unroll
-                for (int j = SPL - 1; j >= 0; --j) { A = fmaf(1.f - c[j].w, A, c[j].w * v[j]); B *= 1.f - c[j].w; }
-                behind[SPL - 1] = warp_behind(A, B, lane, carry);
-#pragma unroll
-                for (int j = SPL - 1; j >= 1; --j) behind[j - 1] = fmaf(1.f - c[j].w, behind[j], c[j].w * v[j]);
-                if (opaque && ib == n_fwd - 1 && lane == zl) {
-#pragma unroll
-                    for (int j = 0; j < SPL; ++j) if (j == zj) behind[j] = s_star;
-                }
-                // T_k inside the iteration
-                pf[0] = 1.f;
-#pragma unroll
-                for (int j = 1; j < SPL; ++j) pf[j] = pf[j - 1] * (1.f - c[j - 1].w);
-                float total;
-                base = tcs[ib] * warp_excl_prod(pf[SPL - 1] * (1.f - c[SPL - 1].w), lane, total);
-            } else {
-                // all-transparent iteration: every map is the identity and every factor is 1 — T_k = T at the start of
-                // the iteration, the colour behind each sample is the carried one; no scan needed
-#pragma unroll
-                for (int j = 0; j < SPL; ++j) { behind[j] = carry; pf[j] = 1.f; }
-                base = tcs[ib];
-            }
-            float4 d[SPL];
-#pragma unroll
-            for (int j = 0; j < SPL; ++j) {
-                const float Tk = base * pf[j];
-                const float wgt = c[j].w * Tk;
-                d[j] = make_float4(wgt * gr.x, wgt * gr.y, wgt * gr.z, Tk * (v[j] - behind[j]));
-                if (full) d[j].w += bom * (1.f / (c[j].w + 1e-4f) + 1.f / (1.f - c[j].w + 1e-4f));   // scripts/train.py:170-177
-                if (g.clamp) { d[j].x *= pass01(raw[j].x); d[j].y *= pass01(raw[j].y); d[j].z *= pass01(raw[j].z); d[j].w *= pass01(raw[j].w); }
-            }
-            if (SPL == 1) {
-                warp_scatter_add(a.grad_grid, lin[0] >= 0, (int64_t)lin[0] * 4, d[0].x, d[0].y, d[0].z, d[0].w, lane, g.pol_grad);
-            } else {
-                // merge runs inside the lane, then one 16-byte reduction per surviving entry
-#pragma unroll
-                for (int j = SPL - 1; j >= 1; --j) {
-                    if (lin[j] >= 0 && lin[j] == lin[j - 1]) {
-                        d[j - 1].x += d[j].x; d[j - 1].y += d[j].y; d[j - 1].z += d[j].z; d[j - 1].w += d[j].w;
-                        lin[j] = -1;
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < SPL; ++j)
-                    if (lin[j] >= 0 && (d[j].x != 0.f || d[j].y != 0.f || d[j].z != 0.f || d[j].w != 0.f))
-                        red_add_v4_hint(a.grad_grid + (int64_t)lin[j] * 4, d[j].x, d[j].y, d[j].z, d[j].w, g.pol_grad);
-            }
-        }
-        ray_loss += this_loss;
-        __syncwarp();                        // the per-warp shared-memory cache is reused by the next ray
     }
     // ---- loss: shared-memory partial per block, the last warp to finish adds it to the global accumulator; that warp
     // also counts the block as done for the cross-GPU signal (its lanes' gradient reductions are ordered before lane 0's
     // fence by the __syncwarp above, the other warps' by their own fence before they bump s_done)
     if (lane == 0 && (a.loss || a.sync.signal_epoch > 0)) {
         if (a.loss) atomicAdd(&s_loss, ray_loss);
-        if (a.sync.signal_epoch > 0) __threadfence(); else __threadfence_block();
+        if (a.sync.signal_epoch > 0) { if (PEER) __threadfence_system(); else __threadfence(); } else __threadfence_block();
         if (atomicAdd(&s_done, 1) == wpb - 1) {
             if (a.loss) atomicAdd(a.loss, atomicAdd(&s_loss, 0.f));
             peer_signal(a.sync);
         }
     }
-}
-
-static int env_int(const char* name, int dflt, int lo, int hi) {
-    const char* e = std::getenv(name);
-    if (e) {
-        const int v = std::atoi(e);
-        if (v >= lo && v <= hi) return v;
-    }
-    return dflt;
 }
 
 // shared memory the fused kernel needs per block; 0 = not launchable (fall back to K1 + K2)
@@ -297,49 +335,47 @@ bool render_train_supported(const PlxRenderTrain& a) {
     return render_train_smem(a.march.num_samples, 2, 1) <= 200 * 1024;
 }
 
+template <bool FAST, int SPL, bool PIPE, bool PEER>
+static cudaError_t launch_train_inst(const PlxRenderTrain& a, unsigned blocks, int wpb, size_t smem, int lin_words, int warp_words,
+                                     cudaStream_t st) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_render_train<FAST, SPL, PIPE, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_render_train<FAST, SPL, PIPE, PEER><<<blocks, wpb * 32, smem, st>>>(a, lin_words, warp_words);
+    return cudaGetLastError();
+}
+
+// Launch shape (measured on C2 / B200): 4 warps per block, 8 blocks per SM (64 registers), 2 samples per lane
+// from 128 samples per ray up; software-pipelined gathers when grid + gradient fit the L2 (+5 % on C2) and off on grids far
+// beyond it, where the extra requests in flight only add DRAM queueing (-8 % on the 256^3 sweep).
 cudaError_t launch_render_train(const PlxRenderTrain& a_in, cudaStream_t st) {
     if (a_in.rays.n_rays == 0) return cudaSuccess;
     PlxRenderTrain a = a_in;
     a.march.flags = (a.march.flags & 0xffffu) | l2_keep_flags(a.march);
-    static const int spl_env = env_int("PLX_TRAIN_SPL", 0, 1, 2);
-    static const int wpb_env = env_int("PLX_TRAIN_WPB", 4, 1, 4);
-    static const int minb = env_int("PLX_TRAIN_MINB", 8, 6, 8);
-    const int spl = spl_env ? spl_env : (a.march.num_samples >= 128 ? 2 : 1);
-    int wpb = wpb_env;
+    const int spl = a.march.num_samples >= 128 ? 2 : 1;
+    int wpb = 4;
     while (wpb > 1 && render_train_smem(a.march.num_samples, spl, wpb) > 200 * 1024) wpb >>= 1;
     const size_t smem = render_train_smem(a.march.num_samples, spl, wpb);
     const int W = 32 * spl;
     const int n_it_max = (a.march.num_samples + W - 1) / W + 1;
-    const int lin_words = n_it_max * W;
-    unsigned blocks = (unsigned)((a.rays.n_rays + wpb - 1) / wpb);
-    if (a.work_counter) {                    // one resident wave: SMs x blocks per SM of this instantiation (8 at 128 threads)
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        static const int per_sm = env_int("PLX_TRAIN_BLOCKS_PER_SM", 8, 1, 16);
-        const unsigned wave = (unsigned)(sms * per_sm);
-        if (blocks > wave) blocks = wave;
-    }
+    const int lin_words = n_it_max * W, warp_words = lin_words + ((n_it_max + 3) & ~3);
+    const unsigned blocks = (unsigned)((a.rays.n_rays + wpb - 1) / wpb);
     const bool fast = fast_ok(a.march, a.grid);
-    // software pipelining pays when the gathers are L2-latency bound (grid + gradient resident in L2: +5 % on C2); on grids
-    // far beyond the L2 the extra requests in flight only add DRAM queueing (-8 % on the 256^3 sweep), so it is off there
-    static const int pipe_env = env_int("PLX_TRAIN_PIPE", -1, 0, 1);
-    const bool pipe = pipe_env >= 0 ? pipe_env != 0 : l2_keep_ok((int64_t)a.march.nx * a.march.ny * a.march.nz);
-#define PLX_TRAIN(FASTP, SPLV, MB)                                                                                              \
-    do {                                                                                                                    \
-        if (smem > 48 * 1024) {                                                                                             \
-            cudaError_t e = pipe ? cudaFuncSetAttribute(k_render_train<FASTP, SPLV, MB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)   \
-                                 : cudaFuncSetAttribute(k_render_train<FASTP, SPLV, MB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) return e;                                                                                 \
-        }                                                                                                                   \
-        if (pipe) k_render_train<FASTP, SPLV, MB, true><<<blocks, wpb * 32, smem, st>>>(a, lin_words, lin_words + ((n_it_max + 3) & ~3));   \
-        else      k_render_train<FASTP, SPLV, MB, false><<<blocks, wpb * 32, smem, st>>>(a, lin_words, lin_words + ((n_it_max + 3) & ~3));  \
-    } while (0)
-    if (!fast) { if (spl == 2) PLX_TRAIN(false, 2, 8); else PLX_TRAIN(false, 1, 8); }
-    else if (spl == 2) { if (minb <= 6) PLX_TRAIN(true, 2, 6); else if (minb == 7) PLX_TRAIN(true, 2, 7); else PLX_TRAIN(true, 2, 8); }
-    else               { if (minb <= 6) PLX_TRAIN(true, 1, 6); else if (minb == 7) PLX_TRAIN(true, 1, 7); else PLX_TRAIN(true, 1, 8); }
+    const bool pipe = l2_keep_ok((int64_t)a.march.nx * a.march.ny * a.march.nz);
+    const bool peer = a.peer_grad.world > 0;
+#define PLX_TRAIN(F, S, P, E) return launch_train_inst<F, S, P, E>(a, blocks, wpb, smem, lin_words, warp_words, st)
+    if (peer) {                              // validated by the ABI layer: contiguous grid only
+        if (spl == 2) { if (pipe) PLX_TRAIN(true, 2, true, true); else PLX_TRAIN(true, 2, false, true); }
+        else          { if (pipe) PLX_TRAIN(true, 1, true, true); else PLX_TRAIN(true, 1, false, true); }
+    }
+    if (fast) {
+        if (spl == 2) { if (pipe) PLX_TRAIN(true, 2, true, false); else PLX_TRAIN(true, 2, false, false); }
+        else          { if (pipe) PLX_TRAIN(true, 1, true, false); else PLX_TRAIN(true, 1, false, false); }
+    }
+    if (spl == 2) { if (pipe) PLX_TRAIN(false, 2, true, false); else PLX_TRAIN(false, 2, false, false); }
+    else          { if (pipe) PLX_TRAIN(false, 1, true, false); else PLX_TRAIN(false, 1, false, false); }
 #undef PLX_TRAIN
-    return cudaGetLastError();
 }
 
 }  // namespace plx

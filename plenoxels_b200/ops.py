@@ -113,12 +113,12 @@ def sample_indices(grid, origins, dirs, num_samples, delta_step, gmin, points_di
 
 def render_train(grid, grad_grid, num_samples, delta_step, gmin, points_distance, *, origins=None, dirs=None,
                  targets=None, rays_per_origin=1, imgs=None, poses=None, fov=None, uv=None, n_rays_global=None,
-                 beta_over_m=0.0, clamp=True, dynamic=False):
+                 beta_over_m=0.0, clamp=True):
     """K12, the fused training march (nearest lookup): forward + mean-MSE + backward in one kernel; the gradient is
     ACCUMULATED into `grad_grid` (contiguous (X,Y,Z,4)).  Rays are either given (`origins`, `dirs`, `targets`) or
     generated in the kernel from (`imgs`, `poses`, `fov`, `uv` (C,R,2)).  Returns (rgba (N,4), loss (1,) device tensor)
-    = the pixels and mean((rgba - targets)^2) of scripts/train.py:151-156.  `dynamic`: rays are claimed from a device
-    counter by the warps of a one-wave grid (PlxRenderTrain.work_counter) instead of the static block -> ray mapping."""
+    = the pixels and mean((rgba - targets)^2) of scripts/train.py:151-156.  `imgs` may be fp32 in [0,1] or uint8 (the
+    target pixel is then converted in the kernel, fp32(u8) / 255)."""
     dev = L.require_cuda(grid, grad_grid, origins, dirs, targets, imgs, poses, uv)
     lib = L.load()
     a = L.PlxRenderTrain()
@@ -127,11 +127,12 @@ def render_train(grid, grad_grid, num_samples, delta_step, gmin, points_distance
     if uv is not None:
         uv = uv.contiguous().float()
         poses = poses.contiguous().float()
-        imgs = imgs.contiguous().float()
+        imgs = imgs.contiguous() if imgs.dtype == torch.uint8 else imgs.contiguous().float()
         keep += [uv, poses, imgs]
         n = uv.shape[0] * uv.shape[1]
         a.rays.n_rays = n
         a.gen.imgs, a.gen.n_cams, a.gen.img_h, a.gen.img_w = imgs.data_ptr(), imgs.shape[0], imgs.shape[1], imgs.shape[2]
+        a.gen.img_format = L.PLX_IMG_U8 if imgs.dtype == torch.uint8 else L.PLX_IMG_F32
         a.gen.poses, a.gen.fov, a.gen.uv, a.gen.rays_per_cam = poses.data_ptr(), float(fov), uv.data_ptr(), uv.shape[1]
     else:
         a.rays = L.make_rays(origins, dirs, rays_per_origin)
@@ -146,10 +147,6 @@ def render_train(grid, grad_grid, num_samples, delta_step, gmin, points_distance
     loss = torch.zeros((1,), dtype=torch.float32, device=dev)
     a.grid, a.grad_grid, a.rgba, a.loss = grid.data_ptr(), grad_grid.data_ptr(), rgba.data_ptr(), loss.data_ptr()
     a.grad_scale, a.loss_scale, a.beta_over_m = 2.0 / (4.0 * n_glob), 1.0 / (4.0 * n_glob), float(beta_over_m)
-    if dynamic:
-        counter = torch.zeros((1,), dtype=torch.int32, device=dev)
-        keep.append(counter)
-        a.work_counter = counter.data_ptr()
     with torch.cuda.device(dev):
         L.check(lib.plx_render_train(C.byref(a), L.stream_ptr(dev)), "plx_render_train")
     return rgba, loss
@@ -184,14 +181,18 @@ def generate_rays(imgs, poses, fov, uv=None, rays_per_cam=None, want_targets=Tru
     dirs = torch.empty((C_ * R, 3), dtype=torch.float32, device=dev)
     targets = None
     H = W = 0
+    gen = L.PlxRayGen()
     if want_targets:
-        if imgs.dtype != torch.float32 or not imgs.is_contiguous():
+        if imgs.dtype != torch.uint8 and (imgs.dtype != torch.float32 or not imgs.is_contiguous()):
             imgs = imgs.contiguous().float()
+        imgs = imgs.contiguous()
         H, W = imgs.shape[1], imgs.shape[2]
         targets = torch.empty((C_ * R, 4), dtype=torch.float32, device=dev)
+        gen.imgs = imgs.data_ptr()
+        gen.img_format = L.PLX_IMG_U8 if imgs.dtype == torch.uint8 else L.PLX_IMG_F32
+    gen.n_cams, gen.img_h, gen.img_w, gen.poses, gen.fov, gen.uv, gen.rays_per_cam = C_, H, W, poses.data_ptr(), float(fov), L.ptr(uv), R
     with torch.cuda.device(dev):
-        L.check(L.load().plx_generate_rays(L.ptr(imgs) if want_targets else None, C_, H, W, poses.data_ptr(), float(fov),
-                                           L.ptr(uv), R, n_side, dirs.data_ptr(), L.ptr(targets), L.stream_ptr(dev)),
+        L.check(L.load().plx_generate_rays_gen(C.byref(gen), n_side, dirs.data_ptr(), L.ptr(targets), L.stream_ptr(dev)),
                 "plx_generate_rays")
     return dirs, targets
 

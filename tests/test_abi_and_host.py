@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(plx_lib):
     for s in declared_symbols():
         assert hasattr(raw, s), f"{s} declared in plenoxel_abi.h but not exported"
         assert s in L.PROTOTYPES, f"{s} has no ctypes prototype"
-    assert plx_lib.plx_version() == 1
+    assert plx_lib.plx_version() == 2
     assert plx_lib.plx_num_chunks(600) >= 19 and plx_lib.plx_num_chunks(0) >= 1
 
 
@@ -174,6 +174,31 @@ def test_slab_ranges_partition_the_grid(n_cells, world):
     assert all(b % 4 == 0 and e % 4 == 0 and e >= b for b, e in edges) and max(sizes) - min(sizes) <= 1
 
 
+@pytest.mark.parametrize("n_cells,world", [(2097152, 1), (2097152, 2), (2097152, 8), (16777216, 8), (1000003, 3), (9, 8), (93 * 91 * 89, 5),
+                                           (2 ** 31 - 1, 7)])
+def test_slab_partition_matches_the_device_owner_function(plx_lib, n_cells, world):
+    """Push exchange (PlxPeerGrad): the march sends the gradient of cell `lin` to rank umulhi(lin, owner_mul).  The slabs
+    plx_slab_partition hands the optimiser must be exactly the preimages of that function: contiguous, tiling [0, n_cells),
+    and the python mirror in trainer.slab_partition must agree with the library."""
+    from plenoxels_b200.trainer import slab_partition
+    edges = []
+    for r in range(world):
+        mul, b, e = C.c_uint32(), C.c_int64(), C.c_int64()
+        assert plx_lib.plx_slab_partition(n_cells, world, r, C.byref(mul), C.byref(b), C.byref(e)) == 0
+        assert (mul.value, b.value, e.value) == slab_partition(n_cells, r, world)
+        edges.append((b.value, e.value))
+    assert edges[0][0] == 0 and edges[-1][1] == n_cells
+    assert all(e0 == b1 for (_, e0), (b1, _) in zip(edges, edges[1:]))
+    m = mul.value
+    owner = lambda lin: (lin * m) >> 32
+    rng = np.random.default_rng(0)
+    for r, (b, e) in enumerate(edges):
+        probes = [b, e - 1] + list(rng.integers(b, e, size=16)) if e > b else []
+        assert all(owner(int(x)) == r for x in probes)
+    sizes = [e - b for b, e in edges]
+    assert max(sizes) - min(sizes) <= n_cells * n_cells * world // 2 ** 32 + 2     # near-equal: the multiplier is floored to 32 bits
+
+
 def test_abi_links_and_runs_from_plain_c(plx_lib, tmp_path):
     """The boundary is a C ABI, not a Python one: a C program that includes plenoxel_abi.h and links libplenoxel_b200.so
     must build with gcc and get the documented error codes / messages back (no GPU needed for the argument checks)."""
@@ -183,7 +208,7 @@ def test_abi_links_and_runs_from_plain_c(plx_lib, tmp_path):
 #include <string.h>
 #include "plenoxel_abi.h"
 int main(void) {
-    if (plx_version() != 1) return 1;
+    if (plx_version() != PLX_ABI_VERSION) return 1;
     if (plx_num_chunks(600) < 19) return 2;
     PlxRenderFwd f; memset(&f, 0, sizeof f);
     if (plx_render_fwd(&f, NULL) != -1 || !strstr(plx_last_error(), "grid")) return 3;      /* PLX_E_NULL */
@@ -191,6 +216,12 @@ int main(void) {
     if (plx_adam_step(NULL, NULL, NULL, NULL, NULL, 0, 1e-3, 0.9, 0.999, 1e-8, 0, 1, NULL) != -2) return 5;   /* step < 1 */
     PlxAdamPeer p; memset(&p, 0, sizeof p);
     if (plx_adam_step_peer(&p, NULL) >= 0) return 6;                                         /* world == 0 */
+    PlxAdamSlab sl; memset(&sl, 0, sizeof sl);
+    if (plx_adam_step_slab(&sl, NULL) >= 0) return 7;                                        /* world == 0 */
+    uint32_t mul; int64_t b, e;
+    if (plx_slab_partition(2097152, 8, 3, &mul, &b, &e) != 0 || mul != 16384u || b != 3 * 262144 || e != 4 * 262144) return 8;
+    if (plx_slab_partition(4, 8, 0, &mul, &b, &e) != PLX_E_SHAPE) return 9;                  /* fewer cells than ranks */
+    if (plx_peer_barrier(NULL, 0, 1, 0, 1, NULL, NULL) != PLX_E_NULL) return 10;
     printf("abi ok: %s\n", plx_last_error());
     return 0;
 }

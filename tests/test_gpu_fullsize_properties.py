@@ -40,7 +40,7 @@ class Full:
         return ops.render_rays(g, self.origins, self.dirs, self.S, self.sc.delta_step, self.gmin, self.sc.points_distance,
                                rays_per_origin=self.R, **kw)
 
-    def train(self, sel=None, n_global=None, dynamic=False):
+    def train(self, sel=None, n_global=None):
         gg = torch.zeros_like(self.grid)
         if sel is None:
             o, d, t, rpo = self.origins, self.dirs, self.targets, self.R
@@ -48,7 +48,7 @@ class Full:
             o = self.origins.repeat_interleave(self.R, 0)[sel].contiguous()
             d, t, rpo = self.dirs[sel].contiguous(), self.targets[sel].contiguous(), 1
         rgba, loss = ops.render_train(self.grid, gg, self.S, self.sc.delta_step, self.gmin, self.sc.points_distance, origins=o,
-                                      dirs=d, targets=t, rays_per_origin=rpo, n_rays_global=n_global, dynamic=dynamic)
+                                      dirs=d, targets=t, rays_per_origin=rpo, n_rays_global=n_global)
         return rgba, loss, gg
 
 
@@ -68,16 +68,6 @@ def test_fused_march_equals_forward_plus_backward_kernels(full):
     assert rel_err(rgba_f.cpu().numpy(), rgba.detach().cpu().numpy()) <= 2e-6
     assert abs(float(loss_f) - float(loss)) <= 2e-6 * float(loss)
     assert rel_err(grad_f.cpu().numpy(), g.grad.cpu().numpy()) <= 5e-6
-
-
-def test_dynamic_ray_claiming_processes_every_ray_exactly_once(full):
-    """Tickets from the device counter instead of the static block -> ray mapping: identical pixels (bitwise: a ray's own
-    arithmetic does not depend on who marches it), same loss and gradient up to the order of the atomic sums."""
-    rgba_s, loss_s, grad_s = full.train()
-    rgba_d, loss_d, grad_d = full.train(dynamic=True)
-    assert torch.equal(rgba_s, rgba_d)
-    assert abs(float(loss_s) - float(loss_d)) <= 2e-6 * float(loss_s)
-    assert rel_err(grad_d.cpu().numpy(), grad_s.cpu().numpy()) <= 2e-6
 
 
 def test_gradient_is_additive_over_ray_shards(full):

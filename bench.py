@@ -1,13 +1,18 @@
 #!/usr/bin/env python
-"""bench.py — training rays/s of the voxel-grid renderer hot path on N B200s (contract: see DESIGN.md §Measurement).
+"""bench.py — training rays/s of the voxel-grid renderer hot path on N B200s (contract: see DESIGN.md §4 Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1] [--impl reference] [--no-extras]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-A step = one pass of the hot path over one ray batch: ray generation -> fused forward + MSE -> fused backward ->
-[gradient all-reduce when N > 1] -> Adam (+ |grad| accumulation), i.e. the loop body of the reference's fit()
+A step = one pass of the hot path over one ray batch: fused march (ray generation + forward + MSE + backward) ->
+[gradient exchange when N > 1] -> Adam (+ |grad| accumulation), i.e. the loop body of the reference's fit()
 (scripts/train.py:130-184, tv = beta = 0, full resolution).  Prints ONE JSON line on rank 0.
+
+Headline = BASELINE.json config #2 (C2).  The same line carries, under "extra", the other BASELINE configs measured in the
+same run: C3 at the same N (config #3), and at N = 1 the C4 inference render (config #4, nearest + trilinear), three C5
+sweep points (config #5) and trilinear training on C2 — each with its own roofline; at N > 1 also a self-check of the
+multi-GPU exchange (replica bit-equality, gradient against the NCCL path) made in the untimed region.
 """
 from __future__ import annotations
 
@@ -29,21 +34,26 @@ from plenoxels_b200 import synth  # noqa: E402
 
 METRIC = "training rays/sec (fwd+bwd+optimiser step)"
 UNIT = "rays/s"
-MAX_DISTINCT_BATCHES = 256
+MAX_DISTINCT_BATCHES = 64
+REPEATS = 9                 # the K-step timed region is repeated; value = the median region
+NVLINK_GBS = 770.0          # measured peer-copy bandwidth per direction per GPU (B200_PROFILING.md)
+L2_NOTE = ("no flush: each step streams 5 grid-sized state arrays plus gathers from the image set, more than the 126 MB L2 "
+           "(c2: 168 MB + 1.02 GB, c3: 1.3 GB + 0.33 GB); a fresh uv batch every step")
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def workload_scene(name: str) -> synth.Scene:
-    return synth.make_scene(name)
-
-
 def workload_label(sc: synth.Scene) -> str:
     C, H = sc.imgs.shape[0], sc.imgs.shape[1]
     return (f"{sc.name}: {sc.G}^3 grid (pd={sc.points_distance:g}), {C} views {H}x{H}, {sc.rays_per_cam} rays/view = "
             f"{sc.n_rays} rays/GPU/step, {sc.num_samples} samples/ray (delta={sc.delta_step:g}), nearest lookup, Adam lr={sc.lr}")
+
+
+def bench_config(sc: synth.Scene) -> dict:
+    """`config` names the workload and nothing run-specific, so both arms (and every N) print the same object."""
+    return {"workload": workload_label(sc), "l2": L2_NOTE}
 
 
 def measured_peak():
@@ -119,29 +129,34 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------- CPU reference arm
-def time_reference_port(sc: synth.Scene, uvs, steps: int, warmup: int, budget_s: float = 150.0):
+NOMINAL_CPU_STEP_S = 0.35           # a C2 step of the torch-CPU port on this pool's 16 host cores
+
+
+def reference_cameras(sc: synth.Scene, steps: int, warmup: int, budget_s: float):
+    """The camera subset the CPU arm renders per step: ALL cameras unless K + W full steps would blow the time budget at the
+    nominal step time — a function of (K, W) only, so every N of a scaling run times exactly the same batch."""
+    n_cams = sc.poses.shape[0]
+    need = NOMINAL_CPU_STEP_S * (sc.n_rays / 12800.0) * (steps + warmup)
+    if need <= budget_s:
+        return None
+    return torch.arange(max(1, int(n_cams * budget_s / need)))
+
+
+def time_reference_port(sc: synth.Scene, uvs, steps: int, warmup: int, budget_s: float = 170.0):
     """The reference's step (scripts/train.py:130-184) through the torch-CPU port on all host cores."""
     from oracle.torch_port import ReferenceStep
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     ref = ReferenceStep(sc.grid, sc.points_distance, sc.poses, sc.fov, sc.imgs, sc.rays_per_cam, sc.num_samples,
                         sc.delta_step, sc.lr)
-    n_cams = sc.poses.shape[0]
-    t0 = time.perf_counter()
-    ref.step(uvs[0])
-    first = time.perf_counter() - t0
-    # bound the whole run to ~budget_s of CPU work: if needed, each step renders a camera subset of the batch
-    cams = None
-    if first * (steps + warmup) > budget_s:
-        keep = max(1, int(n_cams * budget_s / (first * (steps + warmup))))
-        cams = torch.arange(keep)
-    n_step_rays = (len(cams) if cams is not None else n_cams) * sc.rays_per_cam
+    cams = reference_cameras(sc, steps, warmup, budget_s)
+    n_step_rays = (len(cams) if cams is not None else sc.poses.shape[0]) * sc.rays_per_cam
 
     def one(i):
         u = uvs[i % len(uvs)]
         return ref.step(u if cams is None else u[cams], cams)
 
-    for i in range(1, warmup):
+    for i in range(warmup):
         one(i)
     times = []
     for i in range(steps):
@@ -150,8 +165,8 @@ def time_reference_port(sc: synth.Scene, uvs, steps: int, warmup: int, budget_s:
         times.append(time.perf_counter() - t0)
     total = float(sum(times))
     return {"rays_per_s": n_step_rays * steps / total, "ms_per_step": 1e3 * total / steps,
-            "ms_min": 1e3 * min(times), "cores": cores, "rays_per_step": n_step_rays,
-            "subsampled": cams is not None}
+            "ms_min": 1e3 * min(times), "ms_max": 1e3 * max(times), "rays_per_s_best": n_step_rays / min(times), "cores": cores,
+            "rays_per_step": n_step_rays, "subsampled": cams is not None}
 
 
 def time_c_port(sc: synth.Scene, uvs, steps: int, warmup: int):
@@ -186,17 +201,18 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sc = workload_scene(args.workload)
+    sc = synth.make_scene(args.workload)
     n_batches = min(args.steps + args.warmup, MAX_DISTINCT_BATCHES)
     uvs = [synth.random_uv(sc.poses.shape[0], sc.rays_per_cam, seed=1000 + i) for i in range(n_batches)]
     r = time_reference_port(sc, uvs, args.steps, args.warmup)
     sample = (f"{'camera subset: ' if r['subsampled'] else 'full batch: '}{r['rays_per_step']} of {sc.n_rays} rays per step, "
-              f"{args.steps} steps after {args.warmup} warm-up")
+              f"{args.steps} steps after {args.warmup} warm-up; step time min/mean/max {r['ms_min']:.0f}/{r['ms_per_step']:.0f}/{r['ms_max']:.0f} ms")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["rays_per_s"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_label(sc), "device": "host CPU", "threads": r["cores"]},
+        "config": bench_config(sc),
+        "run": {"device": "host CPU", "threads": r["cores"], "best_step_rays_per_s": r["rays_per_s_best"]},
         "cpu_baseline": {"value": r["rays_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["rays_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -209,15 +225,352 @@ def run_reference_arm(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------- GPU arm helpers
+class Ctx:
+    """Process-wide bits every measurement needs."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dev = torch.device("cuda", self.local_rank)
+        self.peak, self.peak_src = measured_peak()
+        self.multi = os.environ.get("PLX_MULTI", "peer") if self.world > 1 else "single"     # peer | nccl
+        self.exchange = os.environ.get("PLX_EXCHANGE") or None                               # push | pull | None = auto
+        self.sampler = ClockSampler(self.local_rank)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def make_trainer(cx: Ctx, sc: synth.Scene, dev_scene: dict, **kw):
+    from plenoxels_b200.trainer import PeerVoxelTrainer, VoxelTrainer
+    args_ = (dev_scene["grid"], sc.points_distance, dev_scene["poses"], sc.fov, dev_scene["imgs"], sc.rays_per_cam, sc.num_samples,
+             sc.delta_step)
+    k = dict(lr=sc.lr, n_rays_global=sc.n_rays * cx.world)
+    k.update(kw)
+    if cx.multi == "peer":
+        try:
+            return PeerVoxelTrainer(*args_, exchange=cx.exchange, **k)
+        except Exception as e:          # symmetric memory unavailable on this box: NCCL all-reduce path (rendezvous failures are
+            log(f"[bench] peer-memory trainer unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce trainer")
+            ok = torch.zeros(1, device=cx.dev)           # collective, so every rank lands here together)
+            cx.dist.all_reduce(ok)
+            cx.multi = "nccl"
+    return VoxelTrainer(*args_, **k)
+
+
+def timed_regions(cx: Ctx, step_fn, flush_fn, K: int, W: int, repeats: int):
+    """W warm-up steps, then `repeats` regions of exactly K steps, each bracketed by barrier + synchronize, CUDA events on the
+    launching stream, max over ranks.  Returns the per-region totals in ms."""
+    i = 0
+    for _ in range(W):
+        step_fn(i)
+        i += 1
+    out = []
+    for _ in range(repeats):
+        cx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            step_fn(i)
+            i += 1
+        flush_fn()
+        e1.record()
+        cx.barrier()
+        out.append(cx.max_over_ranks(e0.elapsed_time(e1)))
+    return out
+
+
+def spread(ms_list, K):
+    a = np.asarray(ms_list) / K
+    return {"n": len(ms_list), "ms_per_step_median": float(np.median(a)), "ms_per_step_min": float(a.min()),
+            "ms_per_step_max": float(a.max())}
+
+
+def count_in_bounds(sc, tr, dev_scene, uv_dev, n=4):
+    from plenoxels_b200 import ops
+    m_in = []
+    for i in range(min(len(uv_dev), n)):
+        dirs, _ = ops.generate_rays(dev_scene["imgs"], tr.poses, sc.fov, uv=uv_dev[i], want_targets=False)
+        _, cnt = ops.render_rays(tr.grid, tr.poses[:, :3, 3], dirs, sc.num_samples, sc.delta_step, tr.gmin, sc.points_distance,
+                                 rays_per_origin=sc.rays_per_cam, return_count=True)
+        m_in.append(int(cnt.sum().item()))
+    return float(np.mean(m_in))
+
+
+def phase_times(cx: Ctx, tr, uv_dev, n_inst: int):
+    """Per-phase device time of the step in situ: the same launches, with CUDA events between the phases."""
+    peer = hasattr(tr, "exchange")
+    names = ["render_train"] + (["barrier_grad", "exchange+adam" if tr.exchange == "pull" else "slab_adam+allgather", "barrier_param"]
+                                if peer and not tr._fused else ["adam" if cx.world == 1 else "exchange+adam"])
+    for w_ in range(3):
+        tr.step(uv_dev[w_ % len(uv_dev)])
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(n_inst)]
+    cx.barrier()
+    for i in range(n_inst):
+        ev = evs[i]
+        ev[0].record()
+        tr.render_phase(uv_dev[i % len(uv_dev)])
+        ev[1].record()
+        if len(names) == 4:
+            marks = iter(ev[2:4])
+            tr._mark = lambda: next(marks).record()
+        tr.update_phase()
+        ev[-1].record()
+    tr._mark = None
+    tr.flush()
+    torch.cuda.synchronize(cx.dev)
+    return {n: float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(n_inst)])) for j, n in enumerate(names)}
+
+
+def roofline_of(cx: Ctx, kms: dict, m_in: float, n_rays: int, cells: int, tr, workload: str, ms_step: float):
+    """Roofline of the dominant phase (HBM byte model of SURVEY.md 8d; NVLink bytes per direction for the exchange) and of the
+    whole step."""
+    W = cx.world
+    alg = {"render_train": 64.0 * m_in + 96.0 * n_rays, "adam": 160.0 * cells}
+    nv = {}
+    if W > 1:
+        f = (W - 1) / W
+        mc = bool(getattr(tr, "multicast", False))
+        exch = getattr(tr, "exchange", "nccl")
+        if exch == "push":
+            alg["slab_adam+allgather"] = 160.0 * cells / W + 16.0 * cells * f       # own slab + the peers' parameter stores landing here
+            nv["slab_adam+allgather"] = 16.0 * cells * f                              # inbound parameters per GPU
+            nv["render_train"] = 16.0 * m_in * f                                      # outbound reductions (upper bound: before run merging)
+        else:
+            alg["exchange+adam"] = 160.0 * cells / W + 16.0 * cells * f
+            nv["exchange+adam"] = 16.0 * cells * (1.0 if mc else 2.0 * f)              # gradients in (reduced by the switch or per peer) + parameters in
+    timed = {k: v for k, v in kms.items() if v and k in alg}
+    dom = max(timed, key=timed.get)
+    hbm_gbs = alg[dom] / (timed[dom] * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get(workload, {}).get(dom)
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": dom, "achieved": hbm_gbs, "peak": cx.peak, "unit": "GB/s", "frac": hbm_gbs / cx.peak,
+            "traffic": traffic, "traffic_source": "static: ncu --set full capture of this kernel on this workload (profiles/traffic.json)"
+            if traffic else None,
+            "peak_source": cx.peak_src, "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": kms,
+            "kernel_gbs": {k: alg[k] / (v * 1e-3) / 1e9 for k, v in timed.items()},
+            "note": "algorithmic bytes follow SURVEY.md 8d (160 B/cell for the optimiser); the optimiser does not store |grad| nor "
+                    "re-clear the gradient of cells no ray touched this step (32 of those 160 B/cell), so its moved bytes (traffic) are "
+                    "below the model and its fraction can exceed 1"}
+    if dom in nv:
+        nv_gbs = nv[dom] / (timed[dom] * 1e-3) / 1e9
+        if nv[dom] / NVLINK_GBS > alg[dom] / cx.peak:        # the NVLink floor of this phase is above its HBM floor
+            roof.update({"bound": "nvlink", "achieved": nv_gbs, "peak": NVLINK_GBS, "frac": nv_gbs / NVLINK_GBS,
+                         "peak_source": "measured peer copy per direction per GPU (B200_PROFILING.md)",
+                         "algorithmic_bytes_per_launch": nv[dom], "hbm_achieved": hbm_gbs})
+    if nv:
+        roof["nvlink"] = {k: {"bytes_per_direction": b, "achieved": b / (kms[k] * 1e-3) / 1e9, "peak": NVLINK_GBS,
+                              "frac": b / (kms[k] * 1e-3) / 1e9 / NVLINK_GBS} for k, b in nv.items() if kms.get(k)}
+    step_bytes = 64.0 * m_in + 96.0 * n_rays + 160.0 * cells
+    step_gbs = step_bytes / (ms_step * 1e-3) / 1e9
+    roof["step"] = {"algorithmic_bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / cx.peak,
+                    "model": "64*M_in + 96*N + 160*cells (per GPU)", "m_in": m_in, "n_rays": n_rays, "cells": cells}
+    return roof
+
+
+def to_device(sc: synth.Scene, dev):
+    return {"grid": sc.grid.to(dev), "poses": sc.poses.to(dev), "imgs": sc.imgs.to(dev)}
+
+
+def measure_training(cx: Ctx, sc: synth.Scene, K: int, W: int, repeats: int, e2e: bool, dev_scene=None, **trainer_kw):
+    """value / e2e / per-phase numbers of one training workload on the current process group."""
+    dev_scene = dev_scene or to_device(sc, cx.dev)
+    C_, R = sc.poses.shape[0], sc.rays_per_cam
+    n_batches = min(K + W, MAX_DISTINCT_BATCHES)
+    # every rank draws its own rays (weak scaling: per-GPU batch fixed); uv generated on the host, seeded
+    uv_host = [synth.random_uv(C_, R, seed=1000 + cx.rank * 100003 + i).pin_memory() for i in range(n_batches)]
+    uv_dev = [u.to(cx.dev) for u in uv_host]
+    tr = make_trainer(cx, sc, dev_scene, **trainer_kw)
+    cells = sc.G ** 3
+    m_in = count_in_bounds(sc, tr, dev_scene, uv_dev)
+    out = {}
+    # ---- region 1: device-resident inputs ("value")
+    cx.sampler.start()
+    ms = timed_regions(cx, lambda i: tr.step(uv_dev[i % n_batches]), tr.flush, K, W, repeats)
+    cx.sampler.stop()
+    ms_med = float(np.median(ms))
+    out.update(value=sc.n_rays * cx.world * K / (ms_med * 1e-3), ms_per_step=ms_med / K, repeats=spread(ms, K),
+               final_loss=float(tr.loss.item()), launches_per_step=tr.launches_per_step)
+    # ---- region 2: end to end from pinned host buffers, loss read on the host every step ("e2e")
+    if e2e:
+        tr2 = make_trainer(cx, sc, dev_scene, **trainer_kw)
+        losses = []
+
+        def host_step(i):
+            tr2.step_host(uv_host[i % n_batches])
+            losses.append(tr2.wait_result())          # the host reads the loss of THIS step (scripts/train.py:159)
+
+        for i in range(W):
+            host_step(i)
+        walls = []
+        cx.sampler.start()
+        for rep in range(repeats):
+            cx.barrier()
+            t0 = time.perf_counter()
+            for i in range(K):
+                host_step(W + rep * K + i)
+            tr2.flush()
+            cx.barrier()
+            walls.append(cx.max_over_ranks(time.perf_counter() - t0) * 1e3)
+        cx.sampler.stop()
+        w_med = float(np.median(walls))
+        out["e2e"] = {"value": sc.n_rays * cx.world * K / (w_med * 1e-3), "unit": UNIT, "h2d_bytes_per_step": sc.n_rays * 8,
+                      "d2h_bytes_per_step": 8, "ms_per_step": w_med / K, "repeats": spread(walls, K), "last_loss": losses[-1],
+                      "note": "per step: the march kernel reads the uv draw out of pinned host memory (zero-copy over PCIe), the "
+                              "optimiser kernel stores {loss, step} into pinned host memory and the host waits for and reads "
+                              "that loss before issuing the next step; images/poses/grid stay resident as in the reference "
+                              "(scripts/train.py:75); wall clock, max over ranks, median of the repeated K-step regions"}
+        del tr2
+    # ---- region 3: per-phase durations in situ
+    tr3 = make_trainer(cx, sc, dev_scene, **trainer_kw)
+    cx.sampler.start()
+    kms = phase_times(cx, tr3, uv_dev, min(K, 64))
+    cx.sampler.stop()
+    out["roofline"] = roofline_of(cx, kms, m_in, sc.n_rays, cells, tr3, sc.name, out["ms_per_step"])
+    out["parallelism"] = ("single GPU" if cx.world == 1 else f"ray-sharded replicas x{cx.world}, " + (
+        {"push": "push exchange: the march reduces every touched cell into the slab owner's buffer over NVLink, slab Adam, parameters "
+                 "stored to every replica" + (" through NVLS multicast" if tr3.multicast else " per peer"),
+         "pull": "pull exchange: gradient reduce-scatter + Adam + parameter all-gather fused in one kernel over NVLink peer memory" +
+                 (" (NVLS in-switch reduce / multicast)" if getattr(tr3, "multicast", False) else "")}[tr3.exchange]
+        if hasattr(tr3, "exchange") else "dense gradient all-reduce (NCCL) + replicated Adam"))
+    del tr, tr3
+    return out
+
+
+def multi_gpu_selfcheck(cx: Ctx, sc: synth.Scene, dev_scene):
+    """Untimed: (1) after a few steps of the product multi-GPU trainer all replicas hold the same bits; (2) the gradient it
+    applied equals the NCCL path's: both trainers take ONE step from the same state and their first Adam moment
+    (= (1 - beta1) * gradient after step 1) is compared over the whole grid."""
+    from plenoxels_b200.trainer import VoxelTrainer
+    dist = cx.dist
+    C_, R = sc.poses.shape[0], sc.rays_per_cam
+    uvs = [synth.random_uv(C_, R, seed=777 + cx.rank * 131 + i).to(cx.dev) for i in range(3)]
+    tp = make_trainer(cx, sc, dev_scene)
+    tn = VoxelTrainer(dev_scene["grid"], sc.points_distance, dev_scene["poses"], sc.fov, dev_scene["imgs"], R, sc.num_samples,
+                      sc.delta_step, lr=sc.lr, n_rays_global=sc.n_rays * cx.world)
+    lp, ln = float(tp.step(uvs[0])), float(tn.step(uvs[0]))
+    tp.flush()
+    torch.cuda.synchronize(cx.dev)
+    m_peer, _ = tp._full_moments()
+    num = float((m_peer - tn.exp_avg).abs().max())
+    den = float(tn.exp_avg.abs().max())
+    for u in uvs[1:]:
+        tp.step(u)
+    tp.flush()
+    torch.cuda.synchronize(cx.dev)
+    ref = tp.grid.detach().clone()
+    dist.broadcast(ref, src=0)
+    same = torch.tensor([1.0 if torch.equal(ref, tp.grid) else 0.0], device=cx.dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    out = {"replicas_bit_equal": bool(same.item() == 1.0), "grad_relerr_vs_nccl_path": num / max(den, 1e-30),
+           "global_loss_peer": lp, "global_loss_nccl": ln, "exchange": getattr(tp, "exchange", "nccl"),
+           "multicast": bool(getattr(tp, "multicast", False)), "steps_checked": 3, "workload": sc.name}
+    del tp, tn
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------- other BASELINE configs
+def timed_call(fn, n=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def extra_c4(cx: Ctx):
+    """BASELINE config #4: 512^3 grid, inference-only render of one 800x800 view (even-spread rays, S = 600, delta = 0.01,
+    alpha threshold 0.2 as scripts/compare_inference_to_image.py:91): the ray-packet kernel behind visulize_3d_in_2d."""
+    from plenoxels_b200 import ops
+    dev = cx.dev
+    G, S, delta, side = 512, 600, 0.01, 800
+    pd = synth.GRID_EXTENT / G
+    grid = synth.ball_grid(G).to(dev).clip_(0, 1)
+    grid[..., 3][grid[..., 3] < 0.2] = 0.0
+    poses = synth.lookat_poses(4)[1:2].to(dev)
+    gmin = ops.grid_origin(grid.shape, pd)
+    n = side * side
+    dirs, _ = ops.generate_rays(None, poses, synth.CAMERA_ANGLE_X, uv=None, rays_per_cam=n, want_targets=False)
+    o = poses[:, :3, 3]
+    out = {"workload": f"c4: {G}^3 grid, one {side}x{side} view = {n} rays, {S} samples/ray (delta={delta}), inference only"}
+    for mode in ("nearest", "trilinear"):
+        _, cnt = ops.render_rays(grid, o, dirs, S, delta, gmin, pd, mode=mode, clamp=False, rays_per_origin=n, return_count=True)
+        m_in = int(cnt.sum())
+        ms = timed_call(lambda: ops.render_rays(grid, o, dirs, S, delta, gmin, pd, mode=mode, clamp=False, rays_per_origin=n,
+                                                coherent=True), n=8)
+        ms_img = timed_call(lambda: ops.render_image_u8(grid, poses, synth.CAMERA_ANGLE_X, side, S, delta, gmin, pd, mode=mode), n=8) \
+            if hasattr(ops, "render_image_u8") else None
+        alg = (16.0 * (8 if mode == "trilinear" else 1)) * m_in + 40.0 * n
+        gbs = alg / (ms * 1e-3) / 1e9
+        out[mode] = {"ms_per_frame": ms, "Mrays_per_s": n / ms / 1e3, "m_in": m_in,
+                     "ms_per_frame_raygen+march+uint8_image": ms_img,
+                     "roofline": {"bound": "hbm", "kernel": "k_render_fwd_packet", "achieved": gbs, "peak": cx.peak, "unit": "GB/s",
+                                  "frac": gbs / cx.peak, "algorithmic_bytes_per_launch": alg,
+                                  "model": ("128" if mode == "trilinear" else "16") + "*M_in + 40*N"}}
+    del grid
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_c5(cx: Ctx):
+    """BASELINE config #5 (three points of the sweep): random ray batches on a 256^3 grid, forward march and fused training
+    march, HBM GB/s against the roofline."""
+    from plenoxels_b200 import ops
+    dev = cx.dev
+    G = 256
+    pd = synth.GRID_EXTENT / G
+    grid = synth.ball_grid(G).to(dev)
+    gg = torch.zeros_like(grid)
+    gmin = ops.grid_origin(grid.shape, pd)
+    poses = synth.lookat_poses(64).to(dev)
+    imgs = torch.rand(64, 32, 32, 4, device=dev)
+    pts = []
+    for logn, S in ((16, 256), (20, 256), (20, 512)):
+        n, delta = 1 << logn, 6.0 / S
+        R = n // 64
+        uv = torch.rand(64, R, 2, device=dev, generator=torch.Generator(device=dev).manual_seed(logn))
+        dirs, targets = ops.generate_rays(imgs, poses, synth.CAMERA_ANGLE_X, uv=uv)
+        o = poses[:, :3, 3]
+        _, cnt = ops.render_rays(grid, o, dirs, S, delta, gmin, pd, rays_per_origin=R, return_count=True)
+        m_in = int(cnt.sum())
+        ms_f = timed_call(lambda: ops.render_rays(grid, o, dirs, S, delta, gmin, pd, rays_per_origin=R), n=6)
+        ms_t = timed_call(lambda: ops.render_train(grid, gg, S, delta, gmin, pd, origins=o, dirs=dirs, targets=targets,
+                                                   rays_per_origin=R), n=6)
+        gf, gt = (16.0 * m_in + 40.0 * n) / (ms_f * 1e-3) / 1e9, (64.0 * m_in + 96.0 * n) / (ms_t * 1e-3) / 1e9
+        pts.append({"rays": n, "S": S, "m_in": m_in, "fwd_ms": ms_f, "fwd_Mrays_s": n / ms_f / 1e3, "train_ms": ms_t,
+                    "train_Mrays_s": n / ms_t / 1e3,
+                    "roofline_fwd": {"bound": "hbm", "achieved": gf, "peak": cx.peak, "frac": gf / cx.peak, "model": "16*M_in + 40*N"},
+                    "roofline_train": {"bound": "hbm", "achieved": gt, "peak": cx.peak, "frac": gt / cx.peak, "model": "64*M_in + 96*N"}})
+    del grid, gg
+    torch.cuda.empty_cache()
+    return {"workload": "c5: 256^3 grid (10 % ball), random rays from 64 cameras", "points": pts}
+
+
 # ----------------------------------------------------------------------------------------------------- GPU arm
 def run_gpu_arm(args):
-    import torch.distributed as dist
-    from plenoxels_b200 import _lib, ops
-    from plenoxels_b200.trainer import PeerVoxelTrainer, VoxelTrainer
+    from plenoxels_b200 import _lib
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     # the contract is ONE JSON line on stdout: libraries (NCCL's version banner) write to fd 1, so park the real stdout
     # and point fd 1 at stderr until the line is ready
     sys.stdout.flush()
@@ -225,196 +578,68 @@ def run_gpu_arm(args):
     os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
+    cx = Ctx()
+    torch.cuda.set_device(cx.local_rank)
+    if cx.world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        cx.dist.init_process_group("nccl", device_id=cx.dev)
     _lib.load()
-
-    sc = workload_scene(args.workload)
-    C_, R, S = sc.poses.shape[0], sc.rays_per_cam, sc.num_samples
-    n_rays = sc.n_rays
     K, W = args.steps, args.warmup
-    n_batches = min(K + W, MAX_DISTINCT_BATCHES)
-    # every rank draws its own rays (weak scaling: per-GPU batch fixed); uv generated on the host, seeded
-    uv_host = [synth.random_uv(C_, R, seed=1000 + rank * 100003 + i).pin_memory() for i in range(n_batches)]
-    uv_dev = [u.to(dev) for u in uv_host]
 
-    multi = os.environ.get("PLX_MULTI", "peer") if world > 1 else "single"
-    state = {"multi": multi}
+    sc = synth.make_scene(args.workload)
+    dev_scene = to_device(sc, cx.dev)
+    head = measure_training(cx, sc, K, W, REPEATS, e2e=True, dev_scene=dev_scene)
+    clocks = cx.sampler.summary()
+    extra = {}
 
-    def new_trainer():
-        args_ = (sc.grid.to(dev), sc.points_distance, sc.poses.to(dev), sc.fov, imgs_dev, R, S, sc.delta_step)
-        kw = dict(lr=sc.lr, n_rays_global=n_rays * world)
-        if state["multi"] == "peer":
-            try:
-                return PeerVoxelTrainer(*args_, **kw)
-            except Exception as e:          # symmetric memory unavailable on this box: NCCL all-reduce path (all ranks agree:
-                log(f"[bench] peer-memory trainer unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce trainer")
-                ok = torch.zeros(1, device=dev)           # rendezvous failures are collective, so every rank lands here)
-                dist.all_reduce(ok)
-                state["multi"] = "nccl"
-        return VoxelTrainer(*args_, **kw)
-
-    imgs_dev = sc.imgs.to(dev)
-    tr = new_trainer()
-    cells = sc.G ** 3
-
-    # in-bounds sample count of the timed batches (oracle-mask definition, counted by K1's exact test; untimed)
-    m_in = []
-    for i in range(min(n_batches, 8)):
-        dirs, _ = ops.generate_rays(imgs_dev, tr.poses, sc.fov, uv=uv_dev[i], want_targets=False)
-        _, cnt = ops.render_rays(tr.grid, tr.poses[:, :3, 3], dirs, S, sc.delta_step, tr.gmin, sc.points_distance,
-                                 rays_per_origin=R, return_count=True)
-        m_in.append(int(cnt.sum().item()))
-    m_in = float(np.mean(m_in))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    sampler = ClockSampler(local_rank)
-
-    # ---- region 1: device-resident inputs ("value")
-    for i in range(W):
-        tr.step(uv_dev[i % n_batches])
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        tr.step(uv_dev[(W + i) % n_batches])
-    tr.flush()                                                 # multi-GPU: every replica complete (no-op on one GPU)
-    e1.record()
-    barrier()
-    sampler.stop()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    value = n_rays * world * K / (ms_total * 1e-3)
-    final_loss = float(tr.loss.item())
-
-    # ---- region 2: end to end from pinned host buffers, loss read on the host every step ("e2e")
-    tr2 = new_trainer()
-    for i in range(W):
-        tr2.step_host(uv_host[i % n_batches])
-        tr2.wait_result()
-    barrier()
-    sampler.start()
-    t0 = time.perf_counter()
-    host_losses = []
-    for i in range(K):
-        tr2.step_host(uv_host[(W + i) % n_batches])
-        host_losses.append(tr2.wait_result())                  # the host reads the loss of THIS step (scripts/train.py:159)
-    tr2.flush()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    sampler.stop()
-    e2e_value = n_rays * world * K / e2e_s
-    del tr2
-
-    # ---- region 3: per-kernel durations in situ (same kernels, launched one by one with events in between)
-    import ctypes as C
-    tr3 = new_trainer()
-    lib = _lib.load()
-    st = _lib.stream_ptr(dev)
-    fused = os.environ.get("PLX_TRAIN_FUSED", "1") != "0"
-    n_inst = min(K, 64)
-    for w_ in range(3):
-        tr3.step(uv_dev[w_ % n_batches])
-    if world > 1:
-        # multi-GPU: the two phases of the step (render | gradient exchange + optimiser)
-        names = ["render_train", "exchange+adam"]
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_inst)]
-        barrier()
-        sampler.start()
-        for i in range(n_inst):
-            ev = evs[i]
-            ev[0].record()
-            tr3.render_phase(uv_dev[(W + i) % n_batches])
-            ev[1].record()
-            tr3.update_phase()
-            ev[2].record()
-    else:
-        names = ["render_train", "adam"] if fused else ["generate_rays", "render_fwd", "render_bwd", "adam"]
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(n_inst)]
-        a = tr3._args
-        fwd, bwd, trn = _lib.PlxRenderFwd(), _lib.PlxRenderBwd(), _lib.PlxRenderTrain()
-        rays = _lib.make_rays(tr3.poses[:, :3, 3], tr3.dirs, R)
-        gs, ls = 2.0 / (4.0 * n_rays * world), 1.0 / (4.0 * n_rays * world)
-        fwd.march, fwd.rays, fwd.grid, fwd.rgba, fwd.tcarry = a.march, rays, a.grid, a.rgba, a.tcarry
-        fwd.targets, fwd.grad_rgba, fwd.loss = a.targets, a.grad_rgba, a.loss
-        fwd.grad_scale, fwd.loss_scale = gs, ls
-        bwd.march, bwd.rays, bwd.grid, bwd.grad_rgba, bwd.tcarry, bwd.grad_grid = a.march, rays, a.grid, a.grad_rgba, a.tcarry, a.grad
-        trn.march, trn.grid, trn.grad_grid, trn.rgba, trn.loss = a.march, a.grid, a.grad, a.rgba, a.loss
-        trn.rays.n_rays = n_rays
-        trn.gen.imgs, trn.gen.n_cams, trn.gen.img_h, trn.gen.img_w = a.imgs, a.n_cams, a.img_h, a.img_w
-        trn.gen.poses, trn.gen.fov, trn.gen.rays_per_cam = a.poses, a.fov, R
-        trn.grad_scale, trn.loss_scale = gs, ls
-        sampler.start()
-        for i in range(n_inst):
-            u = uv_dev[(W + i) % n_batches]
-            ev = evs[i]
-            tr3.loss.zero_()
-            if tr3._dynamic:
-                tr3._work_counter.zero_()
-                trn.work_counter = tr3._work_counter.data_ptr()
-            ev[0].record()
-            if fused:
-                trn.gen.uv = u.data_ptr()
-                _lib.check(lib.plx_render_train(C.byref(trn), st))
-            else:
-                _lib.check(lib.plx_generate_rays(a.imgs, a.n_cams, a.img_h, a.img_w, a.poses, a.fov, u.data_ptr(), R, 0, a.dirs,
-                                                 a.targets, st))
-                ev[1].record()
-                _lib.check(lib.plx_render_fwd(C.byref(fwd), st))
-                ev[2].record()
-                _lib.check(lib.plx_render_bwd(C.byref(bwd), st))
-            ev[-2].record()
-            tr3.step_count += 1
-            _lib.check(lib.plx_adam_step(a.grid, a.grad, a.exp_avg, a.exp_avg_sq, a.grad_abs_sum, cells * 4, sc.lr, 0.9, 0.999,
-                                         1e-8, tr3.step_count, 1, st))
-            ev[-1].record()
-    torch.cuda.synchronize(dev)
-    sampler.stop()
-    kms = {n: float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(n_inst)])) for j, n in enumerate(names)}
-    del tr3
-
-    # ---- roofline of the dominant kernel + of the whole step (SURVEY.md §8d byte model)
-    peak, peak_src = measured_peak()
-    alg = {"generate_rays": 8.0 * n_rays + 28.0 * n_rays, "render_fwd": 16.0 * m_in + 40.0 * n_rays,
-           "render_bwd": 48.0 * m_in + 56.0 * n_rays, "render_train": 64.0 * m_in + 96.0 * n_rays, "adam": 160.0 * cells}
-    timed = {k: v for k, v in kms.items() if v and k in alg}
-    dom = max(timed, key=timed.get)
-    achieved = alg[dom] / (timed[dom] * 1e-3) / 1e9
-    traffic = None
-    prof_json = os.path.join(REPO, "profiles", "traffic.json")
-    if os.path.exists(prof_json):
+    def guarded(name, fn):
+        """An extra record must never break the headline line; a failure is reported in its place (all ranks agree on it)."""
         try:
-            traffic = json.load(open(prof_json)).get(args.workload, {}).get(dom)
-        except Exception:
-            traffic = None
-    step_bytes = 64.0 * m_in + 96.0 * n_rays + 160.0 * cells
-    step_gbs = step_bytes / (ms_total / K * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
-                "kernel_ms": kms, "kernel_gbs": {k: alg[k] / (v * 1e-3) / 1e9 for k, v in timed.items()},
-                "note": "algorithmic bytes follow SURVEY.md 8d (160 B/cell for the optimiser); K3 does not store |grad| nor "
-                        "re-clear the gradient of cells no ray touched this step (32 of those 160 B/cell), so its moved bytes "
-                        "(traffic) are below the model and its fraction can exceed 1",
-                "step": {"algorithmic_bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak,
-                         "model": "64*M_in + 96*N + 160*cells", "m_in": m_in, "n_rays": n_rays, "cells": cells}}
+            extra[name] = fn()
+        except Exception as e:      # noqa: BLE001
+            log(f"[bench] extra '{name}' failed: {type(e).__name__}: {e}")
+            extra[name] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+
+    if cx.world > 1 and cx.multi == "peer":
+        guarded("selfcheck", lambda: multi_gpu_selfcheck(cx, sc, dev_scene))
+    del dev_scene
+    torch.cuda.empty_cache()
+
+    if not args.no_extras:
+        if args.workload != "c3":
+            def c3():
+                s3 = synth.make_scene("c3")
+                d3 = to_device(s3, cx.dev)
+                r = measure_training(cx, s3, K, W, 5, e2e=False, dev_scene=d3)
+                rec = {"config": bench_config(s3), "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "n_gpus": cx.world,
+                       "scaling": "weak", "repeats": r["repeats"], "kernel_ms": r["roofline"]["kernel_ms"], "roofline": r["roofline"],
+                       "parallelism": r["parallelism"]}
+                if cx.world > 1 and cx.multi == "peer":
+                    rec["selfcheck"] = multi_gpu_selfcheck(cx, s3, d3)
+                return rec
+            guarded("c3", c3)
+        if cx.world == 1:
+            def c2_tri():
+                d2 = to_device(sc, cx.dev)
+                r = measure_training(cx, sc, K, W, 5, e2e=False, dev_scene=d2, mode="trilinear")
+                roof = r["roofline"]
+                m_in, n = roof["step"]["m_in"], sc.n_rays
+                ms_r = roof["kernel_ms"]["render_train"]
+                alg = (128.0 + 32.0 * 8) * m_in + 96.0 * n      # 8 corner gathers + 8 gradient read-modify-writes per in-bounds sample
+                return {"workload": workload_label(sc).replace("nearest lookup", "trilinear lookup"), "value": r["value"], "unit": UNIT,
+                        "ms_per_step": r["ms_per_step"], "repeats": r["repeats"], "kernel_ms": roof["kernel_ms"],
+                        "roofline": {"bound": "hbm", "kernel": "render_train (trilinear)", "achieved": alg / (ms_r * 1e-3) / 1e9,
+                                     "peak": cx.peak, "unit": "GB/s", "frac": alg / (ms_r * 1e-3) / 1e9 / cx.peak,
+                                     "algorithmic_bytes_per_launch": alg, "model": "(128 + 256)*M_in + 96*N"}}
+            guarded("c2_trilinear", c2_tri)
+            guarded("c4", lambda: extra_c4(cx))
+            guarded("c5", lambda: extra_c5(cx))
 
     # ---- CPU baseline (rank 0, N = 1 only): the torch-CPU port of the reference's step on the host cores
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if cx.world == 1 and not args.no_cpu_baseline:
+        C_, R = sc.poses.shape[0], sc.rays_per_cam
         uvs = [synth.random_uv(C_, R, seed=1000 + i) for i in range(4)]
         r = time_reference_port(sc, uvs, steps=3, warmup=1, budget_s=30.0)
         cpu_baseline = {"value": r["rays_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
@@ -425,48 +650,40 @@ def run_gpu_arm(args):
         except Exception as e:
             log(f"[bench] C port not timed ({type(e).__name__}: {e})")
 
-    if rank == 0:
+    if cx.rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": cx.world, "steps": K, "warmup": W,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_label(sc),
-                       "l2": "no flush: each step streams 5 grid-sized state arrays (%.0f MB) plus gathers from a %.2f GB "
-                             "image set, more than the 126 MB L2; a fresh uv batch every step" %
-                             (5 * cells * 16 / 1e6, sc.imgs.numel() * 4 / 1e9),
-                       "parallelism": ("single GPU" if world == 1 else
-                                       f"ray-sharded replicas x{world}, " +
-                                       ("gradient reduce-scatter + Adam + parameter all-gather fused in one kernel over NVLink peer memory"
-                                        if state["multi"] == "peer" else "dense gradient all-reduce (NCCL) + replicated Adam")),
-                       "distinct_batches": n_batches, "final_loss": final_loss},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_rays * 8, "d2h_bytes_per_step": 8,
-                    "ms_per_step": 1e3 * e2e_s / K,
-                    "note": "per step: the march kernel reads the uv draw out of pinned host memory (zero-copy over PCIe), the "
-                            "optimiser kernel stores {loss, step} into pinned host memory and the host waits for and reads "
-                            "that loss before issuing the next step; images/poses/grid stay resident as in the reference "
-                            "(scripts/train.py:75)",
-                    "last_loss": host_losses[-1]},
-            "gpu_launches": (getattr(tr, "launches_per_step", 2) if world > 1 else (2 if fused else 4)) * K,
-            "clocks": sampler.summary(),
-            "roofline": roofline,
+            "config": bench_config(sc),
+            "run": {"parallelism": head["parallelism"], "distinct_batches": min(K + W, MAX_DISTINCT_BATCHES),
+                    "final_loss_global": head["final_loss"], "repeats": head["repeats"],
+                    "timing": f"{REPEATS} regions of exactly {K} steps each (barrier + synchronize both sides, CUDA events, max over ranks); "
+                              "value and ms_per_step are the median region"},
+            "e2e": head["e2e"],
+            "gpu_launches": head["launches_per_step"] * K,
+            "clocks": clocks,
+            "roofline": head["roofline"],
             "cpu_baseline": cpu_baseline,
+            "extra": extra,
         }
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if cx.world > 1:
+        cx.dist.barrier()
+        cx.dist.destroy_process_group()
     return 0
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline workload only (skip the C3 / C4 / C5 / trilinear records)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -488,6 +488,7 @@ class PeerVoxelTrainer(VoxelTrainer):
                 p.sync.err = self._err
                 self._peers.append(p)
         self._cur = 0
+        self._mark = None                     # profiling hook (bench.py): called after the first barrier and after the optimiser kernel
         self._args = self._make_args()
         self.launches_per_step = 2 if self._fused else 4          # march, [barrier], exchange / optimiser, [barrier]
         torch.cuda.synchronize(dev)
@@ -555,8 +556,12 @@ class PeerVoxelTrainer(VoxelTrainer):
             self._barrier(0, st)                              # every rank's reductions into my slab have landed
             if self.tv > 0:
                 self._add_tv(*self._slab_cells)
+            if self._mark:
+                self._mark()
             self._loss_tail(self._slab, result_host)
             L.check(self.lib.plx_adam_step_slab(C.byref(self._slab), st), "plx_adam_step_slab")
+            if self._mark:
+                self._mark()
             self._barrier(1, st)                              # every replica holds the new parameters
             return
         b = self._cur
@@ -571,6 +576,8 @@ class PeerVoxelTrainer(VoxelTrainer):
             self._barrier(0, st)                              # every rank's partial gradient is complete
             if self.tv > 0:
                 self._add_tv(*self._slab_cells)               # my slab of my buffer is read by my exchange kernel only
+            if self._mark:
+                self._mark()
         # the buffer consumed by the PREVIOUS step (its readers passed that step's closing barrier / signalled channel 1,
         # which this step's march waited for) is cleared now, on the side stream, behind this step's exchange kernel: that
         # kernel is NVLink-bound and leaves HBM idle, whereas clearing during the march (measured) slowed the march by as
@@ -585,6 +592,8 @@ class PeerVoxelTrainer(VoxelTrainer):
                 ev.record(self._clear_stream)
             self._cleared[o] = ev
         L.check(self.lib.plx_adam_step_peer(C.byref(peer), st), "plx_adam_step_peer")
+        if self._mark and not self._fused:
+            self._mark()
         if not self._fused:
             self._barrier(1, st)                              # every replica holds the new parameters; peers done reading
         self._dirty = b

@@ -180,6 +180,42 @@ __device__ __forceinline__ float4 tri_interp(const PlxMarch& m, const Geo& g, co
     return lerp4(y_c, y_f, t.f[2]);
 }
 
+// the same interpolation that also reports, for the backward pass, which channels of which corner pass the clip gradient:
+// bit (corner * 4 + channel) of `mask`, corner = (x floor ? 4 : 0) | (y floor ? 2 : 0) | (z floor ? 1 : 0)   (scripts/train.py:146)
+template <bool FAST>
+__device__ __forceinline__ float4 tri_interp_mask(const PlxMarch& m, const Geo& g, const float* __restrict__ grid, const TriGeom& t,
+                                                  uint32_t& mask) {
+    float4 c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {            // all eight gathers in flight before the first use
+        const int ix = (k & 4) ? t.lo[0] : t.hi[0], iy = (k & 2) ? t.lo[1] : t.hi[1], iz = (k & 1) ? t.lo[2] : t.hi[2];
+        c[k] = cell_at<FAST>(m, g, grid, ix, iy, iz, (ix * g.ny + iy) * g.nz + iz);
+    }
+    mask = 0xffffffffu;
+    if (g.clamp) {
+        mask = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            mask |= (c[k].x >= 0.f && c[k].x <= 1.f ? 1u : 0u) << (4 * k);
+            mask |= (c[k].y >= 0.f && c[k].y <= 1.f ? 2u : 0u) << (4 * k);
+            mask |= (c[k].z >= 0.f && c[k].z <= 1.f ? 4u : 0u) << (4 * k);
+            mask |= (c[k].w >= 0.f && c[k].w <= 1.f ? 8u : 0u) << (4 * k);
+            c[k] = clamp4(c[k]);
+        }
+    }
+    const float4 x_cc = lerp4(c[0], c[4], t.f[0]), x_cf = lerp4(c[1], c[5], t.f[0]);
+    const float4 x_fc = lerp4(c[2], c[6], t.f[0]), x_ff = lerp4(c[3], c[7], t.f[0]);
+    return lerp4(lerp4(x_cc, x_fc, t.f[1]), lerp4(x_cf, x_ff, t.f[1]), t.f[2]);
+}
+
+// weight of corner k in the interpolated value = d value / d corner (the product of the three lerp weights)
+__device__ __forceinline__ float tri_weight(const TriGeom& t, int k) {
+    return ((k & 4) ? 1.f - t.f[0] : t.f[0]) * ((k & 2) ? 1.f - t.f[1] : t.f[1]) * ((k & 1) ? 1.f - t.f[2] : t.f[2]);
+}
+__device__ __forceinline__ int tri_corner_lin(const Geo& g, const TriGeom& t, int k) {
+    return (((k & 4) ? t.lo[0] : t.hi[0]) * g.ny + ((k & 2) ? t.lo[1] : t.hi[1])) * g.nz + ((k & 1) ? t.lo[2] : t.hi[2]);
+}
+
 template <int MODE, bool FAST>
 __device__ __forceinline__ Sample lookup(const PlxMarch& m, const Geo& g, const float* __restrict__ grid, const Ray& r,
                                          bool fast_ray, int k, bool valid, bool need_value, float& t, TriGeom& tg) {

@@ -64,7 +64,7 @@ struct RayScratch {
 // FR (fast ray): every coordinate of the ray is in the hoisted-division range — the common case, compiled without any
 // slow-path call in its loops; the FR = false instantiation (coordinates near the ends of the fp32 range, NaN / inf) is the
 // same code on __fdiv_rn and the float bounds test, kept out of line.
-template <bool FAST, bool FR, int SPL, bool PIPE, bool PEER>
+template <int MODE, bool FAST, bool FR, int SPL, bool PIPE, bool PEER>
 __device__ __forceinline__ float train_ray(const PlxRenderTrain& a, const Geo& g, const GradDst<PEER>& dst, const RayScratch& sc,
                                            const Ray& r, const float4 tgt, const int64_t ray, const int lane) {
     constexpr int W = 32 * SPL;
@@ -85,20 +85,39 @@ __device__ __forceinline__ float train_ray(const PlxRenderTrain& a, const Geo& g
     int it = 0;
     // software pipeline: the cells of iteration it+1 are requested before iteration it is composited, so the gather
     // latency (L2 / HBM) overlaps the scans instead of stalling the warp at the first use
+    // nearest: rawn = the raw cell (clamped when consumed), linn = its linear index.  trilinear: rawn = the value interpolated
+    // from the eight (clamped) corners, linn = linear index of the floor corner; tgn / maskn = interpolation geometry and the
+    // corners' clip pass-mask, which only the reverse pass consumes
     float4 rawn[SPL];
     int linn[SPL];
+    TriGeom tgn[MODE == PLX_TRILINEAR ? SPL : 1];
+    uint32_t maskn[MODE == PLX_TRILINEAR ? SPL : 1];
     auto fetch = [&](int i) {
         const int kb = k0 + i * W + lane * SPL;
 #pragma unroll
-        for (int j = 0; j < SPL; ++j) linn[j] = fetch_nearest<FAST>(m, g, a.grid, r, FR, kb + j, kb + j <= k1, rawn[j]);
+        for (int j = 0; j < SPL; ++j) {
+            if (MODE == PLX_NEAREST) {
+                linn[j] = fetch_nearest<FAST>(m, g, a.grid, r, FR, kb + j, kb + j <= k1, rawn[j]);
+            } else {
+                float nx, ny, nz;
+                norm3<FAST>(m, g, r, FR, __fmul_rn(g.delta, (float)(kb + j)), nx, ny, nz);
+                rawn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                linn[j] = -1;
+                if (kb + j <= k1 && tri_geom(g, nx, ny, nz, tgn[j])) {
+                    linn[j] = (tgn[j].lo[0] * g.ny + tgn[j].lo[1]) * g.nz + tgn[j].lo[2];
+                    rawn[j] = tri_interp_mask<FAST>(m, g, a.grid, tgn[j], maskn[j]);
+                }
+            }
+        }
     };
+    constexpr bool CLAMP_ON_USE = MODE == PLX_NEAREST;   // trilinear clamps the corners, not the interpolated value
     if (PIPE && n_it > 0) fetch(0);
     for (; it < n_it; ++it) {
         float4 c[SPL];
         int lin[SPL];
         if (!PIPE) fetch(it);
 #pragma unroll
-        for (int j = 0; j < SPL; ++j) { c[j] = g.clamp ? clamp4(rawn[j]) : rawn[j]; lin[j] = linn[j]; }
+        for (int j = 0; j < SPL; ++j) { c[j] = (CLAMP_ON_USE && g.clamp) ? clamp4(rawn[j]) : rawn[j]; lin[j] = linn[j]; }
         if (PIPE && it + 1 < n_it) fetch(it + 1);
         if (SPL == 1) lc[it * W + lane] = lin[0];
         else *reinterpret_cast<int2*>(lc + it * W + lane * 2) = make_int2(lin[0], lin[SPL - 1]);
@@ -138,7 +157,7 @@ __device__ __forceinline__ float train_ray(const PlxRenderTrain& a, const Geo& g
             float4 c[SPL];
             if (!PIPE) fetch(i2);
 #pragma unroll
-            for (int j = 0; j < SPL; ++j) c[j] = g.clamp ? clamp4(rawn[j]) : rawn[j];
+            for (int j = 0; j < SPL; ++j) c[j] = (CLAMP_ON_USE && g.clamp) ? clamp4(rawn[j]) : rawn[j];
             if (PIPE && i2 + 1 < n_it) fetch(i2 + 1);
             composite_iter<SPL>(c, lane, T2, acc2);
         }
@@ -161,6 +180,7 @@ __device__ __forceinline__ float train_ray(const PlxRenderTrain& a, const Geo& g
     float carry = 0.f;                   // S behind the last visited sample (0: end of ray, or irrelevant behind k*)
     __syncwarp();
     auto refetch = [&](int i) {          // indices back from shared memory, cells requested (L1 / L2 hits mostly)
+        if (MODE == PLX_TRILINEAR) { fetch(i); return; }   // trilinear: recompute geometry + interpolation (the corners hit L1 / L2)
         if (SPL == 1) linn[0] = lc[i * W + lane];
         else { const int2 p = *reinterpret_cast<const int2*>(lc + i * W + lane * 2); linn[0] = p.x; linn[SPL - 1] = p.y; }
 #pragma unroll
@@ -180,7 +200,7 @@ __device__ __forceinline__ float train_ray(const PlxRenderTrain& a, const Geo& g
         for (int j = 0; j < SPL; ++j) {
             lin[j] = linn[j];
             raw[j] = rawn[j];
-            c[j] = g.clamp ? clamp4(raw[j]) : raw[j];
+            c[j] = (CLAMP_ON_USE && g.clamp) ? clamp4(raw[j]) : raw[j];
             v[j] = fmaf(c[j].x, gr.x, fmaf(c[j].y, gr.y, fmaf(c[j].z, gr.z, gr.w)));      // c_k . g_rgb + g_A
         }
         if (PIPE && ib > 0) refetch(ib - 1);     // next iteration's cells in flight during this iteration's scans
@@ -221,9 +241,30 @@ __device__ __forceinline__ float train_ray(const PlxRenderTrain& a, const Geo& g
             const float wgt = c[j].w * Tk;
             d[j] = make_float4(wgt * gr.x, wgt * gr.y, wgt * gr.z, Tk * (v[j] - behind[j]));
             if (full) d[j].w += bom * (1.f / (c[j].w + 1e-4f) + 1.f / (1.f - c[j].w + 1e-4f));   // scripts/train.py:170-177
-            if (g.clamp) { d[j].x *= pass01(raw[j].x); d[j].y *= pass01(raw[j].y); d[j].z *= pass01(raw[j].z); d[j].w *= pass01(raw[j].w); }
+            if (CLAMP_ON_USE && g.clamp) { d[j].x *= pass01(raw[j].x); d[j].y *= pass01(raw[j].y); d[j].z *= pass01(raw[j].z); d[j].w *= pass01(raw[j].w); }
         }
-        if (SPL == 1 && !PEER) {
+        if (MODE == PLX_TRILINEAR) {
+            // d = gradient w.r.t. the interpolated value; every corner receives d * (its lerp weight) through its own clip
+            // pass-mask.  Two samples of a lane that share the floor cell share all eight corners: one reduction per corner.
+            const bool same = SPL == 2 && lin[0] >= 0 && lin[0] == lin[SPL - 1] &&
+                              tgn[0].hi[0] == tgn[SPL - 1].hi[0] && tgn[0].hi[1] == tgn[SPL - 1].hi[1] && tgn[0].hi[2] == tgn[SPL - 1].hi[2];
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                if (lin[j] < 0 || (same && j == SPL - 1)) continue;
+                const bool any = d[j].x != 0.f || d[j].y != 0.f || d[j].z != 0.f || d[j].w != 0.f;
+                const bool any2 = same && (d[SPL - 1].x != 0.f || d[SPL - 1].y != 0.f || d[SPL - 1].z != 0.f || d[SPL - 1].w != 0.f);
+                if (!any && !any2) continue;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float w0 = tri_weight(tgn[j], k), w1 = same ? tri_weight(tgn[SPL - 1], k) : 0.f;
+                    if (w0 == 0.f && w1 == 0.f) continue;
+                    const uint32_t mk = maskn[j] >> (4 * k);
+                    float4 o = make_float4(d[j].x * w0, d[j].y * w0, d[j].z * w0, d[j].w * w0);
+                    if (same) { o.x = fmaf(d[SPL - 1].x, w1, o.x); o.y = fmaf(d[SPL - 1].y, w1, o.y); o.z = fmaf(d[SPL - 1].z, w1, o.z); o.w = fmaf(d[SPL - 1].w, w1, o.w); }
+                    dst.add(tri_corner_lin(g, tgn[j], k), (mk & 1u) ? o.x : 0.f, (mk & 2u) ? o.y : 0.f, (mk & 4u) ? o.z : 0.f, (mk & 8u) ? o.w : 0.f);
+                }
+            }
+        } else if (SPL == 1 && !PEER) {
             warp_scatter_add(dst.local, lin[0] >= 0, (int64_t)lin[0] * 4, d[0].x, d[0].y, d[0].z, d[0].w, lane, dst.pol);
         } else {
             // merge runs inside the lane, then one 16-byte reduction per surviving entry
@@ -263,7 +304,7 @@ __device__ __forceinline__ void setup_ray(const PlxRenderTrain& a, int64_t ray, 
 // the rare ray outside the hoisted-division range (coordinates near the ends of the fp32 range, NaN / inf): the same march on
 // the IEEE division and the float bounds test.  Out of line and self-contained (it rebuilds the ray and the geometry from the
 // kernel argument), so the common path pays neither instructions nor registers nor stack traffic for it.
-template <bool FAST, int SPL, bool PEER>
+template <int MODE, bool FAST, int SPL, bool PEER>
 __device__ __noinline__ float train_ray_slow(const PlxRenderTrain* ap, float* const* peers, int* lc, float* tcs, int64_t ray, int lane) {
     const PlxRenderTrain& a = *ap;
     const Geo g = make_geo(a.march);
@@ -274,11 +315,11 @@ __device__ __noinline__ float train_ray_slow(const PlxRenderTrain* ap, float* co
     Ray r;
     float4 tgt;
     setup_ray(a, ray, r, tgt);
-    return train_ray<FAST, false, SPL, false, PEER>(a, g, dst, sc, r, tgt, ray, lane);
+    return train_ray<MODE, FAST, false, SPL, false, PEER>(a, g, dst, sc, r, tgt, ray, lane);
 }
 
-template <bool FAST, int SPL, bool PIPE, bool PEER>
-__global__ void __launch_bounds__(128, 8) k_render_train(const __grid_constant__ PlxRenderTrain a, int lin_words, int warp_words) {
+template <int MODE, bool FAST, int SPL, bool PIPE, bool PEER>
+__global__ void __launch_bounds__(128, MODE == PLX_NEAREST ? 8 : 5) k_render_train(const __grid_constant__ PlxRenderTrain a, int lin_words, int warp_words) {
     extern __shared__ __align__(16) int s_dyn[];   // per warp (warp_words ints, 16-byte multiple): lin cache [lin_words], then chunk transmittances
     __shared__ float s_loss;
     __shared__ int s_done;
@@ -304,9 +345,9 @@ __global__ void __launch_bounds__(128, 8) k_render_train(const __grid_constant__
             const Geo g = make_geo(m);
             GradDst<PEER> dst;
             dst.local = a.grad_grid; dst.peers = s_peer; dst.owner_mul = a.peer_grad.owner_mul; dst.pol = g.pol_grad;
-            ray_loss = train_ray<FAST, true, SPL, PIPE, PEER>(a, g, dst, sc, r, tgt, ray, lane);
+            ray_loss = train_ray<MODE, FAST, true, SPL, PIPE, PEER>(a, g, dst, sc, r, tgt, ray, lane);
         } else {
-            ray_loss = train_ray_slow<FAST, SPL, PEER>(&a, s_peer, sc.lc, sc.tcs, ray, lane);
+            ray_loss = train_ray_slow<MODE, FAST, SPL, PEER>(&a, s_peer, sc.lc, sc.tcs, ray, lane);
         }
     }
     // ---- loss: shared-memory partial per block, the last warp to finish adds it to the global accumulator; that warp
@@ -330,19 +371,19 @@ size_t render_train_smem(int num_samples, int spl, int wpb) {
 }
 
 bool render_train_supported(const PlxRenderTrain& a) {
-    if (a.march.mode != PLX_NEAREST) return false;
+    if (a.march.mode == PLX_TRILINEAR && !fast_ok(a.march, a.grid)) return false;     // trilinear: contiguous grids only (K1 + K2 otherwise)
     if ((int64_t)a.march.nx * a.march.ny * a.march.nz >= (1ll << 31) / 4) return false;
     return render_train_smem(a.march.num_samples, 2, 1) <= 200 * 1024;
 }
 
-template <bool FAST, int SPL, bool PIPE, bool PEER>
+template <int MODE, bool FAST, int SPL, bool PIPE, bool PEER>
 static cudaError_t launch_train_inst(const PlxRenderTrain& a, unsigned blocks, int wpb, size_t smem, int lin_words, int warp_words,
                                      cudaStream_t st) {
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_render_train<FAST, SPL, PIPE, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_render_train<MODE, FAST, SPL, PIPE, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_render_train<FAST, SPL, PIPE, PEER><<<blocks, wpb * 32, smem, st>>>(a, lin_words, warp_words);
+    k_render_train<MODE, FAST, SPL, PIPE, PEER><<<blocks, wpb * 32, smem, st>>>(a, lin_words, warp_words);
     return cudaGetLastError();
 }
 
@@ -364,7 +405,13 @@ cudaError_t launch_render_train(const PlxRenderTrain& a_in, cudaStream_t st) {
     const bool fast = fast_ok(a.march, a.grid);
     const bool pipe = l2_keep_ok((int64_t)a.march.nx * a.march.ny * a.march.nz);
     const bool peer = a.peer_grad.world > 0;
-#define PLX_TRAIN(F, S, P, E) return launch_train_inst<F, S, P, E>(a, blocks, wpb, smem, lin_words, warp_words, st)
+    if (a.march.mode == PLX_TRILINEAR) {     // 8 gathers per sample: no software pipelining (the corners would not fit the registers)
+        if (peer) { if (spl == 2) return launch_train_inst<PLX_TRILINEAR, true, 2, false, true>(a, blocks, wpb, smem, lin_words, warp_words, st);
+                    return launch_train_inst<PLX_TRILINEAR, true, 1, false, true>(a, blocks, wpb, smem, lin_words, warp_words, st); }
+        if (spl == 2) return launch_train_inst<PLX_TRILINEAR, true, 2, false, false>(a, blocks, wpb, smem, lin_words, warp_words, st);
+        return launch_train_inst<PLX_TRILINEAR, true, 1, false, false>(a, blocks, wpb, smem, lin_words, warp_words, st);
+    }
+#define PLX_TRAIN(F, S, P, E) return launch_train_inst<PLX_NEAREST, F, S, P, E>(a, blocks, wpb, smem, lin_words, warp_words, st)
     if (peer) {                              // validated by the ABI layer: contiguous grid only
         if (spl == 2) { if (pipe) PLX_TRAIN(true, 2, true, true); else PLX_TRAIN(true, 2, false, true); }
         else          { if (pipe) PLX_TRAIN(true, 1, true, true); else PLX_TRAIN(true, 1, false, true); }

@@ -106,6 +106,12 @@ typedef struct PlxRenderFwd {
     float* loss;            /* 1 float accumulator (caller zeroes it), or NULL */
     float grad_scale;       /* 2 / (4 * N_global) for mean-MSE */
     float loss_scale;       /* 1 / (4 * N_global) */
+    /* Optional image epilogue of visulize_3d_in_2d (src/visualization.py:150-154): when image_u8 != NULL the rays are the
+     * u-major even-spread lattice of ONE view (n_rays == image_side^2) and ray (iu, iv) also stores its pixel as uint8
+     * clip(rint(255 * rgba), 0, 255) at image_u8[(iv * image_side + iu) * 4 ..], i.e. the (res,res,4) uint8 array the
+     * reference returns after its reshape + transpose.  `rgba` may then be NULL. */
+    uint8_t* image_u8;
+    int32_t image_side;
 } PlxRenderFwd;
 int plx_render_fwd(const PlxRenderFwd* args, void* stream);
 
@@ -366,9 +372,23 @@ int plx_avgpool3d_bwd(const float* grad_out, const int32_t dims[3], int32_t kern
  */
 int plx_tv_loss(const float* grid, const int32_t dims[3], float tv, float* grad, double* scratch, float* loss_out, void* stream);
 /* the same with the gradient added only for the cells [cell_begin, cell_end) (linear cell indices): the share of a rank that
- * owns that slab of the gradient in the multi-GPU exchange; the loss value is still that of the whole grid */
+ * owns that slab of the gradient in the multi-GPU exchange; the loss value is still that of the whole grid.  `atomic` != 0
+ * adds with 16-byte reductions instead of read-modify-write (other GPUs may be reducing into the same buffer meanwhile).
+ * Multi-GPU callers must run it while the replica is stable: after the march, BEFORE the barrier that releases the peers'
+ * optimiser kernels (those store new parameters into this replica). */
 int plx_tv_loss_range(const float* grid, const int32_t dims[3], float tv, float* grad, int64_t cell_begin, int64_t cell_end,
-                      double* scratch, float* loss_out, void* stream);
+                      int32_t atomic, double* scratch, float* loss_out, void* stream);
+
+/*
+ * visulize_3d_in_2d_fast — src/visualization.py:157-232, the point-splat preview scripts/compare_inference_to_image.py:58
+ * calls: every cell of the contiguous (X,Y,Z,4) grid with alpha > 0.1 is projected through the camera (`pose_host`: 16 floats
+ * of HOST memory, the row-major 4x4 camera-to-world matrix) onto an (xs, ys) image and the point NEAREST to the camera wins
+ * each pixel (what the reference's far-to-near assignment order leaves behind); untouched pixels are 1.  Two passes, no sort:
+ * a 64-bit atomicMin per point on (distance bits, cell index), then a resolve of the winners' RGB.
+ * zbuf: xs * ys uint64 of device scratch; image: (xs, ys, 3) fp32, xs = int(ys * aspect) as the reference computes it.
+ */
+int plx_splat_view(const float* grid, const int32_t dims[3], float points_distance, const float* pose_host, float fov,
+                   int32_t xs, int32_t ys, uint64_t* zbuf, float* image, void* stream);
 
 /*
  * Self-test of the library's exact fp32 helpers: evaluates the hoisted-reciprocal quotient x / y (the march's divisor

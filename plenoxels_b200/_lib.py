@@ -43,7 +43,8 @@ class PlxRays(C.Structure):
 class PlxRenderFwd(C.Structure):
     _fields_ = [("march", PlxMarch), ("rays", PlxRays), ("grid", c_void), ("rgba", c_void), ("depth", c_void),
                 ("count", c_void), ("sample_index", c_void), ("tcarry", c_void), ("targets", c_void),
-                ("grad_rgba", c_void), ("loss", c_void), ("grad_scale", C.c_float), ("loss_scale", C.c_float)]
+                ("grad_rgba", c_void), ("loss", c_void), ("grad_scale", C.c_float), ("loss_scale", C.c_float),
+                ("image_u8", c_void), ("image_side", C.c_int32)]
 
 
 class PlxRenderBwd(C.Structure):
@@ -145,8 +146,10 @@ PROTOTYPES = {
     "plx_avgpool3d_fwd": (C.c_int, [c_void, C.POINTER(C.c_int32), C.c_int32, C.c_int32, c_void, c_void, c_void, c_void]),
     "plx_avgpool3d_bwd": (C.c_int, [c_void, C.POINTER(C.c_int32), C.c_int32, C.c_int32, c_void, c_void, c_void, c_void]),
     "plx_tv_loss": (C.c_int, [c_void, C.POINTER(C.c_int32), C.c_float, c_void, c_void, c_void, c_void]),
-    "plx_tv_loss_range": (C.c_int, [c_void, C.POINTER(C.c_int32), C.c_float, c_void, C.c_int64, C.c_int64, c_void, c_void,
-                                    c_void]),
+    "plx_tv_loss_range": (C.c_int, [c_void, C.POINTER(C.c_int32), C.c_float, c_void, C.c_int64, C.c_int64, C.c_int32, c_void,
+                                    c_void, c_void]),
+    "plx_splat_view": (C.c_int, [c_void, C.POINTER(C.c_int32), C.c_float, C.POINTER(C.c_float), C.c_float, C.c_int32, C.c_int32,
+                                 c_void, c_void, c_void]),
     "plx_selftest_arith": (C.c_int, [C.c_float, C.c_uint64, C.c_uint64, c_void, c_void]),
     "plx_train_step": (C.c_int, [C.POINTER(PlxTrainStep), C.c_int32, c_void]),
     "plx_train_step_host": (C.c_int, [C.POINTER(PlxTrainStep), c_void, c_void, C.c_int32, c_void]),

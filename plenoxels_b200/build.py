@@ -12,7 +12,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libplenoxel_b200.so")
-SOURCES = ["plx_render.cu", "plx_train.cu", "plx_adam.cu", "plx_pool.cu", "plx_eager.cu", "plx_abi.cu"]
+SOURCES = ["plx_render.cu", "plx_train.cu", "plx_adam.cu", "plx_pool.cu", "plx_eager.cu", "plx_view.cu", "plx_abi.cu"]
 HEADERS = ["plx_device.cuh", "plx_march.cuh", "plx_raygen.cuh", "plx_launch.h", os.path.join("..", "..", "include", "plenoxel_abi.h")]
 
 NVCC_FLAGS = [

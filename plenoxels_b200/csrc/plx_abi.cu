@@ -61,8 +61,14 @@ int plx_render_fwd(const PlxRenderFwd* a, void* stream) {
     int rc;
     if ((rc = check_march(a->march, a->grid)) != PLX_OK) return rc;
     if ((rc = check_rays(a->rays)) != PLX_OK) return rc;
-    if (a->rays.n_rays > 0 && !a->rgba) return fail(PLX_E_NULL, "rgba is NULL");
+    if (a->rays.n_rays > 0 && !a->rgba && !a->image_u8) return fail(PLX_E_NULL, "rgba is NULL");
     if ((uintptr_t)a->rgba % 16) return fail(PLX_E_ALIGN, "rgba must be 16-byte aligned");
+    if (a->image_u8) {
+        if (a->image_side <= 0 || (int64_t)a->image_side * a->image_side != a->rays.n_rays)
+            return fail(PLX_E_SHAPE, "image epilogue: n_rays (%lld) must equal image_side^2 (%d^2)", (long long)a->rays.n_rays, a->image_side);
+        if ((uintptr_t)a->image_u8 % 4) return fail(PLX_E_ALIGN, "image_u8 must be 4-byte aligned");
+        if (a->targets && !a->rgba) return fail(PLX_E_NULL, "rgba is required with targets");
+    }
     if (a->targets) {
         if (!a->grad_rgba) return fail(PLX_E_NULL, "grad_rgba is required with targets");
         if ((uintptr_t)a->targets % 16 || (uintptr_t)a->grad_rgba % 16) return fail(PLX_E_ALIGN, "targets/grad_rgba must be 16-byte aligned");
@@ -377,18 +383,29 @@ int plx_avgpool3d_bwd(const float* grad_out, const int32_t dims[3], int32_t kern
 }
 
 int plx_tv_loss_range(const float* grid, const int32_t dims[3], float tv, float* grad, int64_t cell_begin, int64_t cell_end,
-                      double* scratch, float* loss_out, void* stream) {
+                      int32_t atomic, double* scratch, float* loss_out, void* stream) {
     if (!dims || !grid || !scratch) return fail(PLX_E_NULL, "grid/dims/scratch is NULL");
     if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return fail(PLX_E_SHAPE, "grid dims must be positive");
     if ((uintptr_t)grid % 16 || (uintptr_t)grad % 16 || (uintptr_t)scratch % 8) return fail(PLX_E_ALIGN, "tv buffers are misaligned");
     const int64_t n = (int64_t)dims[0] * dims[1] * dims[2];
     if (cell_begin < 0 || cell_end < cell_begin || cell_end > n) return fail(PLX_E_SHAPE, "cell range outside the grid");
-    return cuda_result(plx::launch_tv_loss(grid, dims, tv, grad, cell_begin, cell_end, scratch, loss_out, (cudaStream_t)stream), "plx_tv_loss");
+    return cuda_result(plx::launch_tv_loss(grid, dims, tv, grad, cell_begin, cell_end, atomic != 0, scratch, loss_out, (cudaStream_t)stream), "plx_tv_loss");
 }
 
 int plx_tv_loss(const float* grid, const int32_t dims[3], float tv, float* grad, double* scratch, float* loss_out, void* stream) {
     if (!dims) return fail(PLX_E_NULL, "grid/dims/scratch is NULL");
-    return plx_tv_loss_range(grid, dims, tv, grad, 0, (int64_t)dims[0] * dims[1] * dims[2], scratch, loss_out, stream);
+    return plx_tv_loss_range(grid, dims, tv, grad, 0, (int64_t)dims[0] * dims[1] * dims[2], 0, scratch, loss_out, stream);
+}
+
+int plx_splat_view(const float* grid, const int32_t dims[3], float points_distance, const float* pose_host, float fov,
+                   int32_t xs, int32_t ys, uint64_t* zbuf, float* image, void* stream) {
+    if (!grid || !dims || !pose_host || !zbuf || !image) return fail(PLX_E_NULL, "splat: grid/dims/pose/zbuf/image is NULL");
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return fail(PLX_E_SHAPE, "grid dims must be positive");
+    if ((int64_t)dims[0] * dims[1] * dims[2] > 0xffffffffLL) return fail(PLX_E_SHAPE, "grid too large for 32-bit cell indices");
+    if (xs <= 0 || ys <= 0) return fail(PLX_E_SHAPE, "image size must be positive (%d x %d)", xs, ys);
+    if ((uintptr_t)grid % 16 || (uintptr_t)zbuf % 8) return fail(PLX_E_ALIGN, "splat buffers are misaligned");
+    return cuda_result(plx::launch_splat_view(grid, dims, points_distance, pose_host, fov, xs, ys, (unsigned long long*)zbuf, image,
+                                              (cudaStream_t)stream), "plx_splat_view");
 }
 
 int plx_selftest_arith(float y, uint64_t n, uint64_t seed, uint64_t* mismatches, void* stream) {

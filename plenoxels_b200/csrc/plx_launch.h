@@ -49,7 +49,9 @@ cudaError_t launch_avgpool3d_fwd(const float* in, const int32_t* dims, int k, in
 cudaError_t launch_avgpool3d_bwd(const float* gout, const int32_t* dims, int k, int s, float* tmp2, float* tmp1, float* gin,
                                  cudaStream_t st);
 cudaError_t launch_tv_loss(const float* grid, const int32_t* dims, float tv, float* grad, int64_t cell_begin, int64_t cell_end,
-                           double* scratch, float* loss_out, cudaStream_t st);
+                           bool atomic, double* scratch, float* loss_out, cudaStream_t st);
+cudaError_t launch_splat_view(const float* grid, const int32_t* dims, float pd, const float* pose16, float fov, int xs, int ys,
+                              unsigned long long* zbuf, float* image, cudaStream_t st);
 cudaError_t launch_peer_barrier(int32_t* const* flags, int rank, int world, int channel, int epoch, const PlxPeerError& err,
                                 cudaStream_t st);
 

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) k_tv_sumsq(const float4* __restrict__ g, 
 
 __global__ void __launch_bounds__(256) k_tv_grad(const float4* __restrict__ g, int X, int Y, int Z, const double* __restrict__ sum,
                                                  float tv, float4* __restrict__ grad, int64_t cell_begin, int64_t cell_end,
-                                                 float* __restrict__ loss_out) {
+                                                 bool atomic, float* __restrict__ loss_out) {
     const double S = *sum;
     if (blockIdx.x == 0 && threadIdx.x == 0 && loss_out) *loss_out = tv * (float)sqrt(S);
     if (!(S > 0.0) || !grad) return;               // the reference's gradient is 0/0 here; we add nothing
@@ -122,20 +122,24 @@ __global__ void __launch_bounds__(256) k_tv_grad(const float4* __restrict__ g, i
         if (y > 0)     towards(__ldg(g + e - Z));
         if (x + 1 < X) towards(__ldg(g + e + sx));
         if (x > 0)     towards(__ldg(g + e - sx));
-        float4 o = grad[e];
-        o.x = fmaf(scale, d.x, o.x); o.y = fmaf(scale, d.y, o.y); o.z = fmaf(scale, d.z, o.z); o.w = fmaf(scale, d.w, o.w);
-        grad[e] = o;
+        if (atomic) {                            // other GPUs may be reducing into the same cells right now (push exchange)
+            red_add_v4(reinterpret_cast<float*>(grad + e), scale * d.x, scale * d.y, scale * d.z, scale * d.w);
+        } else {
+            float4 o = grad[e];
+            o.x = fmaf(scale, d.x, o.x); o.y = fmaf(scale, d.y, o.y); o.z = fmaf(scale, d.z, o.z); o.w = fmaf(scale, d.w, o.w);
+            grad[e] = o;
+        }
     }
 }
 
 cudaError_t launch_tv_loss(const float* grid, const int32_t* dims, float tv, float* grad, int64_t cell_begin, int64_t cell_end,
-                           double* scratch, float* loss_out, cudaStream_t st) {
+                           bool atomic, double* scratch, float* loss_out, cudaStream_t st) {
     const int X = dims[0], Y = dims[1], Z = dims[2];
     const int64_t n = (int64_t)X * Y * Z;
     cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double), st);
     if (e != cudaSuccess) return e;
     k_tv_sumsq<<<pool_blocks(n), 256, 0, st>>>((const float4*)grid, X, Y, Z, scratch);
-    k_tv_grad<<<pool_blocks(cell_end - cell_begin), 256, 0, st>>>((const float4*)grid, X, Y, Z, scratch, tv, (float4*)grad, cell_begin, cell_end, loss_out);
+    k_tv_grad<<<pool_blocks(cell_end - cell_begin), 256, 0, st>>>((const float4*)grid, X, Y, Z, scratch, tv, (float4*)grad, cell_begin, cell_end, atomic, loss_out);
     return cudaGetLastError();
 }
 

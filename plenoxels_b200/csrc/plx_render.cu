@@ -18,6 +18,16 @@
 
 namespace plx {
 
+// image epilogue of visulize_3d_in_2d (src/visualization.py:150-154): (pix * 255).round().clip(0, 255).astype(uint8), stored
+// transposed (ray (iu, iv) of the u-major lattice -> row iv, column iu)
+__device__ __forceinline__ void store_pixel_u8(const PlxRenderFwd& a, int64_t ray, float r, float g, float b, float al) {
+    const int side = a.image_side;
+    const int iu = (int)(ray / side), iv = (int)(ray % side);
+    auto q = [](float v) { return (unsigned)fminf(fmaxf(rintf(__fmul_rn(v, 255.f)), 0.f), 255.f); };
+    const unsigned px = q(r) | (q(g) << 8) | (q(b) << 16) | (q(al) << 24);
+    reinterpret_cast<unsigned*>(a.image_u8)[(int64_t)iv * side + iu] = px;
+}
+
 // =================================================================================================================
 // K1 — forward
 // =================================================================================================================
@@ -97,7 +107,8 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) k_render_fwd(const P
         if (a.depth) ad = warp_sum(ad);
         if (DBG && a.count) cnt = warp_sum_int(cnt);
         if (lane == 0) {
-            reinterpret_cast<float4*>(a.rgba)[ray] = make_float4(ar, ag, ab, aa);
+            if (a.rgba) reinterpret_cast<float4*>(a.rgba)[ray] = make_float4(ar, ag, ab, aa);
+            if (a.image_u8) store_pixel_u8(a, ray, ar, ag, ab, aa);
             if (a.depth) a.depth[ray] = ad;
             if (DBG && a.count) a.count[ray] = cnt;
             if (a.targets) {                 // mean-MSE over N*4 incl. alpha, scripts/train.py:156
@@ -154,7 +165,8 @@ __global__ void __launch_bounds__(128) k_render_fwd_packet(const PlxRenderFwd a)
             T *= 1.f - c[j].w;
         }
     }
-    reinterpret_cast<float4*>(a.rgba)[ray] = make_float4(ar, ag, ab, aa);
+    if (a.rgba) reinterpret_cast<float4*>(a.rgba)[ray] = make_float4(ar, ag, ab, aa);
+    if (a.image_u8) store_pixel_u8(a, ray, ar, ag, ab, aa);
     if (a.depth) a.depth[ray] = ad;
 }
 

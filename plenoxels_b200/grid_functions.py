@@ -22,7 +22,8 @@ class GridCoords(torch.Tensor):
     exactly as `generate_grid` does (fl32(i - ceil(s/2) + 1) * fl32(pd)), and it survives the two things the reference
     does to these tensors: positive-step slicing of the three leading axes (`grid_grid[start::stride, ...]`,
     scripts/train.py:114-115) and `reshape(-1, 3)` (:116, :122).  Any other operation returns a plain tensor and the
-    reduction is then done for real.
+    reduction is then done for real; an operation that WRITES into a GridCoords (in-place / `out=` / slice assignment)
+    drops the cached origin of every GridCoords argument, because views may share the edited storage.
     """
 
     @staticmethod
@@ -31,9 +32,24 @@ class GridCoords(torch.Tensor):
         out._plx = meta
         return out
 
+    @staticmethod
+    def _writes(func, kwargs) -> bool:
+        name = getattr(func, "__name__", "")
+        if kwargs.get("out") is not None or name in ("__setitem__", "__set__", "set_", "resize_"):
+            return True
+        return (name.endswith("_") and not name.endswith("__")) or (name.startswith("__i") and name.endswith("__") and name != "__index__"
+                                                                     and name != "__init__" and name != "__iter__" and name != "__invert__")
+
     @classmethod
     def __torch_function__(cls, func, types, args=(), kwargs=None):
         kwargs = kwargs or {}
+        if cls._writes(func, kwargs):
+            for a in list(args) + ([kwargs["out"]] if isinstance(kwargs.get("out"), torch.Tensor) else []):
+                if isinstance(a, GridCoords):
+                    meta = a.__dict__.get("_plx")
+                    if meta is not None:
+                        meta["pd"] = -1.0          # shared by every view derived from the same tensor: all of them fall back
+                    a.__dict__.pop("_plx", None)
         with torch._C.DisableTorchFunctionSubclass():
             out = func(*args, **kwargs)
         if not isinstance(out, torch.Tensor):
@@ -57,14 +73,14 @@ class GridCoords(torch.Tensor):
                     start[a] += b * step[a]
                     step[a] *= st
                 if out.numel():
-                    return GridCoords.wrap(out, dict(meta, start=tuple(start), step=tuple(step)))
+                    return GridCoords.wrap(out, dict(meta, start=tuple(start), step=tuple(step), root=meta.get("root", meta)))
         return out
 
 
 def coords_origin(grid_indices: torch.Tensor):
     """(gx, gy, gz) = grid_indices.min(0)[0] as python floats holding fp32 values."""
     meta = getattr(grid_indices, "_plx", None) if isinstance(grid_indices, GridCoords) else None
-    if meta is not None and meta["pd"] > 0:
+    if meta is not None and meta["pd"] > 0 and meta.get("root", meta)["pd"] > 0:
         return ops.grid_origin(meta["dims"], meta["pd"], meta["start"])
     flat = grid_indices.as_subclass(torch.Tensor).reshape(-1, grid_indices.shape[-1])
     return tuple(float(x) for x in flat.min(0)[0].detach().cpu().tolist())

@@ -92,6 +92,25 @@ def render_rays(grid, origins, dirs, num_samples, delta_step, gmin, points_dista
                              bool(return_depth), bool(return_count), float(beta_over_m), bool(coherent))
 
 
+def render_image_u8(grid, pose, fov, side, num_samples, delta_step, gmin, points_distance, mode="nearest", clamp=False):
+    """The (side, side, 4) uint8 image `visulize_3d_in_2d` returns (src/visualization.py:111-154) for ONE camera `pose` (1,4,4):
+    even-spread lattice rays (ray generation kernel), coherent ray-packet march, and the x255 / round-half-even / clip / uint8 /
+    transpose epilogue written by the march kernel itself — two launches, no (N,4) float image, nothing on the host."""
+    dev = L.require_cuda(grid, pose)
+    lib = L.load()
+    pose = pose.reshape(-1, 4, 4)[:1].contiguous().float()
+    n = int(side) * int(side)
+    dirs, _ = generate_rays(None, pose, fov, uv=None, rays_per_cam=n, want_targets=False)
+    img = torch.empty((int(side), int(side), 4), dtype=torch.uint8, device=dev)
+    a = L.PlxRenderFwd()
+    a.march = L.make_march(grid, num_samples, delta_step, gmin, points_distance, mode, clamp, coherent=True)
+    a.rays = L.make_rays(pose[:, :3, 3], dirs, n)
+    a.grid, a.image_u8, a.image_side = grid.data_ptr(), img.data_ptr(), int(side)
+    with torch.cuda.device(dev):
+        L.check(lib.plx_render_fwd(C.byref(a), L.stream_ptr(dev)), "plx_render_fwd(image)")
+    return img
+
+
 def sample_indices(grid, origins, dirs, num_samples, delta_step, gmin, points_distance, mode="nearest",
                    rays_per_origin=1):
     """Parity/debug dump: (N,S) int32 linear cell index ((ix*Y+iy)*Z+iz) of every sample, -1 when out of bounds,
@@ -113,8 +132,8 @@ def sample_indices(grid, origins, dirs, num_samples, delta_step, gmin, points_di
 
 def render_train(grid, grad_grid, num_samples, delta_step, gmin, points_distance, *, origins=None, dirs=None,
                  targets=None, rays_per_origin=1, imgs=None, poses=None, fov=None, uv=None, n_rays_global=None,
-                 beta_over_m=0.0, clamp=True):
-    """K12, the fused training march (nearest lookup): forward + mean-MSE + backward in one kernel; the gradient is
+                 beta_over_m=0.0, clamp=True, mode="nearest"):
+    """K12, the fused training march (nearest or trilinear lookup): forward + mean-MSE + backward in one kernel; the gradient is
     ACCUMULATED into `grad_grid` (contiguous (X,Y,Z,4)).  Rays are either given (`origins`, `dirs`, `targets`) or
     generated in the kernel from (`imgs`, `poses`, `fov`, `uv` (C,R,2)).  Returns (rgba (N,4), loss (1,) device tensor)
     = the pixels and mean((rgba - targets)^2) of scripts/train.py:151-156.  `imgs` may be fp32 in [0,1] or uint8 (the
@@ -122,7 +141,7 @@ def render_train(grid, grad_grid, num_samples, delta_step, gmin, points_distance
     dev = L.require_cuda(grid, grad_grid, origins, dirs, targets, imgs, poses, uv)
     lib = L.load()
     a = L.PlxRenderTrain()
-    a.march = L.make_march(grid, num_samples, delta_step, gmin, points_distance, "nearest", clamp)
+    a.march = L.make_march(grid, num_samples, delta_step, gmin, points_distance, mode, clamp)
     keep = []
     if uv is not None:
         uv = uv.contiguous().float()

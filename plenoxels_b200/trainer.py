@@ -157,12 +157,12 @@ class VoxelTrainer:
                     "plx_train_step(render)")
         self._args.uv = self.uv.data_ptr()
 
-    def _add_tv(self, begin_cell: int | None = None, end_cell: int | None = None) -> None:
-        """tv * tv_loss gradient into the (already exchanged) gradient buffer — of the whole grid, or of the slab of cells
-        this rank's optimiser step consumes.  Every replica computes the same loss value."""
+    def _add_tv(self, begin_cell: int | None = None, end_cell: int | None = None, atomic: bool = False) -> None:
+        """tv * tv_loss gradient into the gradient buffer — of the whole grid, or of the slab of cells this rank's optimiser
+        step consumes (`atomic`: peers may be reducing into the buffer meanwhile).  Every replica computes the same loss."""
         n_cells = self.grid.numel() // 4
         b, e = (0, n_cells) if begin_cell is None else (begin_cell, end_cell)
-        L.check(self.lib.plx_tv_loss_range(self.grid.data_ptr(), self._dims, self.tv, self.grad.data_ptr(), b, e,
+        L.check(self.lib.plx_tv_loss_range(self.grid.data_ptr(), self._dims, self.tv, self.grad.data_ptr(), b, e, int(atomic),
                                            self._tv_scratch.data_ptr(), self.tv_loss.data_ptr(), L.stream_ptr(self.device)),
                 "plx_tv_loss")
 
@@ -537,9 +537,18 @@ class PeerVoxelTrainer(VoxelTrainer):
             sy.signal_channel, sy.signal_epoch = 0, e
             self._args.render_sync = C.pointer(sy)
 
+    def _tv_own_slab(self) -> None:
+        """TV term of the cells this rank owns, added right behind the march: the replica is stable until every rank has
+        entered the barrier that follows (afterwards the peers' optimiser kernels store new parameters into it, and the
+        stencil must not read a mix of old and new values); the owner's partial sum carries the term once."""
+        if self.tv > 0:
+            self._add_tv(*self._slab_cells, atomic=True)
+
     def render_phase(self, uv=None) -> None:
         self._select_buffer()
         super().render_phase(uv)
+        with torch.cuda.device(self.device):
+            self._tv_own_slab()
 
     def _loss_tail(self, a, result_host) -> None:
         s = self.step_count & 1
@@ -554,8 +563,6 @@ class PeerVoxelTrainer(VoxelTrainer):
         self._epoch += 1
         if self.exchange == "push":
             self._barrier(0, st)                              # every rank's reductions into my slab have landed
-            if self.tv > 0:
-                self._add_tv(*self._slab_cells)
             if self._mark:
                 self._mark()
             self._loss_tail(self._slab, result_host)
@@ -574,8 +581,6 @@ class PeerVoxelTrainer(VoxelTrainer):
             sy.signal_channel, sy.signal_epoch = 1, self._epoch
         else:
             self._barrier(0, st)                              # every rank's partial gradient is complete
-            if self.tv > 0:
-                self._add_tv(*self._slab_cells)               # my slab of my buffer is read by my exchange kernel only
             if self._mark:
                 self._mark()
         # the buffer consumed by the PREVIOUS step (its readers passed that step's closing barrier / signalled channel 1,
@@ -629,6 +634,7 @@ class PeerVoxelTrainer(VoxelTrainer):
         with torch.cuda.device(self.device):
             L.check(self.lib.plx_train_step_host(C.byref(self._args), uv_host.data_ptr(), None, L.PLX_STEP_RENDER, st),
                     "plx_train_step_host(render)")
+            self._tv_own_slab()
             self._exchange_and_update(st, self.result_host.data_ptr())
         return self.loss_host
 

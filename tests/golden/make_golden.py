@@ -30,6 +30,10 @@ from plenoxels_b200 import synth      # noqa: E402
 
 assert rgf.__file__.startswith(REF)
 
+# matplotlib / plotly are GUI-only imports of src/visualization.py and absent from this image: empty stand-ins
+GUI_STUBS = ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.cm", "mpl_toolkits", "mpl_toolkits.mplot3d", "plotly",
+             "plotly.graph_objects", "plotly.io", "plotly.express", "plotly.graph_objs")
+
 
 def reference_step(grid, pd, poses, fov, imgs, R, S, delta, uv, mode, even_spread=False):
     """scripts/train.py:130-157 + :181 with the reference's own functions; uv injected in place of torch.rand."""
@@ -131,7 +135,7 @@ def make_tv(name):
 def make_inference(name):
     """visulize_3d_in_2d (src/visualization.py:111-154): ray-marched uint8 image of one camera, with the alpha threshold.
     matplotlib / plotly are GUI-only imports of that module and absent here: empty stand-ins are injected."""
-    for mod in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.cm", "mpl_toolkits", "mpl_toolkits.mplot3d", "plotly", "plotly.graph_objects", "plotly.io", "plotly.express", "plotly.graph_objs"):
+    for mod in GUI_STUBS:
         sys.modules.setdefault(mod, types.ModuleType(mod))
     import src.visualization as rvz
     G, res, S = 24, 12, 80
@@ -146,6 +150,52 @@ def make_inference(name):
                         pd=np.float64(pd), delta=np.float64(6.0 / S), S=np.int64(S), res=np.int64(res), threshold=np.float64(0.2),
                         fov=np.float64(synth.CAMERA_ANGLE_X), image=img)
     print(name, img.shape, img.dtype, int(img[..., 3].max()))
+
+
+def make_splat(name):
+    """visulize_3d_in_2d_fast (src/visualization.py:157-232), the CPU point-splat preview scripts/compare_inference_to_image.py:58
+    calls: the (xs, ys, 3) float64 image of one camera over a clipped, thresholded grid."""
+    for mod in GUI_STUBS:
+        sys.modules.setdefault(mod, types.ModuleType(mod))
+    import src.visualization as rvz
+    G, size_y = 40, 96
+    pd = synth.GRID_EXTENT / G
+    grid = synth.ball_grid(G, seed=41).clip(0.0, 1.0)
+    grid[..., 3][grid[..., 3] < 0.2] = 0.0
+    pose = synth.lookat_poses(7)[3]
+    img = rvz.visulize_3d_in_2d_fast(grid, pd, pose, synth.CAMERA_ANGLE_X, size_y)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), grid=grid.numpy(), pose=pose.numpy(), pd=np.float64(pd),
+                        fov=np.float64(synth.CAMERA_ANGLE_X), size_y=np.int64(size_y), image=img)
+    print(name, img.shape, img.dtype, "painted pixels", int((img != 1.0).any(-1).sum()))
+
+
+def make_signatures(name):
+    """The drop-in boundary frozen as text: `inspect.signature` of every reference function the scripts import by
+    name, read from the reference's source with ast (importing src.visualization would need the GUI toolkits)."""
+    import ast
+    import json
+    wanted = {
+        "src/grid_functions.py": ["generate_grid", "get_nearest_voxels", "average_pool3d_grid", "convolve_grid_to_remove_noise",
+                                  "trilinear_interpolation", "get_grid_points_indices", "find_out_of_bound", "fix_out_of_bounds",
+                                  "collect_cell_information_via_indices"],
+        "src/ray_sampling.py": ["sample_camera_rays_batched", "normalize_samples_for_indecies", "compute_alpha_weighted_pixels",
+                                "generate_rays_batched"],
+        "src/data_processing.py": ["load_data", "load_image_data_from_path", "load_image_data", "read_data", "get_data_from_index"],
+        "src/visualization.py": ["visulize_3d_in_2d", "visulize_3d_in_2d_fast", "visualize_rays_3d"],
+        "scripts/train.py": ["fit"],
+    }
+    out = {}
+    for rel, names in wanted.items():
+        tree = ast.parse(open(os.path.join(REF, rel)).read())
+        for node in tree.body:
+            if isinstance(node, ast.FunctionDef) and node.name in names:
+                a = node.args
+                pos = [x.arg for x in a.posonlyargs + a.args]
+                defaults = [None] * (len(pos) - len(a.defaults)) + [ast.unparse(d) for d in a.defaults]
+                out[f"{rel[:-3].replace('/', '.')}.{node.name}"] = [[n, d] for n, d in zip(pos, defaults)]
+    with open(os.path.join(HERE, f"{name}.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print(name, len(out), "functions")
 
 
 def sha(a: np.ndarray) -> str:
@@ -180,6 +230,8 @@ if __name__ == "__main__":
         make_fullsize("full_c3", "c3")
         sys.exit(0)
     make_inference("inference_g24")
+    make_splat("splat_g40")
+    make_signatures("signatures")
     make_tv("tv_g12")
     make_case("nn_dense_g24", 24, 2, 8, 64, 48, 6.0 / 48, "dense", "nearest", seed=11)
     make_case("nn_ball_g32", 32, 3, 12, 48, 96, 6.0 / 96, "ball", "nearest", seed=12)

@@ -1,6 +1,8 @@
 """The reference-named Python surface (src/*.py -> plenoxels_b200/*.py): host-side logic on CPU, and on the GPU the loop
 body of the reference's fit() (scripts/train.py:104-191) written with the drop-in functions + torch.optim.Adam, checked
 against the torch-CPU port of the reference."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -24,6 +26,49 @@ def test_src_shim_exposes_the_reference_names():
     import src.visualization as vz
     assert callable(dp.load_data) and callable(dp.load_image_data_from_path)
     assert callable(vz.visulize_3d_in_2d) and callable(vz.visulize_3d_in_2d_fast)
+
+
+def test_boundary_signatures_equal_the_references():
+    """the drop-in boundary is the set of Python signatures the unmodified scripts import by name.  Parameter
+    names, order and defaults of every one of them against tests/golden/signatures.json (read off the reference's source with
+    ast by tests/golden/make_golden.py).  `fit` may only ADD trailing parameters that have defaults."""
+    import importlib
+    import inspect
+    import json
+    table = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "signatures.json")))
+    assert len(table) >= 20
+    for qual, want in table.items():
+        mod_name, fn_name = qual.rsplit(".", 1)
+        mod = importlib.import_module("plenoxels_b200.fit" if mod_name == "scripts.train" else mod_name)
+        params = list(inspect.signature(getattr(mod, fn_name)).parameters.values())
+        got = [[p.name, None if p.default is inspect.Parameter.empty else repr(p.default)] for p in params]
+        norm = lambda d: None if d is None else d.replace('"', "'")
+        want_n = [[n, norm(d)] for n, d in want]
+        got_n = [[n, norm(d)] for n, d in got]
+        if fn_name == "fit":
+            assert got_n[:len(want_n)] == want_n and all(d is not None for _, d in got_n[len(want_n):]), qual
+        else:
+            assert got_n == want_n, (qual, got_n, want_n)
+
+
+def test_grid_coords_metadata_does_not_survive_in_place_edits():
+    """GridCoords caches the grid origin; an in-place edit of the coordinates must drop the cache so that
+    coords_origin() falls back to the real reduction instead of returning a stale origin."""
+    import src.grid_functions as gf
+    coords, _, _, grid_grid = gf.generate_grid(6, 6, 6, points_distance=0.5, info_size=4, device="cpu")
+    from plenoxels_b200.grid_functions import coords_origin
+    want = tuple(float(x) for x in coords.as_subclass(torch.Tensor).min(0)[0])
+    assert coords_origin(coords) == want
+    for edit in (lambda t: t.add_(5.0), lambda t: t.mul_(2.0), lambda t: t.__iadd__(1.0), lambda t: t.__setitem__(0, 9.0),
+                 lambda t: t.copy_(torch.zeros_like(t.as_subclass(torch.Tensor)))):
+        c = coords.clone()
+        assert coords_origin(c) == want                       # clone keeps the (still valid) cache
+        edit(c)
+        real = tuple(float(x) for x in c.as_subclass(torch.Tensor).reshape(-1, 3).min(0)[0])
+        assert coords_origin(c) == real, "stale cached origin after an in-place edit"
+    sl = grid_grid[1::2]
+    sl += 1.0
+    assert coords_origin(sl.reshape(-1, 3)) == tuple(float(x) for x in sl.as_subclass(torch.Tensor).reshape(-1, 3).min(0)[0])
 
 
 @pytest.mark.parametrize("G,pd", [(8, 0.1), (93, 0.0125), (20, 0.05)])

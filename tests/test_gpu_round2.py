@@ -1,0 +1,225 @@
+"""Round-2 parity: trilinear inside the fused training march, full-size checks of BASELINE configs #2 (trilinear) and #4
+(512^3 inference, strided rays) against the C oracle, the uint8 image epilogue and the GPU point splat against what the
+UNMODIFIED reference produced (tests/golden), uint8 target images, and the trainer's step() / step_host() agreement with the
+TV term.  Everything goes through the C ABI (plenoxels_b200.ops / trainer)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle as co
+from plenoxels_b200 import _lib as L, ops, synth
+from plenoxels_b200.trainer import VoxelTrainer
+from tests.helpers import Case, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-5                                      # BASELINE.json north_star: RGB, depth, loss, grid gradients within 1e-5 relative
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ------------------------------------------------------------------------------------------------ trilinear in the fused march
+@pytest.mark.parametrize("G,C,H,R,S,kind,beta", [(24, 2, 8, 48, 64, "ball", 0.0), (16, 2, 8, 32, 40, "dense", 0.0),
+                                                 (20, 3, 8, 64, 200, "soft", 0.0), (24, 2, 8, 48, 160, "ball", 5e-3)])
+def test_fused_trilinear_march_matches_oracle_and_unfused_kernels(plx_lib, G, C, H, R, S, kind, beta):
+    """K12 in trilinear mode (eight-corner gather, corner pass-mask bits, in-lane merge of samples sharing a floor cell,
+    two-sided early termination) against the numpy oracle (src/grid_functions.py:7-44, :220-246 + scripts/train.py:146-157)
+    and against the separate K1 + K2 kernels."""
+    cs = Case(G, C, H, R, S, 6.0 / S, kind)
+    d = cs.cuda()
+    gg = torch.zeros_like(d["grid"])
+    bom = beta / (cs.N * S)
+    rgba, loss = ops.render_train(d["grid"], gg, S, cs.delta, cs.gmin, cs.pd, imgs=d["imgs"], poses=d["poses"], fov=cs.fov,
+                                  uv=d["uv"], mode="trilinear", beta_over_m=bom)
+    orgba, odepth, ocount, _ = cs.oracle_forward("trilinear")
+    from oracle import plenoxel_oracle as po
+    oloss, gpix = po.mse_loss(orgba, cs.targets)
+    ograd = cs.oracle_backward(gpix, "trilinear", beta=beta)
+    assert rel_err(rgba.cpu().numpy(), orgba) <= TOL
+    assert abs(float(loss) - oloss) <= TOL * oloss
+    assert rel_err(gg.cpu().numpy(), ograd) <= TOL
+    # the unfused pair (autograd path) on the same rays
+    g2 = d["grid"].clone().requires_grad_(True)
+    pix = ops.render_rays(g2, d["origins"], d["dirs"], S, cs.delta, cs.gmin, cs.pd, mode="trilinear", rays_per_origin=R, beta_over_m=bom)
+    torch.nn.functional.mse_loss(pix, d["targets"]).backward()
+    assert rel_err(rgba.cpu().numpy(), pix.detach().cpu().numpy()) <= 2e-6
+    assert rel_err(gg.cpu().numpy(), g2.grad.cpu().numpy()) <= 5e-6
+
+
+def test_trilinear_training_at_config2_size_matches_the_c_oracle(plx_lib):
+    """BASELINE config #2 in full — 12 800 rays x 600 samples through the 128^3 ball grid — with the trilinear lookup: pixels,
+    depth, loss and the gradient of the fused march against the plain-C oracle on EVERY ray (1e-5), in-bounds counts bit-exact."""
+    sc = synth.make_scene("c2", H=8)
+    C_, R, S = sc.poses.shape[0], sc.rays_per_cam, sc.num_samples
+    grid, poses = sc.grid.to(DEV), sc.poses.to(DEV)
+    gmin = ops.grid_origin(sc.grid.shape, sc.points_distance)
+    uv = synth.random_uv(C_, R, seed=78).to(DEV)
+    dirs, _ = ops.generate_rays(None, poses, sc.fov, uv=uv, want_targets=False)
+    targets = torch.rand(C_ * R, 4, device=DEV, generator=torch.Generator(device=DEV).manual_seed(6))
+    o = np.repeat(sc.poses[:, :3, 3].numpy(), R, axis=0)
+    rgba_o, depth_o, count_o, _ = co.render_forward(sc.grid.numpy(), o, dirs.cpu().numpy(), S, sc.delta_step, np.float32(gmin),
+                                                    sc.points_distance, mode="trilinear", want_lin=False)
+    rgba, depth, count = ops.render_rays(grid, poses[:, :3, 3], dirs, S, sc.delta_step, gmin, sc.points_distance, mode="trilinear",
+                                         rays_per_origin=R, return_depth=True, return_count=True)
+    assert np.array_equal(count.cpu().numpy(), count_o)
+    assert rel_err(rgba.cpu().numpy(), rgba_o) <= TOL and rel_err(depth.cpu().numpy(), depth_o) <= TOL
+    gg = torch.zeros_like(grid)
+    rgba_f, loss_f = ops.render_train(grid, gg, S, sc.delta_step, gmin, sc.points_distance, origins=poses[:, :3, 3], dirs=dirs,
+                                      targets=targets, rays_per_origin=R, mode="trilinear")
+    loss_o, gpix = co.mse_loss(rgba_o, targets.cpu().numpy())
+    grad_o = co.render_backward(sc.grid.numpy(), o, dirs.cpu().numpy(), S, sc.delta_step, np.float32(gmin), sc.points_distance, gpix,
+                                mode="trilinear")
+    assert rel_err(rgba_f.cpu().numpy(), rgba_o) <= TOL
+    assert abs(float(loss_f) - loss_o) <= TOL * loss_o
+    assert rel_err(gg.cpu().numpy(), grad_o) <= TOL
+
+
+# ------------------------------------------------------------------------------------------------ config #4 at full size
+@pytest.mark.parametrize("mode", ["nearest", "trilinear"])
+def test_config4_inference_frame_matches_the_c_oracle_on_strided_rays(plx_lib, mode):
+    """BASELINE config #4: the 512^3 grid (alpha threshold 0.2, scripts/compare_inference_to_image.py:91), one 800x800 view,
+    600 samples per ray, rendered by the coherent ray-packet kernel; every 89th ray of the 640 000 (7 192 rays, all image
+    regions) is restated by the C oracle: in-bounds counts bit-exact, pixels and depth within 1e-5, and the uint8 image the
+    march kernel writes equals the reference's post-processing of those pixels."""
+    G, S, delta, side = 512, 600, 0.01, 800
+    pd = synth.GRID_EXTENT / G
+    grid_h = synth.ball_grid(G).clip_(0.0, 1.0)
+    grid_h[..., 3][grid_h[..., 3] < 0.2] = 0.0
+    grid = grid_h.to(DEV)
+    pose = synth.lookat_poses(4)[1:2]
+    gmin = ops.grid_origin(grid.shape, pd)
+    n = side * side
+    dirs, _ = ops.generate_rays(None, pose.to(DEV), synth.CAMERA_ANGLE_X, uv=None, rays_per_cam=n, want_targets=False)
+    o_dev = pose.to(DEV)[:, :3, 3]
+    packet, depth = ops.render_rays(grid, o_dev, dirs, S, delta, gmin, pd, mode=mode, clamp=False, rays_per_origin=n,
+                                    return_depth=True, coherent=True)
+    _, count = ops.render_rays(grid, o_dev, dirs, S, delta, gmin, pd, mode=mode, clamp=False, rays_per_origin=n, return_count=True)
+    sel = np.arange(0, n, 89)
+    d_sel = dirs.cpu().numpy()[sel]
+    o_sel = np.repeat(pose[:, :3, 3].numpy(), len(sel), axis=0)
+    rgba_o, depth_o, count_o, _ = co.render_forward(grid_h.numpy(), o_sel, d_sel, S, delta, np.float32(gmin), pd, mode=mode,
+                                                    clamp=False, want_lin=False)
+    assert np.array_equal(count.cpu().numpy()[sel], count_o)
+    assert rel_err(packet.cpu().numpy()[sel], rgba_o) <= TOL
+    assert rel_err(depth.cpu().numpy()[sel], depth_o) <= TOL
+    img = ops.render_image_u8(grid, pose.to(DEV), synth.CAMERA_ANGLE_X, side, S, delta, gmin, pd, mode=mode).cpu().numpy()
+    want = np.transpose((packet.cpu().numpy() * 255).round().clip(0, 255).astype(np.uint8).reshape(side, side, 4), (1, 0, 2))
+    assert img.shape == (side, side, 4) and img.dtype == np.uint8
+    assert np.array_equal(img, want), "the kernel's epilogue is src/visualization.py:150-154 bit for bit"
+
+
+# ------------------------------------------------------------------------------------------------ inference epilogue + splat
+def test_image_epilogue_is_the_references_postprocessing(plx_lib):
+    """(pix * 255).round().clip(0, 255).astype(uint8), reshape, transpose — src/visualization.py:150-154 — done by the march
+    kernel: bit-equal to doing it on the host from the same kernel's float pixels, incl. values outside [0, 1] (unclamped
+    grid) and exact .5 ties."""
+    G, side, S = 24, 20, 64
+    pd = synth.GRID_EXTENT / G
+    grid = synth.dense_grid(G, seed=5).to(DEV) * 1.5
+    grid[0, 0, 0] = torch.tensor([0.5 / 255, 1.5 / 255, 2.5 / 255, 1.0])
+    pose = synth.lookat_poses(3)[1:2].to(DEV)
+    gmin = ops.grid_origin(grid.shape, pd)
+    for mode in ("nearest", "trilinear"):
+        img = ops.render_image_u8(grid, pose, synth.CAMERA_ANGLE_X, side, S, 6.0 / S, gmin, pd, mode=mode).cpu().numpy()
+        dirs, _ = ops.generate_rays(None, pose, synth.CAMERA_ANGLE_X, uv=None, rays_per_cam=side * side, want_targets=False)
+        pix = ops.render_rays(grid, pose[:, :3, 3], dirs, S, 6.0 / S, gmin, pd, mode=mode, clamp=False, rays_per_origin=side * side,
+                              coherent=True).cpu().numpy()
+        want = np.transpose((pix * 255).round().clip(0, 255).astype(np.uint8).reshape(side, side, 4), (1, 0, 2))
+        assert np.array_equal(img, want)
+        assert img.max() == 255 and img.min() == 0
+
+
+def test_gpu_splat_matches_the_references_painter_order_image(plx_lib):
+    """visulize_3d_in_2d_fast (src/visualization.py:157-232) against the image the UNMODIFIED reference produced
+    (tests/golden/splat_g40.npz): same shape and dtype; the same pixels painted; colours equal wherever the pixel assignment
+    agrees.  The reference's projection runs through BLAS matmul and an unstable argsort, so a point that lands within an ulp of
+    a pixel boundary, or ties in distance, may legitimately resolve differently: at most 0.5 % of the pixels may differ."""
+    import src.visualization as vz
+    z = np.load(os.path.join(GOLD, "splat_g40.npz"))
+    img = vz.visulize_3d_in_2d_fast(torch.from_numpy(z["grid"]).to(DEV), float(z["pd"]), torch.from_numpy(z["pose"]).to(DEV),
+                                    float(z["fov"]), int(z["size_y"]))
+    ref = z["image"]
+    assert img.shape == ref.shape and img.dtype == ref.dtype == np.float64
+    same = (img == ref).all(-1)
+    assert same.mean() >= 0.995, f"{(~same).sum()} of {same.size} pixels differ"
+    painted, painted_ref = (img != 1.0).any(-1), (ref != 1.0).any(-1)
+    assert abs(int(painted.sum()) - int(painted_ref.sum())) <= 0.005 * painted_ref.sum()
+    with pytest.raises(L.PlxError, match="no CPU fallback"):
+        vz.visulize_3d_in_2d_fast(torch.from_numpy(z["grid"]), float(z["pd"]), torch.from_numpy(z["pose"]), float(z["fov"]), 16)
+
+
+def test_visulize_3d_in_2d_keeps_the_reference_default_and_refuses_the_cpu(plx_lib):
+    import inspect
+    import src.visualization as vz
+    assert inspect.signature(vz.visulize_3d_in_2d).parameters["device"].default == "cpu"       # src/visualization.py:112
+    ck = {"grid": torch.zeros(4, 4, 4, 4), "param": {"points_distance": 0.5, "delta_step": 0.1}}
+    with pytest.raises(L.PlxError, match="no CPU fallback"):
+        vz.visulize_3d_in_2d(ck, torch.eye(4)[None], 0.6, None, torch.zeros(64, 3), False, 0.2, 16, 8)
+
+
+# ------------------------------------------------------------------------------------------------ uint8 target images
+def test_uint8_images_give_the_same_targets_and_pixels_as_the_float_conversion(plx_lib):
+    """src/data_processing.py:58 converts the PNG bytes once, fp32(u8) / 255.  With uint8 images resident the kernels do that
+    conversion when they fetch a target pixel: targets bit-equal, the fused march's pixels bit-equal and loss / gradient equal
+    up to the order of the atomic sums."""
+    C_, H, R, S, G = 3, 16, 64, 64, 24
+    pd = synth.GRID_EXTENT / G
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (C_, H, H, 4), dtype=torch.uint8, generator=g)
+    f32 = torch.tensor(u8.numpy(), dtype=torch.float) / 255                      # the reference's expression
+    poses, uv = synth.lookat_poses(C_).to(DEV), synth.random_uv(C_, R).to(DEV)
+    grid = synth.ball_grid(G).to(DEV)
+    gmin = ops.grid_origin(grid.shape, pd)
+    _, t_u8 = ops.generate_rays(u8.to(DEV), poses, synth.CAMERA_ANGLE_X, uv=uv)
+    _, t_f32 = ops.generate_rays(f32.to(DEV), poses, synth.CAMERA_ANGLE_X, uv=uv)
+    assert torch.equal(t_u8, t_f32)
+    out = []
+    for imgs in (u8, f32):
+        gg = torch.zeros_like(grid)
+        rgba, loss = ops.render_train(grid, gg, S, 6.0 / S, gmin, pd, imgs=imgs.to(DEV), poses=poses, fov=synth.CAMERA_ANGLE_X, uv=uv)
+        out.append((rgba, float(loss), gg))
+    assert torch.equal(out[0][0], out[1][0])
+    assert abs(out[0][1] - out[1][1]) <= 1e-6 * out[1][1]
+    assert rel_err(out[0][2].cpu().numpy(), out[1][2].cpu().numpy()) <= 1e-6
+    # and through the trainer (resident uint8 image set)
+    ta = VoxelTrainer(grid, pd, poses, synth.CAMERA_ANGLE_X, u8.to(DEV), R, S, 6.0 / S, lr=0.0075)
+    tb = VoxelTrainer(grid, pd, poses, synth.CAMERA_ANGLE_X, f32.to(DEV), R, S, 6.0 / S, lr=0.0075)
+    la, lb = float(ta.step(uv)), float(tb.step(uv))
+    assert abs(la - lb) <= 1e-6 * lb and ta.imgs.dtype == torch.uint8
+
+
+# ------------------------------------------------------------------------------------------------ trainer entry points agree
+@pytest.mark.parametrize("tv,beta,mode", [(0.0, 0.0, "nearest"), (1e-4, 0.0, "nearest"), (1e-4, 5e-3, "nearest"), (1e-4, 0.0, "trilinear")])
+def test_step_and_step_host_optimise_the_same_objective(plx_lib, tv, beta, mode):
+    """step() (device uv), step_host() (pinned uv, loss published to the host) and the unfused three-kernel path must apply the
+    same losses — MSE + beta term + TV term — whatever the entry point (the TV weight was dropped on step_host)."""
+    cs = Case(24, 3, 8, 48, 96, 6.0 / 96, "ball")
+    d = cs.cuda()
+    mk = lambda: VoxelTrainer(d["grid"], cs.pd, d["poses"], cs.fov, d["imgs"], cs.R, cs.S, cs.delta, lr=0.0075, tv=tv, beta=beta, mode=mode)
+    ta, tb, tc = mk(), mk(), mk()
+    tc.unfused = True
+    for i in range(3):
+        uv = synth.random_uv(cs.C, cs.R, seed=20 + i)
+        la = float(ta.step(uv.to(DEV)))
+        tb.step_host(uv.pin_memory())
+        lb = tb.wait_result()
+        lc = float(tc.step(uv.to(DEV)))
+        assert abs(la - lb) <= 2e-6 * la and abs(la - lc) <= 2e-6 * la
+    torch.cuda.synchronize()
+    if tv > 0:
+        assert float(ta.tv_loss) > 0 and abs(float(ta.tv_loss) - float(tb.tv_loss)) <= 1e-5 * float(ta.tv_loss)
+    for other in (tb, tc):
+        assert float(torch.quantile((ta.grid - other.grid).abs().flatten(), 0.999)) <= 1e-5
+        assert rel_err(other.grad_abs_sum.cpu().numpy(), ta.grad_abs_sum.cpu().numpy()) <= 1e-5
+
+
+def test_wait_result_raises_instead_of_spinning_forever(plx_lib):
+    cs = Case(16, 2, 8, 16, 32, 6.0 / 32, "ball")
+    d = cs.cuda()
+    tr = VoxelTrainer(d["grid"], cs.pd, d["poses"], cs.fov, d["imgs"], cs.R, cs.S, cs.delta, lr=0.0075)
+    tr.step_host(cs.uv.pin_memory())
+    assert tr.wait_result() > 0
+    tr.wait_timeout_s = 0.2
+    with pytest.raises(L.PlxError, match="never published|not published"):
+        tr.wait_result(step=tr.step_count + 5)              # a step nobody issued: the stream is idle, nothing will arrive

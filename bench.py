@@ -319,6 +319,10 @@ def phase_times(cx: Ctx, tr, uv_dev, n_inst: int):
         tr.step(uv_dev[w_ % len(uv_dev)])
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(n_inst)]
     cx.barrier()
+    # head start: the instrumented loop costs the host more per step (event records) than the device needs to run it, and a
+    # starved stream would book its idle gaps to whichever phase follows; a few ms of device-side spinning lets the host
+    # queue the whole loop first, so the intervals below are device time only
+    torch.cuda._sleep(int(2.0e6 * n_inst))
     for i in range(n_inst):
         ev = evs[i]
         ev[0].record()

@@ -132,12 +132,14 @@ def sample_indices(grid, origins, dirs, num_samples, delta_step, gmin, points_di
 
 def render_train(grid, grad_grid, num_samples, delta_step, gmin, points_distance, *, origins=None, dirs=None,
                  targets=None, rays_per_origin=1, imgs=None, poses=None, fov=None, uv=None, n_rays_global=None,
-                 beta_over_m=0.0, clamp=True, mode="nearest"):
+                 beta_over_m=0.0, clamp=True, mode="nearest", peer_grads=None):
     """K12, the fused training march (nearest or trilinear lookup): forward + mean-MSE + backward in one kernel; the gradient is
     ACCUMULATED into `grad_grid` (contiguous (X,Y,Z,4)).  Rays are either given (`origins`, `dirs`, `targets`) or
     generated in the kernel from (`imgs`, `poses`, `fov`, `uv` (C,R,2)).  Returns (rgba (N,4), loss (1,) device tensor)
     = the pixels and mean((rgba - targets)^2) of scripts/train.py:151-156.  `imgs` may be fp32 in [0,1] or uint8 (the
-    target pixel is then converted in the kernel, fp32(u8) / 255)."""
+    target pixel is then converted in the kernel, fp32(u8) / 255).  `peer_grads`: list of W grid-shaped buffers (push exchange,
+    PlxPeerGrad): the gradient of cell `lin` is added to peer_grads[owner(lin)] instead of `grad_grid`, owner = the slab
+    partition of plx_slab_partition — on a multi-GPU run these are the ranks' peer-mapped buffers."""
     dev = L.require_cuda(grid, grad_grid, origins, dirs, targets, imgs, poses, uv)
     lib = L.load()
     a = L.PlxRenderTrain()
@@ -161,6 +163,14 @@ def render_train(grid, grad_grid, num_samples, delta_step, gmin, points_distance
         a.targets = targets.data_ptr()
     if not grad_grid.is_contiguous() or grad_grid.shape != grid.shape or grad_grid.dtype != torch.float32:
         raise L.PlxError("grad_grid must be a contiguous float32 tensor of the grid's shape")
+    if peer_grads:
+        mul = C.c_uint32()
+        L.check(lib.plx_slab_partition(grid.numel() // 4, len(peer_grads), 0, C.byref(mul), None, None), "plx_slab_partition")
+        for r, buf in enumerate(peer_grads):
+            if not buf.is_contiguous() or buf.shape != grid.shape or buf.dtype != torch.float32:
+                raise L.PlxError("peer_grads must be contiguous float32 tensors of the grid's shape")
+            a.peer_grad.grads[r] = buf.data_ptr()
+        a.peer_grad.owner_mul, a.peer_grad.world = mul.value, len(peer_grads)
     n_glob = n if n_rays_global is None else int(n_rays_global)
     rgba = torch.empty((n, 4), dtype=torch.float32, device=dev)
     loss = torch.zeros((1,), dtype=torch.float32, device=dev)

@@ -334,10 +334,12 @@ def slab_partition(n_cells: int, rank: int, world: int):
 
 
 def pick_exchange(n_rays: int, num_samples: int, n_cells: int) -> str:
-    """"push" when a rank's batch can touch only a fraction of the cells (what crosses NVLink is then 16 B per merged
-    in-bounds sample instead of 16 B per cell), else "pull" (dense reduce-scatter in the optimiser kernel).  About half of
-    a ray's samples lie inside the grid."""
-    return "push" if n_rays * num_samples // 2 < n_cells // 2 else "pull"
+    """"push" unless a rank's batch is so dense that its reductions would outweigh the dense exchange many times over.
+    Measured on B200 (bench.py, 20-step regions): sparse batches (C3: 0.56 M in-bounds samples into 16.8 M cells) 278 vs 501 us per
+    step at N = 2 and 426 vs 624 us at N = 8; dense batches (C2: 3.3 M samples into 2.1 M cells) still 97 vs 127 us at N = 2 and
+    131 vs 147 us at N = 8, because the reductions travel while the march computes.  About half of a ray's samples lie inside
+    the grid; beyond ~8 in-bounds samples per cell the dense pull exchange moves fewer bytes."""
+    return "push" if n_rays * num_samples // 2 < 8 * n_cells else "pull"
 
 
 class PeerVoxelTrainer(VoxelTrainer):

@@ -75,6 +75,36 @@ def test_trilinear_training_at_config2_size_matches_the_c_oracle(plx_lib):
     assert rel_err(gg.cpu().numpy(), grad_o) <= TOL
 
 
+@pytest.mark.parametrize("mode,S,world", [("nearest", 200, 2), ("nearest", 64, 3), ("nearest", 600, 8), ("trilinear", 96, 4)])
+def test_push_exchange_march_sends_every_cell_to_its_slab_owner(plx_lib, mode, S, world):
+    """PlxPeerGrad on ONE device: `world` gradient buffers stand in for the ranks' peer-mapped ones.  Every buffer may only
+    receive cells of its own slab (plx_slab_partition), and the slabs put together are the gradient the plain march produces
+    (the cross-lane run merge of the push path only regroups the sums)."""
+    import ctypes as C
+    from plenoxels_b200.trainer import slab_partition
+    cs = Case(32, 3, 8, 96, S, (0.5 if S == 600 else 1.0) * 6.0 / S, "ball")
+    d = cs.cuda()
+    kw = dict(imgs=d["imgs"], poses=d["poses"], fov=cs.fov, uv=d["uv"], mode=mode)
+    ref = torch.zeros_like(d["grid"])
+    rgba0, loss0 = ops.render_train(d["grid"], ref, S, cs.delta, cs.gmin, cs.pd, **kw)
+    bufs = [torch.zeros_like(d["grid"]) for _ in range(world)]
+    unused = torch.zeros_like(d["grid"])
+    rgba1, loss1 = ops.render_train(d["grid"], unused, S, cs.delta, cs.gmin, cs.pd, peer_grads=bufs, **kw)
+    assert torch.equal(rgba0, rgba1) and float(unused.abs().max()) == 0.0
+    assert abs(float(loss0) - float(loss1)) <= 1e-6 * float(loss0)
+    n_cells = cs.G ** 3
+    total = torch.zeros_like(ref)
+    for r, buf in enumerate(bufs):
+        mul, b, e = slab_partition(n_cells, r, world)
+        flat = buf.view(-1, 4)
+        outside = flat.abs().sum(1)
+        outside[b:e] = 0
+        assert float(outside.max()) == 0.0, f"rank {r} received cells outside its slab"
+        total.view(-1, 4)[b:e] = flat[b:e]
+    assert float(ref.abs().max()) > 0
+    assert rel_err(total.cpu().numpy(), ref.cpu().numpy()) <= 2e-6
+
+
 # ------------------------------------------------------------------------------------------------ config #4 at full size
 @pytest.mark.parametrize("mode", ["nearest", "trilinear"])
 def test_config4_inference_frame_matches_the_c_oracle_on_strided_rays(plx_lib, mode):

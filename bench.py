@@ -311,32 +311,53 @@ def count_in_bounds(sc, tr, dev_scene, uv_dev, n=4):
 
 
 def phase_times(cx: Ctx, tr, uv_dev, n_inst: int):
-    """Per-phase device time of the step in situ: the same launches, with CUDA events between the phases."""
+    """Device time of the step's kernels in situ.  Events BETWEEN the kernels of a step distort a multi-GPU step (they book
+    rank skew and host issue gaps to whichever phase follows), so each kernel is timed the robust way: the same launch, repeated
+    back to back on every rank at once with one event pair around the loop — the march under everybody's reduction traffic,
+    the optimiser / exchange kernel under everybody's parameter stores.  The trainer is a throw-away (its state is not a
+    training state afterwards).  What the full step costs beyond the two kernels (barriers, launch gaps, rank skew) is
+    reported by the caller as step - sum."""
     peer = hasattr(tr, "exchange")
-    names = ["render_train"] + (["barrier_grad", "exchange+adam" if tr.exchange == "pull" else "slab_adam+allgather", "barrier_param"]
-                                if peer and not tr._fused else ["adam" if cx.world == 1 else "exchange+adam"])
+    opt_name = ("slab_adam+allgather" if tr.exchange == "push" else "exchange+adam") if peer else ("adam" if cx.world == 1 else "exchange+adam")
     for w_ in range(3):
         tr.step(uv_dev[w_ % len(uv_dev)])
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(n_inst)]
-    cx.barrier()
-    # head start: the instrumented loop costs the host more per step (event records) than the device needs to run it, and a
-    # starved stream would book its idle gaps to whichever phase follows; a few ms of device-side spinning lets the host
-    # queue the whole loop first, so the intervals below are device time only
-    torch.cuda._sleep(int(2.0e6 * n_inst))
-    for i in range(n_inst):
-        ev = evs[i]
-        ev[0].record()
-        tr.render_phase(uv_dev[i % len(uv_dev)])
-        ev[1].record()
-        if len(names) == 4:
-            marks = iter(ev[2:4])
-            tr._mark = lambda: next(marks).record()
-        tr.update_phase()
-        ev[-1].record()
-    tr._mark = None
     tr.flush()
-    torch.cuda.synchronize(cx.dev)
-    return {n: float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(n_inst)])) for j, n in enumerate(names)}
+
+    def loop(fn):
+        cx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_inst):
+            fn(i)
+        e1.record()
+        cx.barrier()
+        return cx.max_over_ranks(e0.elapsed_time(e1)) / n_inst
+
+    if cx.world == 1:
+        # one GPU: no rank skew to distort anything, so the kernels are timed inside real steps (the march right behind an
+        # optimiser pass that has just streamed 168 MB through the L2, and vice versa), events between them; a device-side
+        # head start lets the host queue the whole loop first so that no interval contains a host issue gap
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_inst)]
+        torch.cuda.synchronize(cx.dev)
+        torch.cuda._sleep(int(2.0e6 * n_inst))
+        for i in range(n_inst):
+            evs[i][0].record()
+            tr.render_phase(uv_dev[i % len(uv_dev)])
+            evs[i][1].record()
+            tr.update_phase()
+            evs[i][2].record()
+        torch.cuda.synchronize(cx.dev)
+        return {n: float(np.mean([e[j].elapsed_time(e[j + 1]) for e in evs])) for j, n in enumerate(["render_train", opt_name])}
+    if peer:
+        tr._no_barriers = True
+    out = {"render_train": loop(lambda i: tr.render_phase(uv_dev[i % len(uv_dev)]))}
+    if peer or cx.world == 1:
+        out[opt_name] = loop(lambda i: tr.update_phase())
+    else:                                        # NCCL trainer: all-reduce + replicated Adam
+        out[opt_name] = loop(lambda i: tr.update_phase())
+    if peer:
+        tr._no_barriers = False
+    return out
 
 
 def roofline_of(cx: Ctx, kms: dict, m_in: float, n_rays: int, cells: int, tr, workload: str, ms_step: float):
@@ -357,6 +378,7 @@ def roofline_of(cx: Ctx, kms: dict, m_in: float, n_rays: int, cells: int, tr, wo
             alg["exchange+adam"] = 160.0 * cells / W + 16.0 * cells * f
             nv["exchange+adam"] = 16.0 * cells * (1.0 if mc else 2.0 * f)              # gradients in (reduced by the switch or per peer) + parameters in
     timed = {k: v for k, v in kms.items() if v and k in alg}
+    kms = dict(kms, **{"step": ms_step, "barriers+gaps": ms_step - sum(timed.values())})
     dom = max(timed, key=timed.get)
     hbm_gbs = alg[dom] / (timed[dom] * 1e-3) / 1e9
     traffic = None

@@ -50,6 +50,8 @@ __device__ __forceinline__ void step_tail(const StepTail& t) {
     }
 }
 
+__device__ __forceinline__ bool differs(const float4 a, const float4 b) { return a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w; }
+
 template <bool HAS_ABS, bool ZERO, bool SKIP>
 __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                               float4* __restrict__ v, float4* __restrict__ ga, int64_t n4,
@@ -66,13 +68,16 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
         // |g| are touched once per step (evict-first), parameters and gradient again by the next march
         float4 P = ld_hint(p + i, pol), G = ld_hint(g + i, pol_g), M = __ldcs(m + i), V = __ldcs(v + i), A;
         if (HAS_ABS) A = __ldcs(ga + i);
+        const float4 P0 = P, M0 = M, V0 = V;
         adam1(P.x, G.x, M.x, V.x, s, bc);
         adam1(P.y, G.y, M.y, V.y, s, bc);
         adam1(P.z, G.z, M.z, V.z, s, bc);
         adam1(P.w, G.w, M.w, V.w, s, bc);
-        st_hint(p + i, P, pol);
-        __stcs(m + i, M);
-        __stcs(v + i, V);
+        // a value that did not change is not stored: a cell no ray has EVER touched keeps m = v = 0 and its parameter, and a cell
+        // whose update has decayed below half an ulp keeps its parameter — their lines stay clean in L2 and are never written back
+        if (differs(P, P0)) st_hint(p + i, P, pol);
+        if (differs(M, M0)) __stcs(m + i, M);
+        if (differs(V, V0)) __stcs(v + i, V);
         // a cell no ray touched this step has g == 0 exactly: |g| adds nothing and the gradient is already clear,
         // so neither store is issued (about half the cells of a C2 step; saves their 32 B/cell of write-back)
         const bool touched = !SKIP || G.x != 0.f || G.y != 0.f || G.z != 0.f || G.w != 0.f;
@@ -121,19 +126,24 @@ __global__ void __launch_bounds__(256) k_adam_slab(const SlabPtrs sp, float4* p_
         const int64_t i = begin4 + (rev ? n4 - 1 - k : k);
         float4 P = p[i], G = g[i], M = __ldcs(m + i), V = __ldcs(v + i), A;
         if (ga) A = __ldcs(ga + i);
+        const float4 P0 = P, M0 = M, V0 = V;
         adam1(P.x, G.x, M.x, V.x, s, bc);
         adam1(P.y, G.y, M.y, V.y, s, bc);
         adam1(P.z, G.z, M.z, V.z, s, bc);
         adam1(P.w, G.w, M.w, V.w, s, bc);
-        if (MC) {
-            multimem_st(p_mc + i, P);                                // one store, replicated into every replica by the switch
-        } else {
+        // replicas hold identical bits, so a parameter that did not change (a cell never touched, or an update below half an ulp)
+        // need not cross NVLink at all; the same goes for untouched moments and the local HBM
+        if (differs(P, P0)) {
+            if (MC) {
+                multimem_st(p_mc + i, P);                            // one store, replicated into every replica by the switch
+            } else {
 #pragma unroll
-            for (int r = 0; r < PLX_MAX_PEERS; ++r)
-                if (r < world) sp.grids[r][i] = P;
+                for (int r = 0; r < PLX_MAX_PEERS; ++r)
+                    if (r < world) sp.grids[r][i] = P;
+            }
         }
-        __stcs(m + i, M);
-        __stcs(v + i, V);
+        if (differs(M, M0)) __stcs(m + i, M);
+        if (differs(V, V0)) __stcs(v + i, V);
         if (G.x != 0.f || G.y != 0.f || G.z != 0.f || G.w != 0.f) {  // untouched cell: |g| adds nothing, gradient already clear
             if (ga) { A.x += fabsf(G.x); A.y += fabsf(G.y); A.z += fabsf(G.z); A.w += fabsf(G.w); __stcs(ga + i, A); }
             g[i] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -490,7 +490,7 @@ class PeerVoxelTrainer(VoxelTrainer):
                 p.sync.err = self._err
                 self._peers.append(p)
         self._cur = 0
-        self._mark = None                     # profiling hook (bench.py): called after the first barrier and after the optimiser kernel
+        self._no_barriers = False             # profiling only (bench.py times the kernels of a throw-away trainer in isolation)
         self._args = self._make_args()
         self.launches_per_step = 2 if self._fused else 4          # march, [barrier], exchange / optimiser, [barrier]
         torch.cuda.synchronize(dev)
@@ -565,12 +565,8 @@ class PeerVoxelTrainer(VoxelTrainer):
         self._epoch += 1
         if self.exchange == "push":
             self._barrier(0, st)                              # every rank's reductions into my slab have landed
-            if self._mark:
-                self._mark()
             self._loss_tail(self._slab, result_host)
             L.check(self.lib.plx_adam_step_slab(C.byref(self._slab), st), "plx_adam_step_slab")
-            if self._mark:
-                self._mark()
             self._barrier(1, st)                              # every replica holds the new parameters
             return
         b = self._cur
@@ -583,8 +579,6 @@ class PeerVoxelTrainer(VoxelTrainer):
             sy.signal_channel, sy.signal_epoch = 1, self._epoch
         else:
             self._barrier(0, st)                              # every rank's partial gradient is complete
-            if self._mark:
-                self._mark()
         # the buffer consumed by the PREVIOUS step (its readers passed that step's closing barrier / signalled channel 1,
         # which this step's march waited for) is cleared now, on the side stream, behind this step's exchange kernel: that
         # kernel is NVLink-bound and leaves HBM idle, whereas clearing during the march (measured) slowed the march by as
@@ -599,8 +593,6 @@ class PeerVoxelTrainer(VoxelTrainer):
                 ev.record(self._clear_stream)
             self._cleared[o] = ev
         L.check(self.lib.plx_adam_step_peer(C.byref(peer), st), "plx_adam_step_peer")
-        if self._mark and not self._fused:
-            self._mark()
         if not self._fused:
             self._barrier(1, st)                              # every replica holds the new parameters; peers done reading
         self._dirty = b
@@ -616,6 +608,8 @@ class PeerVoxelTrainer(VoxelTrainer):
         self.check_errors()
 
     def _barrier(self, channel, st):
+        if self._no_barriers:
+            return
         L.check(self.lib.plx_peer_barrier(self._flag_ptrs, self.rank, self.world, channel, self._epoch, C.byref(self._err), st),
                 "plx_peer_barrier")
 

@@ -391,6 +391,12 @@ int plx_splat_view(const float* grid, const int32_t dims[3], float points_distan
                    int32_t xs, int32_t ys, uint64_t* zbuf, float* image, void* stream);
 
 /*
+ * A/B switches for measurements (tools/ and tests; process-wide, results are identical either way — they only move launch
+ * shapes and skip redundant stores): "adam_skip_same" (-1 = auto), "adam_blocks_per_sm" (4), "train_wpb" (4).
+ */
+int plx_tune(const char* name, int32_t value);
+
+/*
  * Self-test of the library's exact fp32 helpers: evaluates the hoisted-reciprocal quotient x / y (the march's divisor
  * path), the inlined square root and the per-element quotient (Adam) on `n` pseudo-random inputs and counts results
  * that differ in any bit from CUDA's IEEE intrinsics (__fdiv_rn / __fsqrt_rn).  `mismatches` = 3 device uint64 counters

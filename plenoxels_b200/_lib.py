@@ -150,6 +150,7 @@ PROTOTYPES = {
                                     c_void, c_void]),
     "plx_splat_view": (C.c_int, [c_void, C.POINTER(C.c_int32), C.c_float, C.POINTER(C.c_float), C.c_float, C.c_int32, C.c_int32,
                                  c_void, c_void, c_void]),
+    "plx_tune": (C.c_int, [C.c_char_p, C.c_int32]),
     "plx_selftest_arith": (C.c_int, [C.c_float, C.c_uint64, C.c_uint64, c_void, c_void]),
     "plx_train_step": (C.c_int, [C.POINTER(PlxTrainStep), C.c_int32, c_void]),
     "plx_train_step_host": (C.c_int, [C.POINTER(PlxTrainStep), c_void, c_void, C.c_int32, c_void]),

@@ -9,6 +9,13 @@
 #include "plx_device.cuh"
 #include "plx_launch.h"
 
+namespace plx {
+Tuning& tuning() {
+    static Tuning t;
+    return t;
+}
+}  // namespace plx
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -173,6 +180,7 @@ static plx::AdamScalars adam_scalars(double lr, double beta1, double beta2, doub
     s.neg_step_size = (float)(-(lr / bc1));
     s.keep_p = s.keep_g = false;
     s.reverse = (step & 1) != 0;
+    s.skip_same = true;
     return s;
 }
 
@@ -406,6 +414,16 @@ int plx_splat_view(const float* grid, const int32_t dims[3], float points_distan
     if ((uintptr_t)grid % 16 || (uintptr_t)zbuf % 8) return fail(PLX_E_ALIGN, "splat buffers are misaligned");
     return cuda_result(plx::launch_splat_view(grid, dims, points_distance, pose_host, fov, xs, ys, (unsigned long long*)zbuf, image,
                                               (cudaStream_t)stream), "plx_splat_view");
+}
+
+int plx_tune(const char* name, int32_t value) {
+    if (!name) return fail(PLX_E_NULL, "name is NULL");
+    plx::Tuning& t = plx::tuning();
+    if (!std::strcmp(name, "adam_skip_same")) t.adam_skip_same = value;
+    else if (!std::strcmp(name, "adam_blocks_per_sm")) { if (value < 1 || value > 8) return fail(PLX_E_SHAPE, "adam_blocks_per_sm must be 1..8"); t.adam_blocks_per_sm = value; }
+    else if (!std::strcmp(name, "train_wpb")) { if (value != 1 && value != 2 && value != 4) return fail(PLX_E_SHAPE, "train_wpb must be 1, 2 or 4"); t.train_wpb = value; }
+    else return fail(PLX_E_UNSUPPORTED, "unknown tuning switch '%s'", name);
+    return PLX_OK;
 }
 
 int plx_selftest_arith(float y, uint64_t n, uint64_t seed, uint64_t* mismatches, void* stream) {

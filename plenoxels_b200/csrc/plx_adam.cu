@@ -52,6 +52,14 @@ __device__ __forceinline__ void step_tail(const StepTail& t) {
 
 __device__ __forceinline__ bool differs(const float4 a, const float4 b) { return a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w; }
 
+// Store skipping is decided per 128-byte LINE (8 consecutive float4 = 8 consecutive lanes of the warp), never per thread: a line
+// of which only some 16-byte pieces are written reaches DRAM as partial-sector writes, which HBM serves as read-modify-write
+// (measured: per-thread skipping made the 256^3 step 15 % SLOWER, 402 -> 462 us).  True if any lane of this lane's line votes.
+__device__ __forceinline__ bool line_any(bool vote) {
+    const unsigned b = __ballot_sync(FULL, vote);
+    return ((b >> ((threadIdx.x & 31u) & ~7u)) & 0xffu) != 0u;
+}
+
 template <bool HAS_ABS, bool ZERO, bool SKIP>
 __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                               float4* __restrict__ v, float4* __restrict__ ga, int64_t n4,
@@ -62,8 +70,11 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
     // parameters and gradient are re-used by the march of the next step: keep them in L2 when they fit (plx_device.cuh)
     const uint64_t pol = l2_policy(s.keep_p), pol_g = l2_policy(s.keep_g);
     const bool rev = s.reverse;
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += stride) {
-        const int64_t i = rev ? n4 - 1 - k : k;
+    // the trip count is uniform over the warp (the line votes below need every lane present); lanes past the end idle
+    for (int64_t k0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); k0 < n4; k0 += stride) {
+        const int64_t k = k0 + (threadIdx.x & 31u);
+        const bool live = k < n4;
+        const int64_t i = live ? (rev ? n4 - 1 - k : k) : 0;
         // all loads of the iteration are issued before the first use: 5 independent 16-byte requests per thread; m, v and
         // |g| are touched once per step (evict-first), parameters and gradient again by the next march
         float4 P = ld_hint(p + i, pol), G = ld_hint(g + i, pol_g), M = __ldcs(m + i), V = __ldcs(v + i), A;
@@ -75,12 +86,16 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
         adam1(P.w, G.w, M.w, V.w, s, bc);
         // a value that did not change is not stored: a cell no ray has EVER touched keeps m = v = 0 and its parameter, and a cell
         // whose update has decayed below half an ulp keeps its parameter — their lines stay clean in L2 and are never written back
-        if (differs(P, P0)) st_hint(p + i, P, pol);
-        if (differs(M, M0)) __stcs(m + i, M);
-        if (differs(V, V0)) __stcs(v + i, V);
+        const bool all = !s.skip_same;
+        const bool st_p = all || line_any(live && differs(P, P0)), st_m = all || line_any(live && differs(M, M0)),
+                   st_v = all || line_any(live && differs(V, V0));
         // a cell no ray touched this step has g == 0 exactly: |g| adds nothing and the gradient is already clear,
-        // so neither store is issued (about half the cells of a C2 step; saves their 32 B/cell of write-back)
-        const bool touched = !SKIP || G.x != 0.f || G.y != 0.f || G.z != 0.f || G.w != 0.f;
+        // so (when that holds for its whole line) neither store is issued — about half the lines of a C2 step
+        const bool touched = !SKIP || line_any(live && (G.x != 0.f || G.y != 0.f || G.z != 0.f || G.w != 0.f));
+        if (!live) continue;
+        if (st_p) st_hint(p + i, P, pol);
+        if (st_m) __stcs(m + i, M);
+        if (st_v) __stcs(v + i, V);
         if (HAS_ABS && touched) {
             A.x += fabsf(G.x); A.y += fabsf(G.y); A.z += fabsf(G.z); A.w += fabsf(G.w);
             __stcs(ga + i, A);
@@ -122,8 +137,10 @@ __global__ void __launch_bounds__(256) k_adam_slab(const SlabPtrs sp, float4* p_
     const int64_t n4 = end4 - begin4;
     const bool rev = s.reverse;
     float4* const p = sp.grids[0];
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += stride) {
-        const int64_t i = begin4 + (rev ? n4 - 1 - k : k);
+    for (int64_t k0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); k0 < n4; k0 += stride) {      // uniform trip count, see k_adam
+        const int64_t k = k0 + (threadIdx.x & 31u);
+        const bool live = k < n4;
+        const int64_t i = begin4 + (live ? (rev ? n4 - 1 - k : k) : 0);
         float4 P = p[i], G = g[i], M = __ldcs(m + i), V = __ldcs(v + i), A;
         if (ga) A = __ldcs(ga + i);
         const float4 P0 = P, M0 = M, V0 = V;
@@ -133,7 +150,12 @@ __global__ void __launch_bounds__(256) k_adam_slab(const SlabPtrs sp, float4* p_
         adam1(P.w, G.w, M.w, V.w, s, bc);
         // replicas hold identical bits, so a parameter that did not change (a cell never touched, or an update below half an ulp)
         // need not cross NVLink at all; the same goes for untouched moments and the local HBM
-        if (differs(P, P0)) {
+        const bool all = !s.skip_same;
+        const bool st_p = all || line_any(live && differs(P, P0)), st_m = all || line_any(live && differs(M, M0)),
+                   st_v = all || line_any(live && differs(V, V0));
+        const bool touched = line_any(live && (G.x != 0.f || G.y != 0.f || G.z != 0.f || G.w != 0.f));
+        if (!live) continue;
+        if (st_p) {
             if (MC) {
                 multimem_st(p_mc + i, P);                            // one store, replicated into every replica by the switch
             } else {
@@ -142,9 +164,9 @@ __global__ void __launch_bounds__(256) k_adam_slab(const SlabPtrs sp, float4* p_
                     if (r < world) sp.grids[r][i] = P;
             }
         }
-        if (differs(M, M0)) __stcs(m + i, M);
-        if (differs(V, V0)) __stcs(v + i, V);
-        if (G.x != 0.f || G.y != 0.f || G.z != 0.f || G.w != 0.f) {  // untouched cell: |g| adds nothing, gradient already clear
+        if (st_m) __stcs(m + i, M);
+        if (st_v) __stcs(v + i, V);
+        if (touched) {                                               // untouched line: |g| adds nothing, gradient already clear
             if (ga) { A.x += fabsf(G.x); A.y += fabsf(G.y); A.z += fabsf(G.z); A.w += fabsf(G.w); __stcs(ga + i, A); }
             g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -161,8 +183,10 @@ static int resident_blocks(const void* kernel, int cap_per_sm, int64_t want) {
     return (int)(want < resident ? (want < 1 ? 1 : want) : resident);
 }
 
-cudaError_t launch_adam_slab(const PlxAdamSlab& a, const AdamScalars& s, cudaStream_t st) {
+cudaError_t launch_adam_slab(const PlxAdamSlab& a, const AdamScalars& s_in, cudaStream_t st) {
     const int64_t begin4 = a.begin / 4, end4 = a.end / 4;
+    AdamScalars s = s_in;
+    s.skip_same = tuning().adam_skip_same != 0;          // auto = on
     SlabPtrs sp;
     for (int r = 0; r < PLX_MAX_PEERS; ++r)
         sp.grids[r] = r < a.world ? (float4*)a.grids[(a.rank + r) % a.world] : nullptr;     // local replica first
@@ -175,7 +199,7 @@ cudaError_t launch_adam_slab(const PlxAdamSlab& a, const AdamScalars& s, cudaStr
     const int64_t want = (end4 - begin4 + 255) / 256;
     const bool mc = a.grid_mc != nullptr;
     // 4 resident blocks per SM like the single-GPU optimiser; an empty slab still runs one block for the step tail
-    const int blocks = mc ? resident_blocks((const void*)k_adam_slab<true>, 4, want) : resident_blocks((const void*)k_adam_slab<false>, 4, want);
+    const int blocks = mc ? resident_blocks((const void*)k_adam_slab<true>, tuning().adam_blocks_per_sm, want) : resident_blocks((const void*)k_adam_slab<false>, tuning().adam_blocks_per_sm, want);
     if (mc) k_adam_slab<true><<<blocks, 256, 0, st>>>(sp, (float4*)a.grid_mc, a.world, (float4*)a.grad, (float4*)a.exp_avg, (float4*)a.exp_avg_sq,
                                                      (float4*)a.grad_abs_sum, begin4, end4, s, tail, a.err);
     else    k_adam_slab<false><<<blocks, 256, 0, st>>>(sp, nullptr, a.world, (float4*)a.grad, (float4*)a.exp_avg, (float4*)a.exp_avg_sq,
@@ -350,7 +374,7 @@ static cudaError_t launch_adam_vec(float4* p, float4* g, float4* m, float4* v, f
     // 256-thread blocks per SM, grid-stride over the rest (measured: 128^3 4 -> 88.6 us per step, 5 / 6 flat; 256^3 3 -> 424 us,
     // 4 -> 410, 5 -> 410)
     constexpr bool SKIP = HAS_ABS || ZERO;
-    const int blocks = resident_blocks((const void*)k_adam<HAS_ABS, ZERO, SKIP>, 4, (n4 + 255) / 256);
+    const int blocks = resident_blocks((const void*)k_adam<HAS_ABS, ZERO, SKIP>, tuning().adam_blocks_per_sm, (n4 + 255) / 256);
     k_adam<HAS_ABS, ZERO, SKIP><<<blocks, 256, 0, st>>>(p, g, m, v, ga, n4, s, tail);
     return cudaGetLastError();
 }
@@ -363,6 +387,7 @@ cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int
     AdamScalars s = s_in;
     s.keep_p = l2_keep_ok(n / 4);            // parameters tagged evict_last when grid + gradient fit the L2 (measured: +1.3 %)
     s.keep_g = false;                        // the same tag on the gradient lost 3 us on C2
+    s.skip_same = tuning().adam_skip_same < 0 ? !l2_keep_ok(n / 4) : tuning().adam_skip_same != 0;
     const bool aligned = ((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                          ((uintptr_t)v % 16 == 0) && (!gabs || (uintptr_t)gabs % 16 == 0);
     const int64_t n4 = aligned ? n / 4 : 0;

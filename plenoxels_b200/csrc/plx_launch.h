@@ -10,6 +10,16 @@ namespace plx {
 
 constexpr int MAX_WARPS_PER_BLOCK = 8;
 
+// Tuning switches for A/B measurements (plx_tune in the ABI; tools/ and tests only).  Defaults = the measured optimum.
+struct Tuning {
+    int adam_skip_same = -1;     // Adam kernels: do not store lines of parameters / moments that did not change (-1 = auto: always in
+                                 // the multi-GPU slab kernel, where they would cross NVLink; on one GPU only for grids beyond the L2 —
+                                 // 256^3: 399 -> 387 us per step, 128^3 where every line changes: 89.5 -> 90.6)
+    int adam_blocks_per_sm = 4;  // resident 256-thread blocks per SM of the Adam kernels
+    int train_wpb = 4;           // warps per block of the fused training march
+};
+Tuning& tuning();
+
 cudaError_t launch_render_fwd(const PlxRenderFwd& a, cudaStream_t st);
 cudaError_t launch_render_bwd(const PlxRenderBwd& a, cudaStream_t st);
 bool render_train_supported(const PlxRenderTrain& a);
@@ -24,6 +34,7 @@ struct AdamScalars {
     float neg_step_size;     // -lr / (1 - beta1^step)
     bool keep_p, keep_g;     // L2 evict_last tags for parameters / gradient (set by launch_adam)
     bool reverse;            // walk the arrays from the top down (odd steps): the tail the previous step left in L2 is read first
+    bool skip_same;          // do not store values that did not change (set by the launchers from tuning())
 };
 // what one thread of the optimiser kernel does besides Adam: publish this step's loss to pinned host memory
 // { float loss; int32 step } and clear the other loss slot for the next step

@@ -422,7 +422,7 @@ cudaError_t launch_render_train(const PlxRenderTrain& a_in, cudaStream_t st) {
     PlxRenderTrain a = a_in;
     a.march.flags = (a.march.flags & 0xffffu) | l2_keep_flags(a.march);
     const int spl = a.march.num_samples >= 128 ? 2 : 1;
-    int wpb = 4;
+    int wpb = tuning().train_wpb;
     while (wpb > 1 && render_train_smem(a.march.num_samples, spl, wpb) > 200 * 1024) wpb >>= 1;
     const size_t smem = render_train_smem(a.march.num_samples, spl, wpb);
     const int W = 32 * spl;

@@ -198,35 +198,11 @@ def make_signatures(name):
     print(name, len(out), "functions")
 
 
-def write_fit_dataset(root, n_views=8, H=32, seed=51):
-    """Synthetic NeRF-format dataset (RGBA PNGs + transforms_train.json) from seeds only, so the GPU box can rebuild the very
-    same files: a soft coloured ball on a transparent background seen from `n_views` look-at cameras."""
-    import json
-    from PIL import Image
-    os.makedirs(os.path.join(root, "train"), exist_ok=True)
-    poses = synth.lookat_poses(n_views)
-    rng = np.random.default_rng(seed)
-    yy, xx = np.mgrid[0:H, 0:H]
-    frames = []
-    for i in range(n_views):
-        r2 = ((xx - H / 2 + 0.5) ** 2 + (yy - H / 2 + 0.5) ** 2) / (0.33 * H) ** 2
-        a = np.clip(1.2 - r2, 0.0, 1.0)
-        img = np.zeros((H, H, 4))
-        img[..., :3] = (0.35 + 0.65 * rng.random((1, 1, 3))) * a[..., None] + 0.1 * rng.random((H, H, 3)) * a[..., None]
-        img[..., 3] = a
-        Image.fromarray((img.clip(0, 1) * 255).astype(np.uint8), "RGBA").save(os.path.join(root, "train", f"r_{i}.png"))
-        frames.append({"file_path": f"./train/r_{i}", "rotation": 0.1, "transform_matrix": poses[i].tolist()})
-    with open(os.path.join(root, "transforms_train.json"), "w") as f:
-        json.dump({"camera_angle_x": synth.CAMERA_ANGLE_X, "frames": frames}, f)
-    return os.path.join(root, "train"), os.path.join(root, "transforms_train.json")
-
-
-FIT_ARGS = dict(gridsize=[96, 96, 96], points_distance_original=synth.GRID_EXTENT / 96, number_of_rays=48, num_samples=96,
-                delta_step=6.0 / 96, lr=0.0075, tv=1e-5, beta=5e-3, steps=240, even_spread=False)
+from tests.helpers import FIT_ARGS, write_fit_dataset      # noqa: E402  (shared with the GPU test that replays the fit)
 
 
 def make_fit(name):
-    """The UNMODIFIED scripts/train.py::fit (:68-210) on the CPU: 8 synthetic PNGs, 96^3 grid, 240 steps = the whole
+    """The UNMODIFIED scripts/train.py::fit (:68-210) on the CPU: 8 synthetic PNGs, 128^3 grid, 240 steps = the whole
     progressive-growing schedule (46 pooling windows x 5 steps) plus 10 full-resolution steps, train.py's default tv / beta,
     the uv stream of torch.manual_seed(123).  Frozen: a strided subset of the saved grid / grid_grad plus whole-array sums."""
     import tempfile
@@ -246,7 +222,7 @@ def make_fit(name):
         ref_train.fit(path=path, transform_path=tpath, save_path=save, device="cpu", progressive_growing=True, **FIT_ARGS)
         ck = torch.load(save)
     g, gg = ck["grid"].numpy(), ck["grid_grad"].numpy()
-    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), grid_subset=g[::3, ::3, ::3].copy(), grad_subset=gg[::3, ::3, ::3].copy(),
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), grid_subset=g[::4, ::4, ::4].copy(), grad_subset=gg[::4, ::4, ::4].copy(),
                         grid_sum=g.astype(np.float64).reshape(-1, 4).sum(0), grid_abs_sum=np.abs(g).astype(np.float64).reshape(-1, 4).sum(0),
                         grad_sum=gg.astype(np.float64).reshape(-1, 4).sum(0), grid_max=np.float64(np.abs(g).max()),
                         grad_max=np.float64(gg.max()), occupied=np.int64((g[..., 3] > 0.1).sum()), seed=np.int64(123),
@@ -286,7 +262,7 @@ if __name__ == "__main__":
         make_fullsize("full_c3", "c3")
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fit":             # the reference's whole fit() on the CPU (a few minutes)
-        make_fit("fit_g96")
+        make_fit("fit_g128")
         sys.exit(0)
     make_inference("inference_g24")
     make_splat("splat_g40")

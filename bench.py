@@ -121,6 +121,25 @@ class ClockSampler:
             self._thread.join()
             self._thread = None
 
+    def nvlink_kib(self):
+        """Aggregate NVLink payload / raw byte counters of this GPU in KiB (NVML field values, scope = all links), or None."""
+        if self.nv is None:
+            return None
+        nv = self.nv
+        try:
+            ids = [(nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xffffffff), (nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xffffffff),
+                   (nv.NVML_FI_DEV_NVLINK_THROUGHPUT_RAW_TX, 0xffffffff), (nv.NVML_FI_DEV_NVLINK_THROUGHPUT_RAW_RX, 0xffffffff)]
+            vals = nv.nvmlDeviceGetFieldValues(self.h, ids)
+            out = {}
+            for name, v in zip(("data_tx", "data_rx", "raw_tx", "raw_rx"), vals):
+                if v.nvmlReturn != 0:
+                    return None
+                out[name] = int(v.value.ullVal)
+            return out
+        except Exception as e:      # noqa: BLE001
+            log(f"[bench] NVLink counters unavailable ({type(e).__name__}: {e})")
+            return None
+
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
@@ -433,6 +452,26 @@ def measure_training(cx: Ctx, sc: synth.Scene, K: int, W: int, repeats: int, e2e
     ms_med = float(np.median(ms))
     out.update(value=sc.n_rays * cx.world * K / (ms_med * 1e-3), ms_per_step=ms_med / K, repeats=spread(ms, K),
                final_loss=float(tr.loss.item()), launches_per_step=tr.launches_per_step)
+    # ---- NVLink traffic actually moved per step (NVML byte counters of this GPU around a long untimed run of the same steps)
+    if cx.world > 1:
+        n_nv = 1500
+        cx.barrier()
+        time.sleep(0.3)
+        nv0 = cx.sampler.nvlink_kib()
+        t0 = time.perf_counter()
+        for i in range(n_nv):
+            tr.step(uv_dev[i % n_batches])
+        tr.flush()
+        cx.barrier()
+        wall = time.perf_counter() - t0
+        time.sleep(0.3)
+        nv1 = cx.sampler.nvlink_kib()
+        if nv0 and nv1:
+            per = {k: (nv1[k] - nv0[k]) * 1024.0 / n_nv for k in nv0}
+            out["nvlink_measured"] = {"bytes_per_step": per, "steps": n_nv, "ms_per_step_wall": 1e3 * wall / n_nv,
+                                      "source": "NVML NVLINK_THROUGHPUT_DATA / RAW counters of rank 0's GPU, all links",
+                                      "raw_gbs": {d: per["raw_" + d] / (out["ms_per_step"] * 1e-3) / 1e9 for d in ("tx", "rx")},
+                                      "data_gbs": {d: per["data_" + d] / (out["ms_per_step"] * 1e-3) / 1e9 for d in ("tx", "rx")}}
     # ---- region 2: end to end from pinned host buffers, loss read on the host every step ("e2e")
     if e2e:
         tr2 = make_trainer(cx, sc, dev_scene, **trainer_kw)
@@ -469,6 +508,8 @@ def measure_training(cx: Ctx, sc: synth.Scene, K: int, W: int, repeats: int, e2e
     kms = phase_times(cx, tr3, uv_dev, min(K, 64))
     cx.sampler.stop()
     out["roofline"] = roofline_of(cx, kms, m_in, sc.n_rays, cells, tr3, sc.name, out["ms_per_step"])
+    if "nvlink_measured" in out:
+        out["roofline"]["nvlink_measured"] = out.pop("nvlink_measured")
     out["parallelism"] = ("single GPU" if cx.world == 1 else f"ray-sharded replicas x{cx.world}, " + (
         {"push": "push exchange: the march reduces every touched cell into the slab owner's buffer over NVLink, slab Adam, parameters "
                  "stored to every replica" + (" through NVLS multicast" if tr3.multicast else " per peer"),

@@ -21,7 +21,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from .data_processing import load_data, load_image_data_from_path
+from .data_processing import load_data, load_image_bytes_from_path
 
 STEPS_PER_FIELD = 5                                       # scripts/train.py:92
 
@@ -51,7 +51,7 @@ class GridFitter:
         self.gridsize = [int(g) for g in gridsize]
         self.pd0 = points_distance
         self.poses = poses.to(dev).float().contiguous()
-        self.imgs = imgs.to(dev).float().contiguous()
+        self.imgs = (imgs if imgs.dtype == torch.uint8 else imgs.float()).to(dev).contiguous()    # uint8: converted per fetch
         self.fov = float(fov)
         self.S, self.delta, self.lr = int(num_samples), delta_step, lr
         self.tv, self.beta = float(tv), float(beta)
@@ -118,7 +118,7 @@ class GridFitter:
 def fit(gridsize, points_distance_original, number_of_rays, num_samples, delta_step, lr, tv, beta, steps, even_spread, path,
         transform_path, save_path, device, progressive_growing=True, log_every=50):
     """Same arguments and effect as the reference's `fit` (scripts/train.py:68-210); `log_every` is the only addition."""
-    data, imgs = load_image_data_from_path(path, transform_path)                                      # :73
+    data, imgs = load_image_bytes_from_path(path, transform_path)        # :73, pixels stay uint8 (converted in the kernel)
     poses, _, fov = load_data(data)                                                                   # :74
     fitter = GridFitter(gridsize, points_distance_original, poses, fov, imgs, number_of_rays, num_samples, delta_step, lr,
                         tv=tv, beta=beta, even_spread=even_spread, progressive_growing=progressive_growing, device=device)

@@ -453,7 +453,7 @@ def measure_training(cx: Ctx, sc: synth.Scene, K: int, W: int, repeats: int, e2e
     out.update(value=sc.n_rays * cx.world * K / (ms_med * 1e-3), ms_per_step=ms_med / K, repeats=spread(ms, K),
                final_loss=float(tr.loss.item()), launches_per_step=tr.launches_per_step)
     # ---- NVLink traffic actually moved per step (NVML byte counters of this GPU around a long untimed run of the same steps)
-    if cx.world > 1:
+    if cx.world > 1 and cx.sampler.nvlink_kib() is not None:      # N/A on this pool's B200 boxes (NVML_ERROR_NOT_SUPPORTED): then skipped
         n_nv = 1500
         cx.barrier()
         time.sleep(0.3)

@@ -279,9 +279,11 @@ __device__ __forceinline__ float train_ray(const PlxRenderTrain& a, const Geo& g
                 // push exchange: every reduction is a 16-byte packet on NVLink, so runs that continue in the NEXT lane are
                 // merged too — a lane hands the sum of its last entry to its neighbour when that one's first entry is the same
                 // cell (samples enter cells monotonically along the ray, so equal cells are adjacent).  One round takes the
-                // reductions per sample from 0.8 to ~0.6 at delta = pd / 2.  A handed-off entry keeps its index with a zero
-                // sum: whatever the previous lane hands to IT in the same round is then reduced from here, so nothing is lost
-                // however long the run is.
+                // reductions per sample from 0.8 to ~0.6 at delta = pd / 2 (N = 8: 131 -> 116 us per step).  Not used for the
+                // local gradient buffer: there the L2 absorbs the extra atomics and the shuffles cost more than they save (C2
+                // step 89.5 -> 91.7 us, although the kernel alone profiles faster under ncu).  A handed-off entry keeps its
+                // index with a zero sum: whatever the previous lane hands to IT in the same round is then reduced from here,
+                // so nothing is lost however long the run is.
                 int fi = -1, la = -1;                                   // first / last surviving entry of this lane
 #pragma unroll
                 for (int j = SPL - 1; j >= 0; --j) if (lin[j] >= 0) fi = j;

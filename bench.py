@@ -258,6 +258,8 @@ class Ctx:
         self.peak, self.peak_src = measured_peak()
         self.multi = os.environ.get("PLX_MULTI", "peer") if self.world > 1 else "single"     # peer | nccl
         self.exchange = os.environ.get("PLX_EXCHANGE") or None                               # push | pull | None = auto
+        mc = os.environ.get("PLX_MULTICAST")                                                 # 0 | 1 | unset = the trainer's default
+        self.multicast = None if mc is None else mc == "1"
         self.sampler = ClockSampler(self.local_rank)
 
     def barrier(self):
@@ -281,7 +283,7 @@ def make_trainer(cx: Ctx, sc: synth.Scene, dev_scene: dict, **kw):
     k.update(kw)
     if cx.multi == "peer":
         try:
-            return PeerVoxelTrainer(*args_, exchange=cx.exchange, **k)
+            return PeerVoxelTrainer(*args_, exchange=cx.exchange, multicast=cx.multicast, **k)
         except Exception as e:          # symmetric memory unavailable on this box: NCCL all-reduce path (rendezvous failures are
             log(f"[bench] peer-memory trainer unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce trainer")
             ok = torch.zeros(1, device=cx.dev)           # collective, so every rank lands here together)

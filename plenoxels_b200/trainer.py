@@ -441,8 +441,11 @@ class PeerVoxelTrainer(VoxelTrainer):
             sy.err = self._err
         self._flush_epoch = 0
 
-        # NVLS multicast mappings, when the fabric offers them (in-switch reduce / replicate); by default used from 4 ranks
-        # up (at N=2 the switch round trip costs more than it saves: 93 vs 60 us)
+        # NVLS multicast mappings, when the fabric offers them (in-switch reduce / replicate).  Default: pull exchange from 4
+        # ranks up (in-switch reduction of the gathered gradients; at N=2 the switch round trip costs more than it saves: 93 vs
+        # 60 us); push exchange never — a multicast store also loops back into the sender's own replica, so every GPU receives
+        # the WHOLE grid (16 B x cells) instead of the other ranks' slabs; measured per-peer vs multicast stores, us per step:
+        # C2 110 vs 116 (N=4), 115.5 vs 116.5 (N=8); C3 379 vs 433 (N=4), 418 vs 427 (N=8)
         def mc_ptr(h):
             try:
                 return int(h.multicast_ptr or 0)
@@ -450,7 +453,7 @@ class PeerVoxelTrainer(VoxelTrainer):
                 return 0
         mc_grid, mc_grads = mc_ptr(self._h_grid), [mc_ptr(h) for h in self._h_grads]
         have_mc = bool(mc_grid) and (self.exchange == "push" or all(mc_grads))
-        self.multicast = have_mc and (self.world >= 4 if multicast is None else bool(multicast))
+        self.multicast = have_mc and ((self.exchange == "pull" and self.world >= 4) if multicast is None else bool(multicast))
         if multicast and not have_mc:
             raise L.PlxError("multicast requested but the symmetric-memory handles expose no multicast mapping")
         if self.exchange == "push":

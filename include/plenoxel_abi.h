@@ -392,7 +392,7 @@ int plx_splat_view(const float* grid, const int32_t dims[3], float points_distan
 
 /*
  * A/B switches for measurements (tools/ and tests; process-wide, results are identical either way — they only move launch
- * shapes and skip redundant stores): "adam_skip_same" (-1 = auto), "adam_blocks_per_sm" (4), "train_wpb" (4).
+ * shapes and skip redundant stores): "adam_skip_same" (-1 = auto), "adam_blocks_per_sm" (4), "train_wpb" (4), "pdl" (1).
  */
 int plx_tune(const char* name, int32_t value);
 

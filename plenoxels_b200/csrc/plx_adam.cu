@@ -64,6 +64,7 @@ template <bool HAS_ABS, bool ZERO, bool SKIP>
 __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                               float4* __restrict__ v, float4* __restrict__ ga, int64_t n4,
                                               const AdamScalars s, const StepTail tail) {
+    grid_dependency_wait();                  // launched behind the march's tail: its gradient and loss are complete from here on
     step_tail(tail);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const FastDiv bc = make_fastdiv(s.bc2_sqrt);
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(256) k_adam_slab(const SlabPtrs sp, float4* p_
                                                    float4* __restrict__ m, float4* __restrict__ v, float4* __restrict__ ga,
                                                    int64_t begin4, int64_t end4, const AdamScalars s, const StepTail tail,
                                                    const PlxPeerError err) {
+    grid_dependency_wait();                  // launched behind the barrier kernel's tail (programmatic dependent launch)
     if (peer_failed(err)) return;            // an earlier wait gave up: the gradient slab may be incomplete — store nothing
     step_tail(tail);                         // global loss: every rank's partial is complete since the barrier before this kernel
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -200,11 +202,10 @@ cudaError_t launch_adam_slab(const PlxAdamSlab& a, const AdamScalars& s_in, cuda
     const bool mc = a.grid_mc != nullptr;
     // 4 resident blocks per SM like the single-GPU optimiser; an empty slab still runs one block for the step tail
     const int blocks = mc ? resident_blocks((const void*)k_adam_slab<true>, tuning().adam_blocks_per_sm, want) : resident_blocks((const void*)k_adam_slab<false>, tuning().adam_blocks_per_sm, want);
-    if (mc) k_adam_slab<true><<<blocks, 256, 0, st>>>(sp, (float4*)a.grid_mc, a.world, (float4*)a.grad, (float4*)a.exp_avg, (float4*)a.exp_avg_sq,
-                                                     (float4*)a.grad_abs_sum, begin4, end4, s, tail, a.err);
-    else    k_adam_slab<false><<<blocks, 256, 0, st>>>(sp, nullptr, a.world, (float4*)a.grad, (float4*)a.exp_avg, (float4*)a.exp_avg_sq,
-                                                      (float4*)a.grad_abs_sum, begin4, end4, s, tail, a.err);
-    return cudaGetLastError();
+    if (mc) return launch_pdl(k_adam_slab<true>, (unsigned)blocks, 256u, 0, st, sp, (float4*)a.grid_mc, (int)a.world, (float4*)a.grad, (float4*)a.exp_avg,
+                              (float4*)a.exp_avg_sq, (float4*)a.grad_abs_sum, begin4, end4, s, tail, a.err);
+    return launch_pdl(k_adam_slab<false>, (unsigned)blocks, 256u, 0, st, sp, (float4*)nullptr, (int)a.world, (float4*)a.grad, (float4*)a.exp_avg,
+                      (float4*)a.exp_avg_sq, (float4*)a.grad_abs_sum, begin4, end4, s, tail, a.err);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -218,6 +219,7 @@ struct PeerPtrs {
 __global__ void __launch_bounds__(256) k_adam_peer(PeerPtrs pp, int world, float4* __restrict__ m, float4* __restrict__ v,
                                                    float4* __restrict__ ga, int64_t begin4, int64_t end4, const AdamScalars s,
                                                    const StepTail tail, const PlxPeerSync sync) {
+    grid_dependency_wait();
     peer_wait(sync);                         // every rank's partial gradient (and loss) is complete
     __syncthreads();
     if (peer_failed(sync.err)) return;       // a wait gave up (here or in an earlier kernel): store nothing
@@ -263,6 +265,7 @@ __global__ void __launch_bounds__(256) k_adam_mc(const float4* __restrict__ p_lo
                                                  int64_t begin4, int64_t end4, const AdamScalars s, const StepTail tail,
                                                  const PlxPeerSync sync) {
     constexpr int UNROLL = 2;
+    grid_dependency_wait();
     peer_wait(sync);                         // every rank's partial gradient (and loss) is complete
     __syncthreads();
     if (peer_failed(sync.err)) return;
@@ -315,9 +318,8 @@ cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, const S
     const int64_t n4 = end4 - begin4;
     if (a.grid_mc && a.grad_mc) {
         const int blocks = resident_blocks((const void*)k_adam_mc, 1, (n4 + 511) / 512);
-        k_adam_mc<<<blocks, 256, 0, st>>>((const float4*)a.grids[a.rank], (float4*)a.grid_mc, (const float4*)a.grad_mc, (float4*)a.exp_avg,
-                                          (float4*)a.exp_avg_sq, (float4*)a.grad_abs_sum, begin4, end4, s, tail, a.sync);
-        return cudaGetLastError();
+        return launch_pdl(k_adam_mc, (unsigned)blocks, 256u, 0, st, (const float4*)a.grids[a.rank], (float4*)a.grid_mc, (const float4*)a.grad_mc,
+                          (float4*)a.exp_avg, (float4*)a.exp_avg_sq, (float4*)a.grad_abs_sum, begin4, end4, s, tail, a.sync);
     }
     PeerPtrs pp;
     for (int r = 0; r < PLX_MAX_PEERS; ++r) {          // the local replica first, so that the parameter read (grids[0]) is local
@@ -325,15 +327,15 @@ cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, const S
         pp.grads[r] = r < a.world ? (const float4*)a.grads[(a.rank + r) % a.world] : nullptr;
     }
     const int blocks = resident_blocks((const void*)k_adam_peer, 0, (n4 + 255) / 256);
-    k_adam_peer<<<blocks, 256, 0, st>>>(pp, a.world, (float4*)a.exp_avg, (float4*)a.exp_avg_sq, (float4*)a.grad_abs_sum, begin4, end4,
-                                        s, tail, a.sync);
-    return cudaGetLastError();
+    return launch_pdl(k_adam_peer, (unsigned)blocks, 256u, 0, st, pp, (int)a.world, (float4*)a.exp_avg, (float4*)a.exp_avg_sq, (float4*)a.grad_abs_sum,
+                      begin4, end4, s, tail, a.sync);
 }
 
 // cross-GPU barrier over peer-mapped flag arrays (see plenoxel_abi.h)
 struct FlagPtrs { int32_t* p[PLX_MAX_PEERS]; };
 
 __global__ void k_peer_barrier(FlagPtrs f, int rank, int world, int channel, int epoch, const PlxPeerError err) {
+    grid_dependency_wait();                  // everything this rank enqueued before the barrier is complete and visible
     const int r = threadIdx.x;
     if (r < world) {
         int32_t* theirs = f.p[r] + channel * PLX_MAX_PEERS + rank;
@@ -347,8 +349,7 @@ cudaError_t launch_peer_barrier(int32_t* const* flags, int rank, int world, int 
                                 cudaStream_t st) {
     FlagPtrs f;
     for (int r = 0; r < PLX_MAX_PEERS; ++r) f.p[r] = r < world ? flags[r] : nullptr;
-    k_peer_barrier<<<1, 32, 0, st>>>(f, rank, world, channel, epoch, err);
-    return cudaGetLastError();
+    return launch_pdl(k_peer_barrier, 1u, 32u, 0, st, f, rank, world, channel, epoch, err);
 }
 
 // scalar tail / unaligned fallback
@@ -375,8 +376,7 @@ static cudaError_t launch_adam_vec(float4* p, float4* g, float4* m, float4* v, f
     // 4 -> 410, 5 -> 410)
     constexpr bool SKIP = HAS_ABS || ZERO;
     const int blocks = resident_blocks((const void*)k_adam<HAS_ABS, ZERO, SKIP>, tuning().adam_blocks_per_sm, (n4 + 255) / 256);
-    k_adam<HAS_ABS, ZERO, SKIP><<<blocks, 256, 0, st>>>(p, g, m, v, ga, n4, s, tail);
-    return cudaGetLastError();
+    return launch_pdl(k_adam<HAS_ABS, ZERO, SKIP>, (unsigned)blocks, 256u, 0, st, p, g, m, v, ga, n4, s, tail);
 }
 
 __global__ void k_step_tail_only(const StepTail tail) { step_tail(tail); }

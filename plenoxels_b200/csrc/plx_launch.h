@@ -17,8 +17,27 @@ struct Tuning {
                                  // 256^3: 399 -> 387 us per step, 128^3 where every line changes: 89.5 -> 90.6)
     int adam_blocks_per_sm = 4;  // resident 256-thread blocks per SM of the Adam kernels
     int train_wpb = 4;           // warps per block of the fused training march
+    int pdl = 1;                 // programmatic dependent launch of the march / optimiser kernels (launch latency behind the previous kernel's tail)
 };
 Tuning& tuning();
+
+// Launch `kernel` so that it may be scheduled while the previous kernel of the stream drains (programmatic stream
+// serialisation).  The kernel must execute grid_dependency_wait() (plx_device.cuh) before it touches anything the previous
+// kernel wrote; with that, results are identical to a plain launch.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned blocks, unsigned threads, size_t smem, cudaStream_t st, Args... args) {
+    if (!tuning().pdl) {
+        kernel<<<blocks, threads, smem, st>>>(args...);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 cudaError_t launch_render_fwd(const PlxRenderFwd& a, cudaStream_t st);
 cudaError_t launch_render_bwd(const PlxRenderBwd& a, cudaStream_t st);

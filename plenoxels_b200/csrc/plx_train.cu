@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(128, MODE == PLX_NEAREST ? 8 : 5) k_render_tra
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const PlxMarch& m = a.march;
     if (threadIdx.x == 0) { s_loss = 0.f; s_done = 0; }
+    grid_dependency_wait();                  // launched behind the optimiser's tail: its parameter stores are visible from here on
     if (PEER && threadIdx.x < PLX_MAX_PEERS) s_peer[threadIdx.x] = a.peer_grad.grads[threadIdx.x];
     peer_wait(a.sync);                       // multi-GPU: every peer has stored its slab of the previous step's parameters
     __syncthreads();                         // every warp arrives here at once: free
@@ -412,8 +413,7 @@ static cudaError_t launch_train_inst(const PlxRenderTrain& a, unsigned blocks, i
         cudaError_t e = cudaFuncSetAttribute(k_render_train<MODE, FAST, SPL, PIPE, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_render_train<MODE, FAST, SPL, PIPE, PEER><<<blocks, wpb * 32, smem, st>>>(a, lin_words, warp_words);
-    return cudaGetLastError();
+    return launch_pdl(k_render_train<MODE, FAST, SPL, PIPE, PEER>, blocks, (unsigned)(wpb * 32), smem, st, a, lin_words, warp_words);
 }
 
 // Launch shape (measured on C2 / B200): 4 warps per block, 8 blocks per SM (64 registers), 2 samples per lane

@@ -28,5 +28,5 @@ for rep in range(2):
 run("skip_same=1 bps=6", adam_skip_same=1, adam_blocks_per_sm=6)
 run("skip_same=0 bps=6", adam_skip_same=0, adam_blocks_per_sm=6)
 L.check(lib.plx_tune(b"adam_skip_same", 1)); L.check(lib.plx_tune(b"adam_blocks_per_sm", 4))
-for wpb in (4, 2):
-    run(f"train_wpb={wpb}", train_wpb=wpb)
+for pdl in (1, 0, 1, 0):
+    run(f"pdl={pdl}", pdl=pdl)

@@ -210,6 +210,28 @@ typedef struct PlxPeerSync {
     PlxPeerError err;        /* where a wait that gave up is recorded (see PlxPeerError); all-zero = ~10 s bound, no record */
 } PlxPeerSync;
 
+/*
+ * Device-resident step state: lets ONE captured CUDA graph replay every training step (scripts/train.py:104-191 has nothing
+ * that changes from step to step except the uv draw, the loss slot parity and Adam's two bias-corrected scalars).  When
+ * PlxTrainStep.replay != NULL the kernels take the step number from device memory instead of from `step`:
+ *   this step  = *step_dev + 1                         (the march picks loss[step & 1]; the optimiser its walk direction)
+ *   Adam scalars = table[step - table_base - 1]        = { sqrt(1 - beta2^step), -lr / (1 - beta1^step) } as fp32, formed on the
+ *                                                        host in double exactly as plx_adam_step forms them (plx_adam_table)
+ * and the LAST block of the optimiser kernel to finish stores the new step number into *step_dev (block_counter: one device
+ * int32, zero before the first step, returns to zero by itself).  table_len entries; the caller refills the table (outside
+ * the graph) before step - table_base exceeds it — the optimiser kernel records error code 0x7ab1e in *step_dev's sign bit
+ * otherwise: it leaves *step_dev = -1 and applies nothing.
+ */
+typedef struct PlxReplayState {
+    int32_t* step_dev;
+    const float* table;      /* 2 floats per step */
+    int64_t table_base;
+    int32_t table_len;
+    int32_t* block_counter;
+} PlxReplayState;
+/* fills `table_host` (2 * n floats, HOST memory) for the steps first_step .. first_step + n - 1 */
+int plx_adam_table(double lr, double beta1, double beta2, int64_t first_step, int32_t n, float* table_host);
+
 typedef struct PlxRenderTrain {
     PlxMarch march;
     PlxRays rays;
@@ -222,6 +244,8 @@ typedef struct PlxRenderTrain {
     float grad_scale, loss_scale, beta_over_m;
     PlxPeerSync sync;        /* optional cross-GPU wait at the start / signal at the end (all-zero = none) */
     PlxPeerGrad peer_grad;   /* optional multi-GPU push exchange (world == 0: gradient goes to grad_grid) */
+    const int32_t* step_dev; /* optional (graph replay): `loss` then points at TWO slots and the march adds into
+                                loss[(*step_dev + 1) & 1] */
 } PlxRenderTrain;
 int plx_render_train(const PlxRenderTrain* args, void* stream);
 
@@ -440,6 +464,8 @@ typedef struct PlxTrainStep {
     /* optional (multi-GPU): push exchange — the march reduces into the slab owners' buffers instead of `grad` (PlxPeerGrad) */
     const PlxPeerGrad* peer_grad;
     int32_t img_format;       /* PLX_IMG_F32 | PLX_IMG_U8 */
+    /* optional: device-resident step state for CUDA-graph replay (see PlxReplayState); `step` is then ignored */
+    const PlxReplayState* replay;
 } PlxTrainStep;
 int plx_train_step(const PlxTrainStep* args, int32_t phase, void* stream);
 

@@ -75,10 +75,16 @@ class PlxPeerSync(C.Structure):
                 ("signal_epoch", C.c_int32), ("block_counter", c_void), ("err", PlxPeerError)]
 
 
+class PlxReplayState(C.Structure):
+    _fields_ = [("step_dev", c_void), ("table", c_void), ("table_base", C.c_int64), ("table_len", C.c_int32),
+                ("block_counter", c_void)]
+
+
 class PlxRenderTrain(C.Structure):
     _fields_ = [("march", PlxMarch), ("rays", PlxRays), ("targets", c_void), ("gen", PlxRayGen), ("grid", c_void),
                 ("grad_grid", c_void), ("rgba", c_void), ("loss", c_void), ("grad_scale", C.c_float),
-                ("loss_scale", C.c_float), ("beta_over_m", C.c_float), ("sync", PlxPeerSync), ("peer_grad", PlxPeerGrad)]
+                ("loss_scale", C.c_float), ("beta_over_m", C.c_float), ("sync", PlxPeerSync), ("peer_grad", PlxPeerGrad),
+                ("step_dev", c_void)]
 
 
 class PlxAdamPeer(C.Structure):
@@ -111,7 +117,7 @@ class PlxTrainStep(C.Structure):
                 ("beta_over_m", C.c_float),
                 ("dirs", c_void), ("targets", c_void), ("rgba", c_void), ("grad_rgba", c_void), ("tcarry", c_void),
                 ("loss", c_void), ("render_sync", C.POINTER(PlxPeerSync)), ("peer_grad", C.POINTER(PlxPeerGrad)),
-                ("img_format", C.c_int32)]
+                ("img_format", C.c_int32), ("replay", C.POINTER(PlxReplayState))]
 
 
 # name -> (restype, argtypes); every symbol include/plenoxel_abi.h declares
@@ -124,6 +130,7 @@ PROTOTYPES = {
     "plx_render_train": (C.c_int, [C.POINTER(PlxRenderTrain), c_void]),
     "plx_adam_step": (C.c_int, [c_void, c_void, c_void, c_void, c_void, C.c_int64, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_int64, C.c_int32, c_void]),
+    "plx_adam_table": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int32, C.POINTER(C.c_float)]),
     "plx_adam_step_peer": (C.c_int, [C.POINTER(PlxAdamPeer), c_void]),
     "plx_adam_step_slab": (C.c_int, [C.POINTER(PlxAdamSlab), c_void]),
     "plx_slab_partition": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_int64),

@@ -167,6 +167,17 @@ int plx_render_train(const PlxRenderTrain* a, void* stream) {
     return cuda_result(plx::launch_render_train(*a, (cudaStream_t)stream), "plx_render_train");
 }
 
+int plx_adam_table(double lr, double beta1, double beta2, int64_t first_step, int32_t n, float* table_host) {
+    if (!table_host) return fail(PLX_E_NULL, "table_host is NULL");
+    if (first_step < 1 || n < 0) return fail(PLX_E_SHAPE, "steps count from 1");
+    for (int32_t i = 0; i < n; ++i) {        // the same double-precision scalar math as adam_scalars() below
+        const double step = (double)(first_step + i);
+        table_host[2 * i] = (float)std::sqrt(1.0 - std::pow(beta2, step));
+        table_host[2 * i + 1] = (float)(-(lr / (1.0 - std::pow(beta1, step))));
+    }
+    return PLX_OK;
+}
+
 static plx::AdamScalars adam_scalars(double lr, double beta1, double beta2, double eps, int64_t step) {
     // python-double scalar math of torch/optim/adam.py, cast to fp32 where ATen casts the Scalar
     const double bc1 = 1.0 - std::pow(beta1, (double)step);
@@ -458,12 +469,17 @@ static int train_step_impl(const PlxTrainStep* a, const float* uv, void* result_
         t.gen.poses = a->poses; t.gen.fov = a->fov; t.gen.uv = uv; t.gen.rays_per_cam = a->rays_per_cam;
         t.gen.img_format = a->img_format;
         if (a->peer_grad) t.peer_grad = *a->peer_grad;
-        t.grid = a->grid; t.grad_grid = a->grad; t.rgba = a->rgba; t.loss = loss_now;
+        if (a->replay) {
+            if (!a->replay->step_dev || !a->replay->table || !a->replay->block_counter || a->replay->table_len <= 0)
+                return fail(PLX_E_NULL, "train step: incomplete replay state");
+            t.step_dev = a->replay->step_dev;   // the kernel picks the loss slot from the device-resident step number
+        }
+        t.grid = a->grid; t.grad_grid = a->grad; t.rgba = a->rgba; t.loss = a->replay ? a->loss : loss_now;
         t.grad_scale = grad_scale; t.loss_scale = loss_scale; t.beta_over_m = a->beta_over_m;
         if (a->render_sync) t.sync = *a->render_sync;
         const bool synced = t.sync.wait_epoch > 0 || t.sync.signal_epoch > 0;
-        if ((synced || t.peer_grad.world > 0) && !(allow_fused && a->img_h == a->img_w && plx::render_train_supported(t)))
-            return fail(PLX_E_UNSUPPORTED, "train step: render_sync / peer_grad need the fused march (square images, samples within the shared-memory cache)");
+        if ((synced || t.peer_grad.world > 0 || a->replay) && !(allow_fused && a->img_h == a->img_w && plx::render_train_supported(t)))
+            return fail(PLX_E_UNSUPPORTED, "train step: render_sync / peer_grad / replay need the fused march (square images, samples within the shared-memory cache)");
         if (allow_fused && a->img_h == a->img_w && plx::render_train_supported(t)) {
             if ((rc = plx_render_train(&t, stream)) != PLX_OK) return rc;
         } else {
@@ -494,11 +510,18 @@ static int train_step_impl(const PlxTrainStep* a, const float* uv, void* result_
     if (phase & PLX_STEP_OPTIM) {
         const int64_t n = (int64_t)a->march.nx * a->march.ny * a->march.nz * 4;
         if (n > 0 && (!a->grid || !a->grad || !a->exp_avg || !a->exp_avg_sq)) return fail(PLX_E_NULL, "train step: optimiser state is NULL");
-        if (a->step < 1) return fail(PLX_E_SHAPE, "step counts from 1");
+        if (a->step < 1 && !a->replay) return fail(PLX_E_SHAPE, "step counts from 1");
         const plx::StepTail tail{loss_now, loss_next, (float*)result_host, (int32_t)a->step};
+        plx::ReplayArgs rp;
+        if (a->replay) {
+            if (!a->replay->step_dev || !a->replay->table || !a->replay->block_counter || a->replay->table_len <= 0)
+                return fail(PLX_E_NULL, "train step: incomplete replay state");
+            rp.step_dev = a->replay->step_dev; rp.table = a->replay->table; rp.table_base = a->replay->table_base;
+            rp.table_len = a->replay->table_len; rp.block_counter = a->replay->block_counter; rp.loss2 = a->loss;
+        }
         return cuda_result(plx::launch_adam(a->grid, a->grad, a->exp_avg, a->exp_avg_sq, a->grad_abs_sum, n,
-                                            adam_scalars(a->lr, a->beta1, a->beta2, a->eps, a->step), true, tail,
-                                            (cudaStream_t)stream), "plx_train_step(optim)");
+                                            adam_scalars(a->lr, a->beta1, a->beta2, a->eps, a->replay ? 1 : a->step), true, tail,
+                                            (cudaStream_t)stream, rp), "plx_train_step(optim)");
     }
     return PLX_OK;
 }

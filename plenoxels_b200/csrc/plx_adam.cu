@@ -63,8 +63,23 @@ __device__ __forceinline__ bool line_any(bool vote) {
 template <bool HAS_ABS, bool ZERO, bool SKIP>
 __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                               float4* __restrict__ v, float4* __restrict__ ga, int64_t n4,
-                                              const AdamScalars s, const StepTail tail) {
+                                              AdamScalars s, StepTail tail, const ReplayArgs rp) {
     grid_dependency_wait();                  // launched behind the march's tail: its gradient and loss are complete from here on
+    if (rp.step_dev) {
+        // graph replay: this step's number, loss slots and bias-corrected scalars live in device memory (PlxReplayState)
+        const int32_t step = *reinterpret_cast<const volatile int32_t*>(rp.step_dev) + 1;
+        const int64_t row = (int64_t)step - rp.table_base - 1;
+        if (step <= 0 || row < 0 || row >= rp.table_len) {           // table exhausted (or an earlier failure): apply nothing, say so
+            if (blockIdx.x == 0 && threadIdx.x == 0) *rp.step_dev = -1;
+            return;
+        }
+        s.bc2_sqrt = __ldg(rp.table + 2 * row);
+        s.neg_step_size = __ldg(rp.table + 2 * row + 1);
+        s.reverse = (step & 1) != 0;
+        tail.src = rp.loss2 + (step & 1);
+        tail.clear = rp.loss2 + ((step + 1) & 1);
+        tail.step = step;
+    }
     step_tail(tail);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const FastDiv bc = make_fastdiv(s.bc2_sqrt);
@@ -102,6 +117,13 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
             __stcs(ga + i, A);
         }
         if (ZERO && touched) st_hint(g + i, make_float4(0.f, 0.f, 0.f, 0.f), pol_g);
+    }
+    if (rp.step_dev) {                       // the last block to finish publishes the new step number (every block has read the old one)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicInc(reinterpret_cast<unsigned*>(rp.block_counter), gridDim.x - 1) == gridDim.x - 1) *rp.step_dev = tail.step;
+        }
     }
 }
 
@@ -370,19 +392,19 @@ __global__ void k_adam_scalar(float* p, float* g, float* m, float* v, float* ga,
 
 template <bool HAS_ABS, bool ZERO>
 static cudaError_t launch_adam_vec(float4* p, float4* g, float4* m, float4* v, float4* ga, int64_t n4, const AdamScalars& s,
-                                   const StepTail& tail, cudaStream_t st) {
+                                   const StepTail& tail, cudaStream_t st, const ReplayArgs& rp) {
     // skipping the |g| / clear stores of untouched cells only matters where either store exists.  One wave of 4 resident
     // 256-thread blocks per SM, grid-stride over the rest (measured: 128^3 4 -> 88.6 us per step, 5 / 6 flat; 256^3 3 -> 424 us,
     // 4 -> 410, 5 -> 410)
     constexpr bool SKIP = HAS_ABS || ZERO;
     const int blocks = resident_blocks((const void*)k_adam<HAS_ABS, ZERO, SKIP>, tuning().adam_blocks_per_sm, (n4 + 255) / 256);
-    return launch_pdl(k_adam<HAS_ABS, ZERO, SKIP>, (unsigned)blocks, 256u, 0, st, p, g, m, v, ga, n4, s, tail);
+    return launch_pdl(k_adam<HAS_ABS, ZERO, SKIP>, (unsigned)blocks, 256u, 0, st, p, g, m, v, ga, n4, s, tail, rp);
 }
 
 __global__ void k_step_tail_only(const StepTail tail) { step_tail(tail); }
 
 cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int64_t n, const AdamScalars& s_in,
-                        bool zero_grad, const StepTail& tail, cudaStream_t st) {
+                        bool zero_grad, const StepTail& tail, cudaStream_t st, const ReplayArgs& rp) {
     if (n == 0) return cudaSuccess;
     AdamScalars s = s_in;
     s.keep_p = l2_keep_ok(n / 4);            // parameters tagged evict_last when grid + gradient fit the L2 (measured: +1.3 %)
@@ -395,8 +417,8 @@ cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int
     if (n4 > 0) {
         cudaError_t e;
         float4 *p4 = (float4*)p, *g4 = (float4*)g, *m4 = (float4*)m, *v4 = (float4*)v, *a4 = (float4*)gabs;
-        if (gabs) e = zero_grad ? launch_adam_vec<true, true>(p4, g4, m4, v4, a4, n4, s, tail, st) : launch_adam_vec<true, false>(p4, g4, m4, v4, a4, n4, s, tail, st);
-        else      e = zero_grad ? launch_adam_vec<false, true>(p4, g4, m4, v4, nullptr, n4, s, tail, st) : launch_adam_vec<false, false>(p4, g4, m4, v4, nullptr, n4, s, tail, st);
+        if (gabs) e = zero_grad ? launch_adam_vec<true, true>(p4, g4, m4, v4, a4, n4, s, tail, st, rp) : launch_adam_vec<true, false>(p4, g4, m4, v4, a4, n4, s, tail, st, rp);
+        else      e = zero_grad ? launch_adam_vec<false, true>(p4, g4, m4, v4, nullptr, n4, s, tail, st, rp) : launch_adam_vec<false, false>(p4, g4, m4, v4, nullptr, n4, s, tail, st, rp);
         if (e != cudaSuccess) return e;
     }
     if (n4 == 0 && (tail.src || tail.clear)) k_step_tail_only<<<1, 32, 0, st>>>(tail);

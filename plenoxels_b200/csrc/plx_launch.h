@@ -68,8 +68,17 @@ struct StepTail {
     int32_t n_peers = 0;
     float* global_out = nullptr;
 };
+// graph replay (PlxReplayState): step number, loss slots and Adam scalars come from device memory
+struct ReplayArgs {
+    int32_t* step_dev = nullptr;
+    const float* table = nullptr;
+    int64_t table_base = 0;
+    int32_t table_len = 0;
+    int32_t* block_counter = nullptr;
+    float* loss2 = nullptr;          // the two loss slots
+};
 cudaError_t launch_adam(float* p, float* g, float* m, float* v, float* gabs, int64_t n, const AdamScalars& s,
-                        bool zero_grad, const StepTail& tail, cudaStream_t st);
+                        bool zero_grad, const StepTail& tail, cudaStream_t st, const ReplayArgs& replay = ReplayArgs());
 
 cudaError_t launch_adam_peer(const PlxAdamPeer& a, const AdamScalars& s, const StepTail& tail, cudaStream_t st);
 cudaError_t launch_adam_slab(const PlxAdamSlab& a, const AdamScalars& s, cudaStream_t st);

@@ -383,11 +383,12 @@ __global__ void __launch_bounds__(128, MODE == PLX_NEAREST ? 8 : 5) k_render_tra
     // ---- loss: shared-memory partial per block, the last warp to finish adds it to the global accumulator; that warp
     // also counts the block as done for the cross-GPU signal (its lanes' gradient reductions are ordered before lane 0's
     // fence by the __syncwarp above, the other warps' by their own fence before they bump s_done)
+    float* const loss_dst = a.loss && a.step_dev ? a.loss + ((__ldg(a.step_dev) + 1) & 1) : a.loss;      // graph replay: slot by device step parity
     if (lane == 0 && (a.loss || a.sync.signal_epoch > 0)) {
         if (a.loss) atomicAdd(&s_loss, ray_loss);
         if (a.sync.signal_epoch > 0) { if (PEER) __threadfence_system(); else __threadfence(); } else __threadfence_block();
         if (atomicAdd(&s_done, 1) == wpb - 1) {
-            if (a.loss) atomicAdd(a.loss, atomicAdd(&s_loss, 0.f));
+            if (a.loss) atomicAdd(loss_dst, atomicAdd(&s_loss, 0.f));
             peer_signal(a.sync);
         }
     }

@@ -268,6 +268,64 @@ class VoxelTrainer:
                         "plx_train_step_host")
         return self.loss_host
 
+    # ------------------------------------------------------------------------------------------------ CUDA-graph replay
+    GRAPH_TABLE_STEPS = 1 << 16
+
+    def _refill_replay_table(self) -> None:
+        """Adam's two step-dependent scalars for the next GRAPH_TABLE_STEPS steps, formed on the host in double like
+        plx_adam_step forms them (plx_adam_table), uploaded outside the graph."""
+        n = self.GRAPH_TABLE_STEPS
+        host = torch.empty((n, 2), dtype=torch.float32)
+        L.check(self.lib.plx_adam_table(self.lr, self.betas[0], self.betas[1], self.step_count + 1, n,
+                                        C.cast(host.data_ptr(), C.POINTER(C.c_float))), "plx_adam_table")
+        self._replay_table.copy_(host)
+        self._replay.table_base = self.step_count
+
+    def capture_graph(self, host_uv: bool = False) -> None:
+        """Capture the whole step (fused march + optimiser, both launched programmatically dependent) into ONE CUDA graph that
+        `step_graph()` replays: the step number, the loss slot and Adam's bias-corrected scalars come from device memory
+        (PlxReplayState), so nothing in the graph changes from step to step.  The march reads the uv draw from `self.uv`
+        (device; `host_uv=False`) or zero-copy from the pinned host buffer `self.uv_host` (`host_uv=True`, the optimiser kernel
+        then also publishes {loss, step} to `self.result_host` as `step_host` does).  Single GPU, tv = 0."""
+        if self._distributed() or self.tv > 0:
+            raise L.PlxError("capture_graph: single-GPU trainers with tv = 0 only (the exchange / TV kernels are not part of the graph)")
+        dev = self.device
+        self._step_dev = torch.tensor([self.step_count], dtype=torch.int32, device=dev)
+        self._replay_counter = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self._replay_table = torch.empty((self.GRAPH_TABLE_STEPS, 2), dtype=torch.float32, device=dev)
+        rp = L.PlxReplayState()
+        rp.step_dev, rp.table, rp.block_counter = self._step_dev.data_ptr(), self._replay_table.data_ptr(), self._replay_counter.data_ptr()
+        rp.table_len = self.GRAPH_TABLE_STEPS
+        self._replay = rp
+        self._refill_replay_table()
+        self._args.replay = C.pointer(rp)
+        if host_uv:
+            self.uv_host = torch.empty(tuple(self.uv.shape), dtype=torch.float32).pin_memory()
+        self._graph_host = bool(host_uv)
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(graph):
+            st = L.stream_ptr(dev)
+            if host_uv:
+                L.check(self.lib.plx_train_step_host(C.byref(self._args), self.uv_host.data_ptr(), self._result_ptr, self._phase(L.PLX_STEP_ALL), st),
+                        "plx_train_step_host(capture)")
+            else:
+                self._args.uv = self.uv.data_ptr()
+                L.check(self.lib.plx_train_step(C.byref(self._args), self._phase(L.PLX_STEP_ALL), st), "plx_train_step(capture)")
+        self._graph = graph
+
+    def step_graph(self):
+        """Replay the captured step on the current contents of `self.uv` / `self.uv_host`.  Returns the device loss view
+        (`host_uv=False`) or the pinned `loss_host` (`host_uv=True`: read it with `wait_result()`)."""
+        if self.step_count - self._replay.table_base >= self.GRAPH_TABLE_STEPS:
+            torch.cuda.current_stream(self.device).synchronize()
+            self._refill_replay_table()
+        self.step_count += 1
+        s = self.step_count & 1
+        self.loss = self._loss2[s:s + 1]
+        self._graph.replay()
+        return self.loss_host if self._graph_host else self.loss
+
     def flush(self) -> None:
         """Everything a step promised is complete once the stream is (single GPU / NCCL exchange): nothing to do here.
         PeerVoxelTrainer overrides it."""

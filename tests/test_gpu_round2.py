@@ -331,3 +331,35 @@ def test_unmodified_reference_fit_runs_on_the_dropin_functions(plx_lib, tmp_path
     e_grad = np.abs(gg[::4, ::4, ::4] - z["grad_subset"]).max() / float(z["grad_max"])
     print(f"unmodified fit() on the drop-in functions vs on the reference's own: grid {e_grid:.2e}, grid_grad {e_grad:.2e}")
     assert e_grid <= 5e-4 and e_grad <= 5e-4, (e_grid, e_grad)
+
+
+# ------------------------------------------------------------------------------------------------ CUDA-graph replay of the step
+@pytest.mark.parametrize("host_uv", [False, True])
+def test_graph_replay_equals_plain_steps(plx_lib, host_uv):
+    """One captured CUDA graph (fused march + optimiser, device-resident step number / loss slot / Adam scalars,
+    PlxReplayState) replayed for 7 steps against the same steps issued one by one: Adam's scalars come from the table
+    plx_adam_table fills in double like plx_adam_step, so losses agree to sum-order noise and the state to the 1e-5 bar."""
+    cs = Case(24, 3, 8, 64, 96, 6.0 / 96, "ball")
+    d = cs.cuda()
+    mk = lambda: VoxelTrainer(d["grid"], cs.pd, d["poses"], cs.fov, d["imgs"], cs.R, cs.S, cs.delta, lr=0.0075)
+    ta, tb = mk(), mk()
+    for i in range(2):                                   # the graph is captured mid-run: step numbering must carry on
+        u = synth.random_uv(cs.C, cs.R, seed=40 + i).to(DEV)
+        ta.step(u), tb.step(u)
+    tb.capture_graph(host_uv=host_uv)
+    for i in range(2, 9):
+        uv = synth.random_uv(cs.C, cs.R, seed=40 + i)
+        la = float(ta.step(uv.to(DEV)))
+        if host_uv:
+            tb.uv_host.copy_(uv)
+            tb.step_graph()
+            lb = tb.wait_result()
+        else:
+            tb.uv.copy_(uv.to(DEV))
+            lb = float(tb.step_graph())
+        assert abs(la - lb) <= 2e-6 * la, (i, la, lb)
+    torch.cuda.synchronize()
+    assert ta.step_count == tb.step_count == 9 and int(tb._step_dev.item()) == 9
+    assert float(torch.quantile((ta.grid - tb.grid).abs().flatten(), 0.999)) <= 1e-5
+    assert rel_err(tb.exp_avg_sq.cpu().numpy(), ta.exp_avg_sq.cpu().numpy()) <= 1e-5
+    assert rel_err(tb.grad_abs_sum.cpu().numpy(), ta.grad_abs_sum.cpu().numpy()) <= 1e-5

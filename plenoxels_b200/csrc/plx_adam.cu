@@ -60,12 +60,13 @@ __device__ __forceinline__ bool line_any(bool vote) {
     return ((b >> ((threadIdx.x & 31u) & ~7u)) & 0xffu) != 0u;
 }
 
-template <bool HAS_ABS, bool ZERO, bool SKIP>
-__global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
-                                              float4* __restrict__ v, float4* __restrict__ ga, int64_t n4,
-                                              AdamScalars s, StepTail tail, const ReplayArgs rp) {
+// REPLAY: the graph-replay variant (PlxReplayState) is its own instantiation, so the plain kernel keeps its 4 blocks per SM
+template <bool HAS_ABS, bool ZERO, bool SKIP, bool REPLAY>
+__global__ void __launch_bounds__(256, 4) k_adam(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
+                                                 float4* __restrict__ v, float4* __restrict__ ga, int64_t n4,
+                                                 AdamScalars s, StepTail tail, const ReplayArgs rp) {
     grid_dependency_wait();                  // launched behind the march's tail: its gradient and loss are complete from here on
-    if (rp.step_dev) {
+    if (REPLAY) {
         // graph replay: this step's number, loss slots and bias-corrected scalars live in device memory (PlxReplayState)
         const int32_t step = *reinterpret_cast<const volatile int32_t*>(rp.step_dev) + 1;
         const int64_t row = (int64_t)step - rp.table_base - 1;
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
         }
         if (ZERO && touched) st_hint(g + i, make_float4(0.f, 0.f, 0.f, 0.f), pol_g);
     }
-    if (rp.step_dev) {                       // the last block to finish publishes the new step number (every block has read the old one)
+    if (REPLAY) {                            // the last block to finish publishes the new step number (every block has read the old one)
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -397,8 +398,12 @@ static cudaError_t launch_adam_vec(float4* p, float4* g, float4* m, float4* v, f
     // 256-thread blocks per SM, grid-stride over the rest (measured: 128^3 4 -> 88.6 us per step, 5 / 6 flat; 256^3 3 -> 424 us,
     // 4 -> 410, 5 -> 410)
     constexpr bool SKIP = HAS_ABS || ZERO;
-    const int blocks = resident_blocks((const void*)k_adam<HAS_ABS, ZERO, SKIP>, tuning().adam_blocks_per_sm, (n4 + 255) / 256);
-    return launch_pdl(k_adam<HAS_ABS, ZERO, SKIP>, (unsigned)blocks, 256u, 0, st, p, g, m, v, ga, n4, s, tail, rp);
+    if (rp.step_dev) {
+        const int blocks = resident_blocks((const void*)k_adam<HAS_ABS, ZERO, SKIP, true>, tuning().adam_blocks_per_sm, (n4 + 255) / 256);
+        return launch_pdl(k_adam<HAS_ABS, ZERO, SKIP, true>, (unsigned)blocks, 256u, 0, st, p, g, m, v, ga, n4, s, tail, rp);
+    }
+    const int blocks = resident_blocks((const void*)k_adam<HAS_ABS, ZERO, SKIP, false>, tuning().adam_blocks_per_sm, (n4 + 255) / 256);
+    return launch_pdl(k_adam<HAS_ABS, ZERO, SKIP, false>, (unsigned)blocks, 256u, 0, st, p, g, m, v, ga, n4, s, tail, rp);
 }
 
 __global__ void k_step_tail_only(const StepTail tail) { step_tail(tail); }

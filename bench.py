@@ -408,7 +408,7 @@ def roofline_of(cx: Ctx, kms: dict, m_in: float, n_rays: int, cells: int, tr, wo
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": hbm_gbs, "peak": cx.peak, "unit": "GB/s", "frac": hbm_gbs / cx.peak,
-            "traffic": traffic, "traffic_source": "static: ncu --set full capture of this kernel on this workload (profiles/traffic.json)"
+            "traffic": traffic, "traffic_source": "static: in-situ ncu capture (--cache-control none) of this kernel on this workload, N = 1 (profiles/traffic.json)"
             if traffic else None,
             "peak_source": cx.peak_src, "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": kms,
             "kernel_gbs": {k: alg[k] / (v * 1e-3) / 1e9 for k, v in timed.items()},

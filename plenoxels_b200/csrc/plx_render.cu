@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) k_render_fwd(const P
 // Image-order rays of one view pass through neighbouring cells at equal depth, so the 32 lanes of a load share sectors
 // and L1 lines; the transmittance recurrence runs sequentially in registers (no warp scan), UNR samples are looked up
 // (independent loads) before they are composited.  Same exact index arithmetic, same results as K1 up to summation order.
-template <int MODE, bool FAST, int UNR>
-__global__ void __launch_bounds__(128) k_render_fwd_packet(const PlxRenderFwd a) {
+template <int MODE, bool FAST, int UNR, int MINB = 1>
+__global__ void __launch_bounds__(128, MINB) k_render_fwd_packet(const PlxRenderFwd a) {
     const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ray >= a.rays.n_rays) return;
     const PlxMarch& m = a.march;
@@ -301,12 +301,15 @@ cudaError_t launch_render_fwd(const PlxRenderFwd& a_in, cudaStream_t st) {
     const bool dbg = a.count || a.sample_index || (a.march.flags & PLX_NO_EARLY_STOP);
     if ((a.march.flags & PLX_COHERENT_RAYS) && !dbg && !a.tcarry && !a.targets) {
         const unsigned pblocks = (unsigned)((a.rays.n_rays + 127) / 128);
-        static const int unr = warps_per_block("PLX_PACKET_UNROLL", 4);     // samples looked up before compositing; measured on C4: 4 -> 0.85 ms, 6 -> 0.88, 8 -> 1.01
+        const int variant = tuning().packet_variant;     // samples looked up before compositing x resident blocks per SM
         if (a.march.mode == PLX_NEAREST) {
-            if (!fast)         k_render_fwd_packet<PLX_NEAREST, false, 4><<<pblocks, 128, 0, st>>>(a);
-            else if (unr >= 8) k_render_fwd_packet<PLX_NEAREST, true, 8><<<pblocks, 128, 0, st>>>(a);
-            else if (unr >= 6) k_render_fwd_packet<PLX_NEAREST, true, 6><<<pblocks, 128, 0, st>>>(a);
-            else               k_render_fwd_packet<PLX_NEAREST, true, 4><<<pblocks, 128, 0, st>>>(a);
+            if (!fast)             k_render_fwd_packet<PLX_NEAREST, false, 4><<<pblocks, 128, 0, st>>>(a);
+            else if (variant == 1) k_render_fwd_packet<PLX_NEAREST, true, 4, 12><<<pblocks, 128, 0, st>>>(a);
+            else if (variant == 2) k_render_fwd_packet<PLX_NEAREST, true, 2, 16><<<pblocks, 128, 0, st>>>(a);
+            else if (variant == 3) k_render_fwd_packet<PLX_NEAREST, true, 6, 10><<<pblocks, 128, 0, st>>>(a);
+            else if (variant == 4) k_render_fwd_packet<PLX_NEAREST, true, 4, 16><<<pblocks, 128, 0, st>>>(a);
+            else if (variant == 5) k_render_fwd_packet<PLX_NEAREST, true, 8, 12><<<pblocks, 128, 0, st>>>(a);
+            else                   k_render_fwd_packet<PLX_NEAREST, true, 4><<<pblocks, 128, 0, st>>>(a);
         } else {
             if (fast) k_render_fwd_packet<PLX_TRILINEAR, true, 1><<<pblocks, 128, 0, st>>>(a);
             else      k_render_fwd_packet<PLX_TRILINEAR, false, 1><<<pblocks, 128, 0, st>>>(a);

@@ -652,7 +652,10 @@ def run_gpu_arm(args):
     if cx.world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         cx.dist.init_process_group("nccl", device_id=cx.dev)
-    _lib.load()
+    lib = _lib.load()
+    for kv in args.tune:            # A/B runs only: library tuning switches (plx_tune); the defaults are the measured optimum
+        k, v = kv.split("=")
+        _lib.check(lib.plx_tune(k.encode(), int(v)), f"plx_tune({kv})")
     K, W = args.steps, args.warmup
 
     sc = synth.make_scene(args.workload)
@@ -753,6 +756,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline workload only (skip the C3 / C4 / C5 / trilinear records)")
+    ap.add_argument("--tune", action="append", default=[], metavar="NAME=INT", help="A/B runs: set a library tuning switch (plx_tune)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

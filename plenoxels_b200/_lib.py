@@ -167,7 +167,9 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    """The in-tree library.  `PLX_AB_LIBRARY` (tools/ab_step.py only) points at another BUILD of the same sources, so that two
+    versions of a kernel can be timed in the same run on the same GPU; it is still this library or nothing (no fallback)."""
+    return os.environ.get("PLX_AB_LIBRARY") or _build.LIB_PATH
 
 
 def load():

@@ -139,6 +139,35 @@ def test_config4_inference_frame_matches_the_c_oracle_on_strided_rays(plx_lib, m
     assert np.array_equal(img, want), "the kernel's epilogue is src/visualization.py:150-154 bit for bit"
 
 
+@pytest.mark.parametrize("side,views", [(20, 1), (37, 2), (8, 3), (64, 1)])
+def test_packet_tiles_render_the_same_pixels_as_lattice_rows(plx_lib, side, views):
+    """The ray-packet kernel marches the even-spread lattice in 16 x 8 tiles per block (plx_render.cu); which thread marches a
+    ray must not change the ray: pixels and depth bit-equal to the lattice-row order (plx_tune packet_tile = 0) and to the
+    warp-per-ray kernel within 1e-5, for sides that are not multiples of the tile and for several views in one launch."""
+    G, S = 24, 96
+    pd = synth.GRID_EXTENT / G
+    grid = synth.ball_grid(G, occupancy_radius=0.4).to(DEV)
+    poses = synth.lookat_poses(views + 1)[1:].to(DEV)
+    gmin = ops.grid_origin(grid.shape, pd)
+    n = side * side
+    dirs, _ = ops.generate_rays(None, poses, synth.CAMERA_ANGLE_X, uv=None, rays_per_cam=n, want_targets=False)
+    o = poses[:, :3, 3]
+    lib = L.load()
+    for mode in ("nearest", "trilinear"):
+        out = {}
+        try:
+            for tile in (1, 0):
+                L.check(lib.plx_tune(b"packet_tile", tile))
+                out[tile] = ops.render_rays(grid, o, dirs, S, 6.0 / S, gmin, pd, mode=mode, rays_per_origin=n, return_depth=True, coherent=True)
+        finally:
+            L.check(lib.plx_tune(b"packet_tile", 1))
+        assert torch.equal(out[1][0], out[0][0]) and torch.equal(out[1][1], out[0][1])
+        warp, depth_w = ops.render_rays(grid, o, dirs, S, 6.0 / S, gmin, pd, mode=mode, rays_per_origin=n, return_depth=True)
+        assert float(out[1][0].abs().sum()) > 0
+        assert rel_err(out[1][0].cpu().numpy(), warp.cpu().numpy()) <= TOL
+        assert rel_err(out[1][1].cpu().numpy(), depth_w.cpu().numpy()) <= TOL
+
+
 # ------------------------------------------------------------------------------------------------ inference epilogue + splat
 def test_image_epilogue_is_the_references_postprocessing(plx_lib):
     """(pix * 255).round().clip(0, 255).astype(uint8), reshape, transpose — src/visualization.py:150-154 — done by the march

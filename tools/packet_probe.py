@@ -1,3 +1,6 @@
+"""A/B of the ray-packet inference kernel on C4 (512^3 grid, one 800x800 view): lattice tiles vs lattice rows
+   (the unroll / occupancy sweep behind the launch shape is profiles/r2_packet_sweep_c4.log).
+   python tools/packet_probe.py"""
 import json, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from plenoxels_b200 import ops, synth, _lib as L
@@ -14,7 +17,13 @@ def t(fn, reps=8):
     e0.record()
     for _ in range(reps): fn()
     e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / reps
-for v in (0, 1, 2, 3, 4, 5, 0):
-    L.check(lib.plx_tune(b"packet_variant", v))
-    ms = t(lambda: ops.render_rays(grid, o, dirs, S, delta, gmin, pd, clamp=False, rays_per_origin=n, coherent=True))
-    print(json.dumps({"packet_variant": v, "ms_per_frame": round(ms, 4)}))
+ref = {}
+for mode in ("nearest", "trilinear"):
+    for tile in (0, 1, 0, 1):
+        L.check(lib.plx_tune(b"packet_tile", tile))
+        fn = lambda: ops.render_rays(grid, o, dirs, S, delta, gmin, pd, mode=mode, clamp=False, rays_per_origin=n, coherent=True)
+        ms = t(fn)
+        out = fn()
+        same = bool(torch.equal(out, ref.setdefault(mode, out)))
+        print(json.dumps({"mode": mode, "packet_tile": tile, "ms_per_frame": round(ms, 4), "bit_equal_to_first": same}), flush=True)
+L.check(lib.plx_tune(b"packet_tile", 1))

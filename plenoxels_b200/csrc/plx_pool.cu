@@ -4,7 +4,8 @@
 // fit() applies to the whole grid on each of its first 230 steps (scripts/train.py:110-118, windows 93^3 .. 3^3, stride
 // max(1, k // 4)).  A k^3 window is the product of three 1-D box sums, so the forward is  Z-pass -> Y-pass -> X-pass with
 // k additions per output each (instead of k^3), and the backward is the three transposed passes in gather form (every
-// input cell sums the <= ceil(k/s) windows that cover it): no atomics, every access a 16-byte cell.
+// input cell sums the <= ceil(k/s) windows that cover it): no atomics, every access a 16-byte cell.  Stride-1 windows (the
+// last pooled stage, window 3) take a one-pass sliding-window kernel instead (k_box3_stride1 below).
 #include "plx_device.cuh"
 #include "plx_launch.h"
 
@@ -41,6 +42,82 @@ __global__ void __launch_bounds__(256) k_box_bwd(const float4* __restrict__ gout
     }
 }
 
+// Stride-1 windows (the last pooled stage of fit(): window 3, stride max(1, 3 // 4) = 1; scripts/train.py:110-118) in ONE pass
+// instead of three: out = in (*) box_K^3 with `in` read as zero outside its bounds,
+//   out[x][y][z] = sum_{dx,dy,dz < K} in[x - pad + dx][y - pad + dy][z - pad + dz] / K^3.
+// pad = 0 is the forward (out = in - (K-1) per axis), pad = K - 1 the backward (out = in + (K-1): every input cell gathers the
+// windows that cover it).  One thread owns an (y, z) column of a chunk of x and slides along x keeping the last K plane sums
+// (K^2 cells each) in registers: K^2 loads per output instead of K^3, neighbouring threads share them through L1, DRAM sees the
+// input once and the output once (3 separable passes move each three times: 256^3, window 3: 0.93 -> see DESIGN.md 4).
+template <int K, bool PADDED>
+__global__ void __launch_bounds__(256) k_box3_stride1(const float4* __restrict__ in, float4* __restrict__ out, int IX, int IY, int IZ,
+                                                      int OX, int OY, int OZ, int xchunk) {
+    const int pad = PADDED ? K - 1 : 0;
+    const int64_t cols = (int64_t)OY * OZ;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunk = (int)(e / cols);
+    const int x0 = chunk * xchunk;
+    if (x0 >= OX) return;
+    const int x1 = x0 + xchunk < OX ? x0 + xchunk : OX;
+    const int oy = (int)((e % cols) / OZ), oz = (int)(e % OZ);
+    auto plane = [&](int ix) {               // sum of the K x K cells of input plane ix under this column's window
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (PADDED && (ix < 0 || ix >= IX)) return acc;
+#pragma unroll
+        for (int dy = 0; dy < K; ++dy) {
+            const int iy = oy - pad + dy;
+            if (PADDED && (iy < 0 || iy >= IY)) continue;
+#pragma unroll
+            for (int dz = 0; dz < K; ++dz) {
+                const int iz = oz - pad + dz;
+                if (PADDED && (iz < 0 || iz >= IZ)) continue;
+                acc = add4(acc, __ldg(in + ((int64_t)ix * IY + iy) * IZ + iz));
+            }
+        }
+        return acc;
+    };
+    float4 ring[K];
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j) ring[j] = plane(x0 - pad + j);
+    const float n = (float)(K * K * K);
+    for (int xb = x0; xb < x1; xb += K) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {        // ring slot (K - 1 + j) % K receives plane x + K - 1: compile-time slots, no local memory
+            const int x = xb + j;
+            if (x < x1) {
+                ring[(K - 1 + j) % K] = plane(x - pad + K - 1);
+                float4 acc = ring[(j) % K];
+#pragma unroll
+                for (int t = 1; t < K; ++t) acc = add4(acc, ring[(j + t) % K]);
+                out[((int64_t)x * OY + oy) * OZ + oz] = make_float4(acc.x / n, acc.y / n, acc.z / n, acc.w / n);
+            }
+        }
+    }
+}
+
+template <bool PADDED>
+static bool launch_box3_stride1(const float* in, float* out, int IX, int IY, int IZ, int k, cudaStream_t st) {
+    const int d = PADDED ? k - 1 : -(k - 1);
+    const int OX = IX + d, OY = IY + d, OZ = IZ + d;
+    const int64_t cols = (int64_t)OY * OZ;
+    // enough threads for two full waves of 2048 threads per SM; every chunk re-reads K - 1 planes, so not more than needed
+    int chunks = (int)((2ll * 148 * 2048 + cols - 1) / cols);
+    if (chunks < 1) chunks = 1;
+    if (chunks > (OX + 7) / 8) chunks = (OX + 7) / 8;
+    const int xchunk = (OX + chunks - 1) / chunks;
+    chunks = (OX + xchunk - 1) / xchunk;
+    const unsigned blocks = (unsigned)((cols * chunks + 255) / 256);
+    const float4* i4 = (const float4*)in;
+    float4* o4 = (float4*)out;
+    switch (k) {
+        case 2: k_box3_stride1<2, PADDED><<<blocks, 256, 0, st>>>(i4, o4, IX, IY, IZ, OX, OY, OZ, xchunk); return true;
+        case 3: k_box3_stride1<3, PADDED><<<blocks, 256, 0, st>>>(i4, o4, IX, IY, IZ, OX, OY, OZ, xchunk); return true;
+        case 4: k_box3_stride1<4, PADDED><<<blocks, 256, 0, st>>>(i4, o4, IX, IY, IZ, OX, OY, OZ, xchunk); return true;
+        case 5: k_box3_stride1<5, PADDED><<<blocks, 256, 0, st>>>(i4, o4, IX, IY, IZ, OX, OY, OZ, xchunk); return true;
+        default: return false;
+    }
+}
+
 static unsigned pool_blocks(int64_t n) {
     int64_t b = (n + 255) / 256;
     const int64_t cap = 148 * 16;
@@ -51,6 +128,7 @@ cudaError_t launch_avgpool3d_fwd(const float* in, const int32_t* dims, int k, in
                                  cudaStream_t st) {
     const int X = dims[0], Y = dims[1], Z = dims[2];
     const int Ox = (X - k) / s + 1, Oy = (Y - k) / s + 1, Oz = (Z - k) / s + 1;
+    if (s == 1 && launch_box3_stride1<false>(in, out, X, Y, Z, k, st)) return cudaGetLastError();
     const float inv = 1.f / (float)k;
     // Z pass: (X*Y, Z, 1) -> (X*Y, Oz, 1)
     k_box_fwd<<<pool_blocks((int64_t)X * Y * Oz), 256, 0, st>>>((const float4*)in, (float4*)tmp1, (int64_t)X * Y, Z, Oz, 1, k, s, inv);
@@ -65,6 +143,7 @@ cudaError_t launch_avgpool3d_bwd(const float* gout, const int32_t* dims, int k, 
                                  cudaStream_t st) {
     const int X = dims[0], Y = dims[1], Z = dims[2];
     const int Ox = (X - k) / s + 1, Oy = (Y - k) / s + 1, Oz = (Z - k) / s + 1;
+    if (s == 1 && launch_box3_stride1<true>(gout, gin, Ox, Oy, Oz, k, st)) return cudaGetLastError();
     const float inv = 1.f / (float)k;
     k_box_bwd<<<pool_blocks((int64_t)X * Oy * Oz), 256, 0, st>>>((const float4*)gout, (float4*)tmp2, 1, X, Ox, (int64_t)Oy * Oz, k, s, inv);
     k_box_bwd<<<pool_blocks((int64_t)X * Y * Oz), 256, 0, st>>>((const float4*)tmp2, (float4*)tmp1, X, Y, Oy, Oz, k, s, inv);

@@ -289,10 +289,11 @@ def test_train_steps_match_oracle(mode):
         assert np.quantile(diff, 0.999) <= 1e-5, f"step {step}: {np.quantile(diff, 0.999)}"
 
 
-@pytest.mark.parametrize("G,k,s", [(24, 3, 1), (24, 5, 1), (40, 9, 2), (40, 21, 5), (64, 33, 8), (31, 7, 3)])
+@pytest.mark.parametrize("G,k,s", [(24, 3, 1), (24, 5, 1), (16, 2, 1), (20, 4, 1), (70, 3, 1), (12, 6, 1), (40, 9, 2), (40, 21, 5), (64, 33, 8), (31, 7, 3)])
 def test_average_pool3d_grid_matches_library(plx_lib, G, k, s):
-    """Separable box-filter pooling (plx_avgpool3d_fwd/bwd) vs F.avg_pool3d as average_pool3d_grid calls it
-    (src/grid_functions.py:173-181), forward and backward; tolerance = summation order only."""
+    """Box-filter pooling (plx_avgpool3d_fwd/bwd: three separable passes, or the one-pass sliding-window kernel for stride-1
+    windows up to 5) vs F.avg_pool3d as average_pool3d_grid calls it (src/grid_functions.py:173-181), forward and backward;
+    tolerance = summation order only."""
     torch.manual_seed(G + k)
     grid = (torch.rand(G, G + 1, G + 2, 4, device="cuda") * 1.4 - 0.2).requires_grad_(True)
     out = ops.avgpool3d_grid(grid, k, s)

@@ -47,49 +47,75 @@ __global__ void __launch_bounds__(256) k_box_bwd(const float4* __restrict__ gout
 //   out[x][y][z] = sum_{dx,dy,dz < K} in[x - pad + dx][y - pad + dy][z - pad + dz] / K^3.
 // pad = 0 is the forward (out = in - (K-1) per axis), pad = K - 1 the backward (out = in + (K-1): every input cell gathers the
 // windows that cover it).  One thread owns an (y, z) column of a chunk of x and slides along x keeping the last K plane sums
-// (K^2 cells each) in registers: K^2 loads per output instead of K^3, neighbouring threads share them through L1, DRAM sees the
-// input once and the output once (3 separable passes move each three times: 256^3, window 3: 0.93 -> see DESIGN.md 4).
+// (K^2 cells each) in registers: K (K + 1) / 2 loads per output instead of K^3 (two z-neighbours per thread), neighbouring
+// threads share them through L1, DRAM sees the input once and the output once (the three separable passes move each three
+// times).  256^3, window 3, forward + backward: 0.93 ms -> 0.33 ms (0.15 + 0.18; 497 MB of DRAM traffic each).
 template <int K, bool PADDED>
 __global__ void __launch_bounds__(256) k_box3_stride1(const float4* __restrict__ in, float4* __restrict__ out, int IX, int IY, int IZ,
                                                       int OX, int OY, int OZ, int xchunk) {
     const int pad = PADDED ? K - 1 : 0;
-    const int64_t cols = (int64_t)OY * OZ;
+    const int OZP = (OZ + 1) / 2;            // a thread owns TWO neighbouring z outputs: their windows share K - 1 of K + 1 cells per row
+    const int64_t cols = (int64_t)OY * OZP;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int chunk = (int)(e / cols);
     const int x0 = chunk * xchunk;
     if (x0 >= OX) return;
     const int x1 = x0 + xchunk < OX ? x0 + xchunk : OX;
-    const int oy = (int)((e % cols) / OZ), oz = (int)(e % OZ);
-    auto plane = [&](int ix) {               // sum of the K x K cells of input plane ix under this column's window
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (PADDED && (ix < 0 || ix >= IX)) return acc;
+    const int oy = (int)((e % cols) / OZP), oz = 2 * (int)(e % OZP);
+    const bool second = oz + 1 < OZ;
+    const int y_lo = oy - pad, z_lo = oz - pad;                                      // first row / cell under the two windows
+    const bool yz_inside = y_lo >= 0 && y_lo + K <= IY && z_lo >= 0 && z_lo + K + 1 <= IZ;     // K rows x (K + 1) cells all exist
+    // sums of the K x K cells of input plane ix under the window of output z (s0) and of output z + 1 (s1)
+    auto plane = [&](int ix, float4& s0, float4& s1) {
+        s0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        s1 = s0;
+        if (PADDED && (ix < 0 || ix >= IX)) return;
+        const float4* base = in + ((int64_t)ix * IY + y_lo) * IZ + z_lo;
+        if (yz_inside) {                     // interior column: no per-cell tests
 #pragma unroll
-        for (int dy = 0; dy < K; ++dy) {
-            const int iy = oy - pad + dy;
-            if (PADDED && (iy < 0 || iy >= IY)) continue;
+            for (int dy = 0; dy < K; ++dy) {
+                const float4* row = base + (int64_t)dy * IZ;
+                float4 c[K + 1];
 #pragma unroll
-            for (int dz = 0; dz < K; ++dz) {
-                const int iz = oz - pad + dz;
-                if (PADDED && (iz < 0 || iz >= IZ)) continue;
-                acc = add4(acc, __ldg(in + ((int64_t)ix * IY + iy) * IZ + iz));
+                for (int dz = 0; dz <= K; ++dz) c[dz] = __ldg(row + dz);
+                float4 mid = c[1];
+#pragma unroll
+                for (int dz = 2; dz < K; ++dz) mid = add4(mid, c[dz]);
+                s0 = add4(s0, K > 1 ? add4(c[0], mid) : c[0]);
+                s1 = add4(s1, K > 1 ? add4(mid, c[K]) : c[K]);
+            }
+        } else {
+#pragma unroll
+            for (int dy = 0; dy < K; ++dy) {
+                const int iy = y_lo + dy;
+                if (iy < 0 || iy >= IY) continue;
+#pragma unroll
+                for (int dz = 0; dz <= K; ++dz) {
+                    const int iz = z_lo + dz;
+                    if (iz < 0 || iz >= IZ) continue;
+                    const float4 c = __ldg(base + (int64_t)dy * IZ + dz);
+                    if (dz < K) s0 = add4(s0, c);
+                    if (dz > 0) s1 = add4(s1, c);
+                }
             }
         }
-        return acc;
     };
-    float4 ring[K];
+    float4 r0[K], r1[K];
 #pragma unroll
-    for (int j = 0; j < K - 1; ++j) ring[j] = plane(x0 - pad + j);
-    const float n = (float)(K * K * K);
+    for (int j = 0; j < K - 1; ++j) plane(x0 - pad + j, r0[j], r1[j]);
+    const FastDiv dn = make_fastdiv((float)(K * K * K));     // sum / K^3 as the correctly rounded quotient (3 FMAs, plx_device.cuh)
     for (int xb = x0; xb < x1; xb += K) {
 #pragma unroll
         for (int j = 0; j < K; ++j) {        // ring slot (K - 1 + j) % K receives plane x + K - 1: compile-time slots, no local memory
             const int x = xb + j;
             if (x < x1) {
-                ring[(K - 1 + j) % K] = plane(x - pad + K - 1);
-                float4 acc = ring[(j) % K];
+                plane(x - pad + K - 1, r0[(K - 1 + j) % K], r1[(K - 1 + j) % K]);
+                float4 a0 = r0[j % K], a1 = r1[j % K];
 #pragma unroll
-                for (int t = 1; t < K; ++t) acc = add4(acc, ring[(j + t) % K]);
-                out[((int64_t)x * OY + oy) * OZ + oz] = make_float4(acc.x / n, acc.y / n, acc.z / n, acc.w / n);
+                for (int t = 1; t < K; ++t) { a0 = add4(a0, r0[(j + t) % K]); a1 = add4(a1, r1[(j + t) % K]); }
+                float4* dst = out + ((int64_t)x * OY + oy) * OZ + oz;
+                dst[0] = make_float4(fdiv_hoisted(a0.x, dn), fdiv_hoisted(a0.y, dn), fdiv_hoisted(a0.z, dn), fdiv_hoisted(a0.w, dn));
+                if (second) dst[1] = make_float4(fdiv_hoisted(a1.x, dn), fdiv_hoisted(a1.y, dn), fdiv_hoisted(a1.z, dn), fdiv_hoisted(a1.w, dn));
             }
         }
     }
@@ -99,21 +125,23 @@ template <bool PADDED>
 static bool launch_box3_stride1(const float* in, float* out, int IX, int IY, int IZ, int k, cudaStream_t st) {
     const int d = PADDED ? k - 1 : -(k - 1);
     const int OX = IX + d, OY = IY + d, OZ = IZ + d;
-    const int64_t cols = (int64_t)OY * OZ;
-    // enough threads for two full waves of 2048 threads per SM; every chunk re-reads K - 1 planes, so not more than needed
-    int chunks = (int)((2ll * 148 * 2048 + cols - 1) / cols);
+    const int64_t cols = (int64_t)OY * ((OZ + 1) / 2);
+    // about one wave of 2048 threads per SM in 128-thread blocks (measured on 256^3, window 3: x chunks of 16 .. 64 planes and
+    // blocks of 64 .. 256 threads are within 10 % of each other; longer chunks starve the SMs, shorter ones re-read K - 1 planes
+    // too often)
+    int chunks = (int)((148ll * 2048 + cols - 1) / cols);
     if (chunks < 1) chunks = 1;
     if (chunks > (OX + 7) / 8) chunks = (OX + 7) / 8;
     const int xchunk = (OX + chunks - 1) / chunks;
     chunks = (OX + xchunk - 1) / xchunk;
-    const unsigned blocks = (unsigned)((cols * chunks + 255) / 256);
+    const unsigned blocks = (unsigned)((cols * chunks + 127) / 128);
     const float4* i4 = (const float4*)in;
     float4* o4 = (float4*)out;
     switch (k) {
-        case 2: k_box3_stride1<2, PADDED><<<blocks, 256, 0, st>>>(i4, o4, IX, IY, IZ, OX, OY, OZ, xchunk); return true;
-        case 3: k_box3_stride1<3, PADDED><<<blocks, 256, 0, st>>>(i4, o4, IX, IY, IZ, OX, OY, OZ, xchunk); return true;
-        case 4: k_box3_stride1<4, PADDED><<<blocks, 256, 0, st>>>(i4, o4, IX, IY, IZ, OX, OY, OZ, xchunk); return true;
-        case 5: k_box3_stride1<5, PADDED><<<blocks, 256, 0, st>>>(i4, o4, IX, IY, IZ, OX, OY, OZ, xchunk); return true;
+        case 2: k_box3_stride1<2, PADDED><<<blocks, 128, 0, st>>>(i4, o4, IX, IY, IZ, OX, OY, OZ, xchunk); return true;
+        case 3: k_box3_stride1<3, PADDED><<<blocks, 128, 0, st>>>(i4, o4, IX, IY, IZ, OX, OY, OZ, xchunk); return true;
+        case 4: k_box3_stride1<4, PADDED><<<blocks, 128, 0, st>>>(i4, o4, IX, IY, IZ, OX, OY, OZ, xchunk); return true;
+        case 5: k_box3_stride1<5, PADDED><<<blocks, 128, 0, st>>>(i4, o4, IX, IY, IZ, OX, OY, OZ, xchunk); return true;
         default: return false;
     }
 }

@@ -262,6 +262,41 @@ def test_adam_step_matches_oracle():
     assert np.array_equal(pc.cpu().numpy(), pn), "Adam parameters are bit-exact against the fp32 oracle"
 
 
+@pytest.mark.parametrize("skip_same", [1, 0])
+def test_adam_sparse_steps_are_bit_exact(plx_lib, skip_same):
+    """The large-grid form of K3 — per-line skipping of unchanged stores — forced on / off on a small array (plx_tune): sparse
+    gradients, cells that were never touched, cells whose moments still move their parameter long after their last gradient,
+    a NaN gradient; every step bit-exact against the fp32 oracle, untouched cells keep their exact bits (incl. -0.0)."""
+    from plenoxels_b200 import _lib as L
+    lib = L.load()
+    torch.manual_seed(3)
+    n = 48 * 1024 * 4
+    p = (torch.rand(n) * 1.4 - 0.2)
+    p[:64] = -0.0
+    m, v, ga = torch.zeros(n), torch.zeros(n), torch.zeros(n)
+    pc, mc, vc, gac = (t.cuda() for t in (p, m, v, ga))
+    pn, mn, vn, gan = (t.numpy().copy() for t in (p, m, v, ga))
+    try:
+        L.check(lib.plx_tune(b"adam_skip_same", skip_same))
+        for step in range(1, 9):
+            g = torch.zeros(n)
+            if step <= 5:                     # a few 128-byte lines per step; steps 6-8 have no gradient at all (moments only)
+                lines = torch.randint(2, n // 32, (40,))
+                for ln in lines.tolist():
+                    g[ln * 32: ln * 32 + 32] = torch.randn(32) * 1e-3 * (torch.rand(32) < 0.7)
+            if step == 3:
+                g[n - 7] = float("nan")
+            gc = g.cuda()
+            ops.adam_step(pc, gc, mc, vc, gac, step, lr=0.0075)
+            pn, mn, vn, gan = po.adam_step(pn, g.numpy(), mn, vn, gan, 0.0075, step)
+            assert float(torch.nan_to_num(gc).abs().max()) == 0.0 and not bool(torch.isnan(gc).any())
+            for name, a, b in (("m", mc, mn), ("v", vc, vn), ("|g|", gac, gan), ("p", pc, pn)):
+                assert np.array_equal(a.cpu().numpy(), b, equal_nan=True), f"step {step}: {name}"
+        assert np.array_equal(np.signbit(pc[:64].cpu().numpy()), np.signbit(pn[:64]))
+    finally:
+        L.check(lib.plx_tune(b"adam_skip_same", -1))
+
+
 @pytest.mark.parametrize("mode", ["nearest", "trilinear"])
 def test_train_steps_match_oracle(mode):
     """Three whole steps (ray generation -> forward -> MSE -> backward -> Adam) through plx_train_step."""

@@ -46,7 +46,10 @@ extern "C" {
 #define PLX_NO_EARLY_STOP 4u  /* keep marching after the transmittance reached exactly 0 */
 #define PLX_COHERENT_RAYS 8u  /* hint: consecutive rays are neighbouring pixels of one view (inference, even-spread lattice);
                                  plx_render_fwd then marches one ray per THREAD, 32 neighbouring rays per warp, so that the
-                                 lanes of a load hit neighbouring cells (sector / L1 reuse) and no warp scan is needed */
+                                 lanes of a load hit neighbouring cells (sector / L1 reuse) and no warp scan is needed.
+                                 When rays_per_origin is a square number side^2 the rays of each origin are taken to be the
+                                 side x side lattice (ray = iu * side + iv) and a block marches a 16 x 8 tile of it; the
+                                 result of a ray never depends on which thread marched it */
 
 /* Ray-marching geometry shared by the fused kernels. */
 typedef struct PlxMarch {

@@ -12,6 +12,9 @@
 //     later samples have zero gradient; the only later quantity the gradient of k* needs is the colour seen behind it,
 //     S_k* = sum_{j>k*} alpha_j v_j prod_{k*<i<j} (1-alpha_i), which is linear in the pixel gradient g, so the forward
 //     pass keeps compositing a second accumulator behind k* (until that one saturates too) and S_k* = acc2 . g.
+//   * trilinear lookup: the forward pass caches each sample's interpolated value (16 B) and the clip pass-mask of its eight
+//     corners (4 B) instead of a cell index; the reverse pass recomputes only the geometry (corner indices, lerp weights: no
+//     loads) and never repeats the eight gathers, the masks or the seven lerps.
 // Same exact index arithmetic as K1 (plx_march.cuh), so indices match the reference bit for bit.
 #include <cstdlib>
 
@@ -56,8 +59,10 @@ struct GradDst {
 
 // per-warp scratch of one ray
 struct RayScratch {
-    int* lc;        // cached linear cell index of every visited sample
+    int* lc;        // nearest: cached linear cell index of every visited sample
     float* tcs;     // transmittance in front of every iteration
+    float4* cv;     // trilinear: cached interpolated value of every visited sample ...
+    uint32_t* mk;   // ... and the clip pass-mask bits of its eight corners
 };
 
 // One ray, start to finish: forward march + compositing, MSE gradient, reverse march + scatter-add.  Returns the ray's loss.
@@ -103,6 +108,7 @@ __device__ __forceinline__ float train_ray(const PlxRenderTrain& a, const Geo& g
                 norm3<FAST>(m, g, r, FR, __fmul_rn(g.delta, (float)(kb + j)), nx, ny, nz);
                 rawn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 linn[j] = -1;
+                maskn[j] = 0u;
                 if (kb + j <= k1 && tri_geom(g, nx, ny, nz, tgn[j])) {
                     linn[j] = (tgn[j].lo[0] * g.ny + tgn[j].lo[1]) * g.nz + tgn[j].lo[2];
                     rawn[j] = tri_interp_mask<FAST>(m, g, a.grid, tgn[j], maskn[j]);
@@ -119,8 +125,15 @@ __device__ __forceinline__ float train_ray(const PlxRenderTrain& a, const Geo& g
 #pragma unroll
         for (int j = 0; j < SPL; ++j) { c[j] = (CLAMP_ON_USE && g.clamp) ? clamp4(rawn[j]) : rawn[j]; lin[j] = linn[j]; }
         if (PIPE && it + 1 < n_it) fetch(it + 1);
-        if (SPL == 1) lc[it * W + lane] = lin[0];
-        else *reinterpret_cast<int2*>(lc + it * W + lane * 2) = make_int2(lin[0], lin[SPL - 1]);
+        if (MODE == PLX_NEAREST) {
+            if (SPL == 1) lc[it * W + lane] = lin[0];
+            else *reinterpret_cast<int2*>(lc + it * W + lane * 2) = make_int2(lin[0], lin[SPL - 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) sc.cv[it * W + lane * SPL + j] = c[j];
+            if (SPL == 1) sc.mk[it * W + lane] = maskn[0];
+            else *reinterpret_cast<uint2*>(sc.mk + it * W + lane * 2) = make_uint2(maskn[0], maskn[SPL - 1]);
+        }
         if (lane == 0) tcs[it] = T;
         // empty space is the common case (a trained grid is mostly alpha == 0, fit() even starts from all zeros):
         // an iteration whose 32*SPL samples are all transparent changes neither T nor the pixel — skip its scan
@@ -180,7 +193,20 @@ __device__ __forceinline__ float train_ray(const PlxRenderTrain& a, const Geo& g
     float carry = 0.f;                   // S behind the last visited sample (0: end of ray, or irrelevant behind k*)
     __syncwarp();
     auto refetch = [&](int i) {          // indices back from shared memory, cells requested (L1 / L2 hits mostly)
-        if (MODE == PLX_TRILINEAR) { fetch(i); return; }   // trilinear: recompute geometry + interpolation (the corners hit L1 / L2)
+        if (MODE == PLX_TRILINEAR) {         // geometry recomputed (no loads), value and corner masks back from shared memory
+            const int kb = k0 + i * W + lane * SPL;
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                float nx, ny, nz;
+                norm3<FAST>(m, g, r, FR, __fmul_rn(g.delta, (float)(kb + j)), nx, ny, nz);
+                linn[j] = -1;
+                if (kb + j <= k1 && tri_geom(g, nx, ny, nz, tgn[j])) linn[j] = (tgn[j].lo[0] * g.ny + tgn[j].lo[1]) * g.nz + tgn[j].lo[2];
+                rawn[j] = sc.cv[i * W + lane * SPL + j];
+            }
+            if (SPL == 1) maskn[0] = sc.mk[i * W + lane];
+            else { const uint2 q = *reinterpret_cast<const uint2*>(sc.mk + i * W + lane * 2); maskn[0] = q.x; maskn[SPL - 1] = q.y; }
+            return;
+        }
         if (SPL == 1) linn[0] = lc[i * W + lane];
         else { const int2 p = *reinterpret_cast<const int2*>(lc + i * W + lane * 2); linn[0] = p.x; linn[SPL - 1] = p.y; }
 #pragma unroll
@@ -334,13 +360,11 @@ __device__ __forceinline__ void setup_ray(const PlxRenderTrain& a, int64_t ray, 
 // the IEEE division and the float bounds test.  Out of line and self-contained (it rebuilds the ray and the geometry from the
 // kernel argument), so the common path pays neither instructions nor registers nor stack traffic for it.
 template <int MODE, bool FAST, int SPL, bool PEER>
-__device__ __noinline__ float train_ray_slow(const PlxRenderTrain* ap, float* const* peers, int* lc, float* tcs, int64_t ray, int lane) {
+__device__ __noinline__ float train_ray_slow(const PlxRenderTrain* ap, float* const* peers, const RayScratch sc, int64_t ray, int lane) {
     const PlxRenderTrain& a = *ap;
     const Geo g = make_geo(a.march);
     GradDst<PEER> dst;
     dst.local = a.grad_grid; dst.peers = peers; dst.owner_mul = a.peer_grad.owner_mul; dst.pol = g.pol_grad;
-    RayScratch sc;
-    sc.lc = lc; sc.tcs = tcs;
     Ray r;
     float4 tgt;
     setup_ray(a, ray, r, tgt);
@@ -348,7 +372,7 @@ __device__ __noinline__ float train_ray_slow(const PlxRenderTrain* ap, float* co
 }
 
 template <int MODE, bool FAST, int SPL, bool PIPE, bool PEER>
-__global__ void __launch_bounds__(128, MODE == PLX_NEAREST ? 8 : 5) k_render_train(const __grid_constant__ PlxRenderTrain a, int lin_words, int warp_words) {
+__global__ void __launch_bounds__(MODE == PLX_NEAREST ? 128 : 64, MODE == PLX_NEAREST ? 8 : 7) k_render_train(const __grid_constant__ PlxRenderTrain a, int lin_words, int warp_words) {
     extern __shared__ __align__(16) int s_dyn[];   // per warp (warp_words ints, 16-byte multiple): lin cache [lin_words], then chunk transmittances
     __shared__ float s_loss;
     __shared__ int s_done;
@@ -365,9 +389,21 @@ __global__ void __launch_bounds__(128, MODE == PLX_NEAREST ? 8 : 5) k_render_tra
     // every config: 61 vs 48 us on C2 even with the ticket drawn one ray ahead)
     const int64_t ray = (int64_t)blockIdx.x * wpb + wib;
     if (ray < a.rays.n_rays) {
+        // per warp: nearest    [lin cache: lin_words ints][chunk transmittances]
+        //           trilinear  [chunk transmittances][values: lin_words float4][corner masks: lin_words words]
         RayScratch sc;
-        sc.lc = s_dyn + wib * warp_words;
-        sc.tcs = reinterpret_cast<float*>(sc.lc + lin_words);
+        int* const base = s_dyn + wib * warp_words;
+        if (MODE == PLX_NEAREST) {
+            sc.lc = base;
+            sc.tcs = reinterpret_cast<float*>(base + lin_words);
+            sc.cv = nullptr; sc.mk = nullptr;
+        } else {
+            const int tcs_words = warp_words - 5 * lin_words;
+            sc.lc = nullptr;
+            sc.tcs = reinterpret_cast<float*>(base);
+            sc.cv = reinterpret_cast<float4*>(base + tcs_words);
+            sc.mk = reinterpret_cast<uint32_t*>(base + tcs_words + 4 * lin_words);
+        }
         Ray r;
         float4 tgt;
         setup_ray(a, ray, r, tgt);
@@ -377,7 +413,7 @@ __global__ void __launch_bounds__(128, MODE == PLX_NEAREST ? 8 : 5) k_render_tra
             dst.local = a.grad_grid; dst.peers = s_peer; dst.owner_mul = a.peer_grad.owner_mul; dst.pol = g.pol_grad;
             ray_loss = train_ray<MODE, FAST, true, SPL, PIPE, PEER>(a, g, dst, sc, r, tgt, ray, lane);
         } else {
-            ray_loss = train_ray_slow<MODE, FAST, SPL, PEER>(&a, s_peer, sc.lc, sc.tcs, ray, lane);
+            ray_loss = train_ray_slow<MODE, FAST, SPL, PEER>(&a, s_peer, sc, ray, lane);
         }
     }
     // ---- loss: shared-memory partial per block, the last warp to finish adds it to the global accumulator; that warp
@@ -395,16 +431,17 @@ __global__ void __launch_bounds__(128, MODE == PLX_NEAREST ? 8 : 5) k_render_tra
 }
 
 // shared memory the fused kernel needs per block; 0 = not launchable (fall back to K1 + K2)
-size_t render_train_smem(int num_samples, int spl, int wpb) {
+size_t render_train_smem(int num_samples, int spl, int wpb, int mode) {
     const int W = 32 * spl;
     const int n_it_max = (num_samples + W - 1) / W + 1;
-    return (size_t)wpb * ((size_t)n_it_max * W + ((n_it_max + 3) & ~3)) * sizeof(int);
+    const size_t per_sample_words = mode == PLX_TRILINEAR ? 5 : 1;       // value (4) + corner masks (1), or the cell index
+    return (size_t)wpb * ((size_t)n_it_max * W * per_sample_words + ((n_it_max + 3) & ~3)) * sizeof(int);
 }
 
 bool render_train_supported(const PlxRenderTrain& a) {
     if (a.march.mode == PLX_TRILINEAR && !fast_ok(a.march, a.grid)) return false;     // trilinear: contiguous grids only (K1 + K2 otherwise)
     if ((int64_t)a.march.nx * a.march.ny * a.march.nz >= (1ll << 31) / 4) return false;
-    return render_train_smem(a.march.num_samples, 2, 1) <= 200 * 1024;
+    return render_train_smem(a.march.num_samples, 2, 1, a.march.mode) <= 200 * 1024;
 }
 
 template <int MODE, bool FAST, int SPL, bool PIPE, bool PEER>
@@ -425,12 +462,14 @@ cudaError_t launch_render_train(const PlxRenderTrain& a_in, cudaStream_t st) {
     PlxRenderTrain a = a_in;
     a.march.flags = (a.march.flags & 0xffffu) | l2_keep_flags(a.march);
     const int spl = a.march.num_samples >= 128 ? 2 : 1;
-    int wpb = tuning().train_wpb;
-    while (wpb > 1 && render_train_smem(a.march.num_samples, spl, wpb) > 200 * 1024) wpb >>= 1;
-    const size_t smem = render_train_smem(a.march.num_samples, spl, wpb);
+    const bool tri = a.march.mode == PLX_TRILINEAR;
+    // trilinear keeps 20 B per sample in shared memory: two warps per block so that the blocks pack the SM (S = 600: 28 KB each)
+    int wpb = tri && tuning().train_wpb > 2 ? 2 : tuning().train_wpb;
+    while (wpb > 1 && render_train_smem(a.march.num_samples, spl, wpb, a.march.mode) > 200 * 1024) wpb >>= 1;
+    const size_t smem = render_train_smem(a.march.num_samples, spl, wpb, a.march.mode);
     const int W = 32 * spl;
     const int n_it_max = (a.march.num_samples + W - 1) / W + 1;
-    const int lin_words = n_it_max * W, warp_words = lin_words + ((n_it_max + 3) & ~3);
+    const int lin_words = n_it_max * W, warp_words = lin_words * (tri ? 5 : 1) + ((n_it_max + 3) & ~3);
     const unsigned blocks = (unsigned)((a.rays.n_rays + wpb - 1) / wpb);
     const bool fast = fast_ok(a.march, a.grid);
     const bool pipe = l2_keep_ok((int64_t)a.march.nx * a.march.ny * a.march.nz);

@@ -434,6 +434,7 @@ int plx_tune(const char* name, int32_t value) {
     else if (!std::strcmp(name, "adam_blocks_per_sm")) { if (value < 1 || value > 8) return fail(PLX_E_SHAPE, "adam_blocks_per_sm must be 1..8"); t.adam_blocks_per_sm = value; }
     else if (!std::strcmp(name, "train_wpb")) { if (value != 1 && value != 2 && value != 4) return fail(PLX_E_SHAPE, "train_wpb must be 1, 2 or 4"); t.train_wpb = value; }
     else if (!std::strcmp(name, "pdl")) t.pdl = value != 0;
+    else if (!std::strcmp(name, "train_cache_it")) { if (value < 0) return fail(PLX_E_SHAPE, "train_cache_it must be >= 0"); t.train_cache_it = value; }
     else if (!std::strcmp(name, "packet_tile")) t.packet_tile = value != 0;
     else return fail(PLX_E_UNSUPPORTED, "unknown tuning switch '%s'", name);
     return PLX_OK;

@@ -17,6 +17,8 @@ struct Tuning {
                                  // 256^3: 399 -> 387 us per step, 128^3 where every line changes: 89.5 -> 90.6)
     int adam_blocks_per_sm = 4;  // resident 256-thread blocks per SM of the Adam kernels
     int train_wpb = 4;           // warps per block of the fused training march
+    int train_cache_it = 0;      // trilinear fused march: iterations the per-warp value cache holds (0 = sized from the grid's diagonal;
+                                 // tests force 1 so that every ray takes the uncached path)
     int packet_tile = 1;         // ray-packet inference kernel marches 16 x 8 lattice tiles per block (0 = 128 consecutive rays)
     int pdl = 1;                 // programmatic dependent launch of the march / optimiser kernels (launch latency behind the previous kernel's tail)
 };

@@ -16,6 +16,7 @@
 //     corners (4 B) instead of a cell index; the reverse pass recomputes only the geometry (corner indices, lerp weights: no
 //     loads) and never repeats the eight gathers, the masks or the seven lerps.
 // Same exact index arithmetic as K1 (plx_march.cuh), so indices match the reference bit for bit.
+#include <cmath>
 #include <cstdlib>
 
 #include "plx_march.cuh"
@@ -69,17 +70,18 @@ struct RayScratch {
 // FR (fast ray): every coordinate of the ray is in the hoisted-division range — the common case, compiled without any
 // slow-path call in its loops; the FR = false instantiation (coordinates near the ends of the fp32 range, NaN / inf) is the
 // same code on __fdiv_rn and the float bounds test, kept out of line.
-template <int MODE, bool FAST, bool FR, int SPL, bool PIPE, bool PEER>
+// CACHE (trilinear only): the ray's iterations fit the per-warp value / mask cache; a ray that needs more (the cache is sized for
+// unit-length directions through the grid's diagonal, launch_render_train) runs with CACHE = false and recomputes the
+// interpolation in its reverse pass, as every trilinear ray did before the cache existed.
+template <int MODE, bool FAST, bool FR, int SPL, bool PIPE, bool PEER, bool CACHE>
 __device__ __forceinline__ float train_ray(const PlxRenderTrain& a, const Geo& g, const GradDst<PEER>& dst, const RayScratch& sc,
-                                           const Ray& r, const float4 tgt, const int64_t ray, const int lane) {
+                                           const Ray& r, const float4 tgt, const int64_t ray, const int lane, const int k0, const int k1) {
     constexpr int W = 32 * SPL;
     const PlxMarch& m = a.march;
     int* lc = sc.lc;
     float* tcs = sc.tcs;
     const float bom = a.beta_over_m;
     const bool full = bom != 0.f;        // the sparsity term touches every in-bounds sample: no early stop
-    int k0, k1;
-    clip_range(m, r, k0, k1);
     const int n_it = k0 <= k1 ? (k1 - k0) / W + 1 : 0;
 
     // ---------------------------------------------------------------------------------------- forward
@@ -128,7 +130,7 @@ __device__ __forceinline__ float train_ray(const PlxRenderTrain& a, const Geo& g
         if (MODE == PLX_NEAREST) {
             if (SPL == 1) lc[it * W + lane] = lin[0];
             else *reinterpret_cast<int2*>(lc + it * W + lane * 2) = make_int2(lin[0], lin[SPL - 1]);
-        } else {
+        } else if (CACHE) {
 #pragma unroll
             for (int j = 0; j < SPL; ++j) sc.cv[it * W + lane * SPL + j] = c[j];
             if (SPL == 1) sc.mk[it * W + lane] = maskn[0];
@@ -193,6 +195,7 @@ __device__ __forceinline__ float train_ray(const PlxRenderTrain& a, const Geo& g
     float carry = 0.f;                   // S behind the last visited sample (0: end of ray, or irrelevant behind k*)
     __syncwarp();
     auto refetch = [&](int i) {          // indices back from shared memory, cells requested (L1 / L2 hits mostly)
+        if (MODE == PLX_TRILINEAR && !CACHE) { fetch(i); return; }       // geometry + gathers + interpolation all over again
         if (MODE == PLX_TRILINEAR) {         // geometry recomputed (no loads), value and corner masks back from shared memory
             const int kb = k0 + i * W + lane * SPL;
 #pragma unroll
@@ -356,8 +359,8 @@ __device__ __forceinline__ void setup_ray(const PlxRenderTrain& a, int64_t ray, 
     }
 }
 
-// the rare ray outside the hoisted-division range (coordinates near the ends of the fp32 range, NaN / inf): the same march on
-// the IEEE division and the float bounds test.  Out of line and self-contained (it rebuilds the ray and the geometry from the
+// the rare ray outside the hoisted-division range (coordinates near the ends of the fp32 range, NaN / inf), or (trilinear) longer
+// than the per-warp cache: the same march on the IEEE division and the float bounds test, without the value cache.  Out of line and self-contained (it rebuilds the ray and the geometry from the
 // kernel argument), so the common path pays neither instructions nor registers nor stack traffic for it.
 template <int MODE, bool FAST, int SPL, bool PEER>
 __device__ __noinline__ float train_ray_slow(const PlxRenderTrain* ap, float* const* peers, const RayScratch sc, int64_t ray, int lane) {
@@ -368,11 +371,13 @@ __device__ __noinline__ float train_ray_slow(const PlxRenderTrain* ap, float* co
     Ray r;
     float4 tgt;
     setup_ray(a, ray, r, tgt);
-    return train_ray<MODE, FAST, false, SPL, false, PEER>(a, g, dst, sc, r, tgt, ray, lane);
+    int k0, k1;
+    clip_range(a.march, r, k0, k1);
+    return train_ray<MODE, FAST, false, SPL, false, PEER, false>(a, g, dst, sc, r, tgt, ray, lane, k0, k1);
 }
 
 template <int MODE, bool FAST, int SPL, bool PIPE, bool PEER>
-__global__ void __launch_bounds__(MODE == PLX_NEAREST ? 128 : 64, MODE == PLX_NEAREST ? 8 : 7) k_render_train(const __grid_constant__ PlxRenderTrain a, int lin_words, int warp_words) {
+__global__ void __launch_bounds__(MODE == PLX_NEAREST ? 128 : 64, 8) k_render_train(const __grid_constant__ PlxRenderTrain a, int lin_words, int warp_words) {
     extern __shared__ __align__(16) int s_dyn[];   // per warp (warp_words ints, 16-byte multiple): lin cache [lin_words], then chunk transmittances
     __shared__ float s_loss;
     __shared__ int s_done;
@@ -397,7 +402,7 @@ __global__ void __launch_bounds__(MODE == PLX_NEAREST ? 128 : 64, MODE == PLX_NE
             sc.lc = base;
             sc.tcs = reinterpret_cast<float*>(base + lin_words);
             sc.cv = nullptr; sc.mk = nullptr;
-        } else {
+        } else {                             // lin_words = cache capacity in samples (may be less than the ray can visit, see `fits`)
             const int tcs_words = warp_words - 5 * lin_words;
             sc.lc = nullptr;
             sc.tcs = reinterpret_cast<float*>(base);
@@ -407,11 +412,15 @@ __global__ void __launch_bounds__(MODE == PLX_NEAREST ? 128 : 64, MODE == PLX_NE
         Ray r;
         float4 tgt;
         setup_ray(a, ray, r, tgt);
-        if (FAST && ray_in_fast_range(m, r)) {
+        int k0, k1;
+        clip_range(m, r, k0, k1);
+        // trilinear: lin_words = the samples the per-warp cache holds
+        const bool fits = MODE == PLX_NEAREST || k0 > k1 || ((k1 - k0) / (32 * SPL) + 1) * (32 * SPL) <= lin_words;
+        if (FAST && fits && ray_in_fast_range(m, r)) {
             const Geo g = make_geo(m);
             GradDst<PEER> dst;
             dst.local = a.grad_grid; dst.peers = s_peer; dst.owner_mul = a.peer_grad.owner_mul; dst.pol = g.pol_grad;
-            ray_loss = train_ray<MODE, FAST, true, SPL, PIPE, PEER>(a, g, dst, sc, r, tgt, ray, lane);
+            ray_loss = train_ray<MODE, FAST, true, SPL, PIPE, PEER, true>(a, g, dst, sc, r, tgt, ray, lane, k0, k1);
         } else {
             ray_loss = train_ray_slow<MODE, FAST, SPL, PEER>(&a, s_peer, sc, ray, lane);
         }
@@ -431,17 +440,35 @@ __global__ void __launch_bounds__(MODE == PLX_NEAREST ? 128 : 64, MODE == PLX_NE
 }
 
 // shared memory the fused kernel needs per block; 0 = not launchable (fall back to K1 + K2)
-size_t render_train_smem(int num_samples, int spl, int wpb, int mode) {
+// iterations of 32 * spl samples a ray can visit: all S of them, or (cache_it: the trilinear value cache) what a UNIT-length
+// direction can spend inside the grid grown by the clip margins — the grid's diagonal; longer rays take the uncached path
+static int train_iterations(const PlxMarch& m, int spl, bool cache_it) {
     const int W = 32 * spl;
-    const int n_it_max = (num_samples + W - 1) / W + 1;
-    const size_t per_sample_words = mode == PLX_TRILINEAR ? 5 : 1;       // value (4) + corner masks (1), or the cell index
-    return (size_t)wpb * ((size_t)n_it_max * W * per_sample_words + ((n_it_max + 3) & ~3)) * sizeof(int);
+    int n_it = (m.num_samples + W - 1) / W + 1;
+    if (cache_it && m.delta_step > 0.f && m.points_distance > 0.f) {
+        if (tuning().train_cache_it > 0) return tuning().train_cache_it < n_it ? tuning().train_cache_it : n_it;
+        const double pd = m.points_distance;
+        double d2 = 0.0;
+        for (int n : {m.nx, m.ny, m.nz}) { const double e = pd * (n + 8); d2 += e * e; }       // 4 cells of margin per side (clip_range: < 3)
+        const double samples = std::sqrt(d2) / m.delta_step + 8.0;
+        if (samples < 1e9) { const int fit = (int)std::ceil(samples / W) + 1; if (fit < n_it) n_it = fit; }
+    }
+    return n_it;
+}
+
+size_t render_train_smem(const PlxMarch& m, int spl, int wpb) {
+    const int W = 32 * spl;
+    const bool tri = m.mode == PLX_TRILINEAR;
+    const int n_it_max = train_iterations(m, spl, false);
+    const size_t sample_words = tri ? (size_t)train_iterations(m, spl, true) * W * 5      // value (4) + corner masks (1) per cached sample
+                                    : (size_t)n_it_max * W;                               // the cell index of every sample
+    return (size_t)wpb * (sample_words + ((n_it_max + 3) & ~3)) * sizeof(int);
 }
 
 bool render_train_supported(const PlxRenderTrain& a) {
     if (a.march.mode == PLX_TRILINEAR && !fast_ok(a.march, a.grid)) return false;     // trilinear: contiguous grids only (K1 + K2 otherwise)
     if ((int64_t)a.march.nx * a.march.ny * a.march.nz >= (1ll << 31) / 4) return false;
-    return render_train_smem(a.march.num_samples, 2, 1, a.march.mode) <= 200 * 1024;
+    return render_train_smem(a.march, 2, 1) <= 200 * 1024;
 }
 
 template <int MODE, bool FAST, int SPL, bool PIPE, bool PEER>
@@ -456,20 +483,22 @@ static cudaError_t launch_train_inst(const PlxRenderTrain& a, unsigned blocks, i
 
 // Launch shape (measured on C2 / B200): 4 warps per block, 8 blocks per SM (64 registers), 2 samples per lane
 // from 128 samples per ray up; software-pipelined gathers when grid + gradient fit the L2 (+5 % on C2) and off on grids far
-// beyond it, where the extra requests in flight only add DRAM queueing (-8 % on the 256^3 sweep).
+// beyond it, where the extra requests in flight only add DRAM queueing (-8 % on the 256^3 sweep).  Trilinear: 2 warps per
+// block, 8 blocks per SM at 120 registers (9 blocks at 96 registers spill: 242 vs 217 us per C2 step), the value cache sized
+// from the grid's diagonal instead of S (C2: 9 instead of 11 iterations = 16 instead of 14 resident warps: 237 -> 217 us).
 cudaError_t launch_render_train(const PlxRenderTrain& a_in, cudaStream_t st) {
     if (a_in.rays.n_rays == 0) return cudaSuccess;
     PlxRenderTrain a = a_in;
     a.march.flags = (a.march.flags & 0xffffu) | l2_keep_flags(a.march);
     const int spl = a.march.num_samples >= 128 ? 2 : 1;
     const bool tri = a.march.mode == PLX_TRILINEAR;
-    // trilinear keeps 20 B per sample in shared memory: two warps per block so that the blocks pack the SM (S = 600: 28 KB each)
+    // trilinear keeps 20 B per cached sample in shared memory: two warps per block so that the blocks pack the SM (C2: 23 KB each)
     int wpb = tri && tuning().train_wpb > 2 ? 2 : tuning().train_wpb;
-    while (wpb > 1 && render_train_smem(a.march.num_samples, spl, wpb, a.march.mode) > 200 * 1024) wpb >>= 1;
-    const size_t smem = render_train_smem(a.march.num_samples, spl, wpb, a.march.mode);
+    while (wpb > 1 && render_train_smem(a.march, spl, wpb) > 200 * 1024) wpb >>= 1;
+    const size_t smem = render_train_smem(a.march, spl, wpb);
     const int W = 32 * spl;
-    const int n_it_max = (a.march.num_samples + W - 1) / W + 1;
-    const int lin_words = n_it_max * W, warp_words = lin_words * (tri ? 5 : 1) + ((n_it_max + 3) & ~3);
+    const int n_it_max = train_iterations(a.march, spl, false);
+    const int lin_words = train_iterations(a.march, spl, tri) * W, warp_words = lin_words * (tri ? 5 : 1) + ((n_it_max + 3) & ~3);
     const unsigned blocks = (unsigned)((a.rays.n_rays + wpb - 1) / wpb);
     const bool fast = fast_ok(a.march, a.grid);
     const bool pipe = l2_keep_ok((int64_t)a.march.nx * a.march.ny * a.march.nz);

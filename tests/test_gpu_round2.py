@@ -75,6 +75,41 @@ def test_trilinear_training_at_config2_size_matches_the_c_oracle(plx_lib):
     assert rel_err(gg.cpu().numpy(), grad_o) <= TOL
 
 
+@pytest.mark.parametrize("scale", [1.0, 0.25])
+def test_trilinear_rays_longer_than_the_value_cache_take_the_uncached_path(plx_lib, scale):
+    """The fused trilinear march caches interpolated values per ray in shared memory, sized for unit directions through the
+    grid's diagonal; a ray that visits more samples (here: directions scaled to a quarter length, and the cache forced down to
+    one iteration with plx_tune) must run the uncached path and produce the same pixels, loss and gradient."""
+    G, S = 24, 192
+    cs = Case(G, 2, 8, 40, S, 6.0 / S, "ball")
+    d = cs.cuda()
+    dirs, targets = ops.generate_rays(d["imgs"], d["poses"], cs.fov, uv=d["uv"])
+    o = d["poses"][:, :3, 3].repeat_interleave(cs.R, 0).contiguous()
+    dirs = (dirs * scale).contiguous()
+    delta = cs.delta / scale                  # same world-space sample spacing: same pixels as the unit-length rays when scale = 1
+    lib = L.load()
+    out = {}
+    try:
+        for cap in (0, 1):
+            L.check(lib.plx_tune(b"train_cache_it", cap))
+            gg = torch.zeros_like(d["grid"])
+            rgba, loss = ops.render_train(d["grid"], gg, S, delta if scale != 1.0 else cs.delta, cs.gmin, cs.pd, origins=o, dirs=dirs,
+                                          targets=targets, rays_per_origin=1, mode="trilinear")
+            out[cap] = (rgba, float(loss), gg)
+    finally:
+        L.check(lib.plx_tune(b"train_cache_it", 0))
+    assert float(out[0][2].abs().sum()) > 0
+    assert torch.equal(out[0][0], out[1][0])
+    assert abs(out[0][1] - out[1][1]) <= 1e-6 * out[0][1]          # summed with atomics: order differs from launch to launch
+    assert rel_err(out[1][2].cpu().numpy(), out[0][2].cpu().numpy()) <= 1e-6
+    # and both equal the separate forward + backward kernels
+    grid = d["grid"].clone().requires_grad_(True)
+    px = ops.render_rays(grid, o, dirs, S, delta if scale != 1.0 else cs.delta, cs.gmin, cs.pd, mode="trilinear", rays_per_origin=1)
+    ((px - targets) ** 2).mean().backward()
+    assert rel_err(out[0][0].cpu().numpy(), px.detach().cpu().numpy()) <= TOL
+    assert rel_err(out[0][2].cpu().numpy(), grid.grad.cpu().numpy()) <= TOL
+
+
 @pytest.mark.parametrize("mode,S,world", [("nearest", 200, 2), ("nearest", 64, 3), ("nearest", 600, 8), ("trilinear", 96, 4)])
 def test_push_exchange_march_sends_every_cell_to_its_slab_owner(plx_lib, mode, S, world):
     """PlxPeerGrad on ONE device: `world` gradient buffers stand in for the ranks' peer-mapped ones.  Every buffer may only

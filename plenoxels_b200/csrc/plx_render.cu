@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) k_render_fwd(const P
 // 16 x 8 TILE of it (2 x 2 warps of 8 x 4 rays) instead of 128 consecutive rays of one lattice row: the cells a warp touches at
 // equal depth then form a compact patch (fewer sectors per load, L1 lines shared by the warps of the block and by consecutive
 // samples).  Which thread marches a ray does not change the ray's result.  Measured on C4 (512^3, 800 x 800 view, B200):
-// rows 0.77 ms -> tiles 0.62 ms per frame at 64 resident warps / SM; 4 x 8 and 16 x 2 warp tiles were within 2 % of 8 x 4.
+// rows 0.77 ms -> tiles 0.62 ms per frame at 64 resident warps / SM (0.61 with one lookup per loop trip); 4 x 8 and 16 x 2 warp
+// tiles were within 2 % of 8 x 4.
 template <int MODE, bool FAST, int UNR, int MINB = 1>
 __global__ void __launch_bounds__(128, MINB) k_render_fwd_packet(const PlxRenderFwd a, const int side, const int tiles_v, const int tiles_per_view) {
     int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -330,11 +331,12 @@ cudaError_t launch_render_fwd(const PlxRenderFwd& a_in, cudaStream_t st) {
             }
         }
         // The kernel is gather-latency bound on a grid far beyond the L2 (C4: long_scoreboard 12 stalled warps per issue), so
-        // resident warps beat samples in flight per thread: nearest = 2 lookups before compositing at 32 registers (64 warps / SM),
+        // resident warps beat samples in flight per thread: nearest = 1 lookup per loop trip at 32 registers (64 warps / SM),
         // trilinear (8 corners per sample) = 1 at 48 registers.  Sweep on C4, ms per frame: nearest (4 lookups, 54 registers) 0.94,
-        // (4, 40 r) 0.70, (3, 32 r) 0.66, (2, 32 r) 0.62; trilinear (1, 68 r) 2.18, (1, 48 r) 2.06, (1, 40 r) 2.38, (2, 64 r) 2.12.
+        // (4, 40 r) 0.70, (3, 32 r) 0.66, (2, 40 r) 0.67, (2, 32 r) 0.62, (1, 32 r) 0.61; trilinear (1, 68 r) 2.18, (1, 48 r) 2.06,
+        // (1, 40 r) 2.38, (2, 64 r) 2.12.
 #define PLX_PACKET(...) k_render_fwd_packet<__VA_ARGS__><<<pblocks, 128, 0, st>>>(a, side, tiles_v, tiles_per_view)
-        if (a.march.mode == PLX_NEAREST) { if (fast) PLX_PACKET(PLX_NEAREST, true, 2, 16); else PLX_PACKET(PLX_NEAREST, false, 4); }
+        if (a.march.mode == PLX_NEAREST) { if (fast) PLX_PACKET(PLX_NEAREST, true, 1, 16); else PLX_PACKET(PLX_NEAREST, false, 4); }
         else                             { if (fast) PLX_PACKET(PLX_TRILINEAR, true, 1, 10); else PLX_PACKET(PLX_TRILINEAR, false, 1); }
 #undef PLX_PACKET
         return cudaGetLastError();

@@ -109,6 +109,32 @@ def test_argument_errors_are_reported_not_thrown(plx_lib):
     assert plx_lib.plx_generate_rays(None, 1, 4, 4, None, 0.5, None, 4, 2, None, None, None) == -1
 
 
+def test_tuning_switches_are_the_documented_ones(plx_lib):
+    """plx_tune (A/B switches for tools and tests; host-side state only, no launch): every switch DESIGN.md 9 lists exists and
+    takes its default back, an unknown name or an out-of-range value is an error code, never an exception."""
+    documented = {"adam_skip_same": -1, "adam_blocks_per_sm": 4, "train_wpb": 4, "train_cache_it": 0, "pdl": 1, "packet_tile": 1}
+    design = open(os.path.join(REPO, "DESIGN.md")).read()
+    for name, default in documented.items():
+        assert f"`{name}`" in design, f"{name} is not documented in DESIGN.md"
+        assert plx_lib.plx_tune(name.encode(), default) == 0, plx_lib.plx_last_error()
+    assert plx_lib.plx_tune(b"no_such_switch", 1) == -3 and b"no_such_switch" in plx_lib.plx_last_error()     # PLX_E_UNSUPPORTED
+    assert plx_lib.plx_tune(b"adam_blocks_per_sm", 99) == -2 and plx_lib.plx_tune(b"train_wpb", 3) == -2        # PLX_E_SHAPE
+    assert plx_lib.plx_tune(None, 1) == -1
+    # the A/B library override is honoured by the loader and by nothing else
+    src = open(os.path.join(REPO, "plenoxels_b200", "_lib.py")).read()
+    assert src.count("PLX_AB_LIBRARY") == 2
+
+
+def test_tools_are_importable_python():
+    """tools/*.py are measurement drivers that only run on a GPU box; at least they must stay valid Python."""
+    import py_compile
+    tools = os.path.join(REPO, "tools")
+    files = sorted(f for f in os.listdir(tools) if f.endswith(".py"))
+    assert files
+    for f in files:
+        py_compile.compile(os.path.join(tools, f), doraise=True)
+
+
 @pytest.mark.parametrize("G,pd", [(64, 0.05), (128, 0.025), (256, 0.0125), (93, 0.0125), (7, 0.3)])
 def test_grid_origin_matches_oracle(G, pd):
     assert np.array_equal(np.float32(ops.grid_origin((G, G, G), pd)), po.grid_origin((G, G, G), pd))

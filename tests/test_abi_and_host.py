@@ -168,6 +168,16 @@ def test_product_package_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
 
 
+def test_exchange_choice_follows_the_batch_density():
+    """pick_exchange (trainer.py): the BASELINE configs take the push exchange (C2: ~1.8 in-bounds samples per cell, C3: 0.03);
+    only a batch with many more samples than ~8 per cell falls back to the dense pull exchange."""
+    from plenoxels_b200.trainer import pick_exchange
+    assert pick_exchange(12800, 600, 128 ** 3) == "push"
+    assert pick_exchange(4096, 256, 256 ** 3) == "push"
+    assert pick_exchange(1 << 20, 512, 64 ** 3) == "pull"
+    assert pick_exchange(0, 600, 128 ** 3) == "push"
+
+
 @pytest.mark.parametrize("n,world", [(100, 1), (100, 2), (100, 8), (7, 4), (3, 8)])
 def test_shard_cameras_partitions(n, world):
     seen = []
